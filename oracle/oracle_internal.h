@@ -1,0 +1,122 @@
+// oracle_internal.h — shared internals of the CPU oracle (TEST INFRASTRUCTURE, see oracle.h).
+#pragma once
+#include "oracle.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace orc {
+
+struct f3 {
+    float x, y, z;
+    float &operator[](int i) { return (&x)[i]; }
+    float operator[](int i) const { return (&x)[i]; }
+};
+static inline f3 mk(float x, float y, float z) { return f3{x, y, z}; }
+static inline f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline f3 operator*(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline f3 operator*(f3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+static inline f3 operator*(float s, f3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+static inline f3 operator/(f3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+static inline f3 operator/(f3 a, f3 b) { return mk(a.x / b.x, a.y / b.y, a.z / b.z); }
+static inline f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
+// HLSL min/max return the non-NaN operand; fminf/fmaxf have the same rule.
+static inline f3 vmin(f3 a, f3 b) { return mk(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+static inline f3 vmax(f3 a, f3 b) { return mk(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+static inline f3 vabs(f3 a) { return mk(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+// dot(): left-to-right mul/add, never fused (the library is built with -ffp-contract=off).
+static inline float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+static inline f3 cross(f3 a, f3 b) {
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+static inline float length(f3 a) { return sqrtf(dot(a, a)); }
+// HLSL normalize(v) = v * rsqrt(dot(v,v)); restated with IEEE sqrt + divide (DESIGN.md "Float semantics").
+static inline f3 normalize(f3 a) {
+    float inv = 1.0f / sqrtf(dot(a, a));
+    return a * inv;
+}
+static inline float saturate(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// 3x4 affine transform applied to a point (w=1) or a vector (w=0): mul(M, float4(v,w)).
+// Pinned evaluation order: ((m0*x + m1*y) + m2*z) + m3*w.
+static inline f3 xform_point(const float m[12], f3 v) {
+    return mk(((m[0] * v.x + m[1] * v.y) + m[2] * v.z) + m[3], ((m[4] * v.x + m[5] * v.y) + m[6] * v.z) + m[7],
+              ((m[8] * v.x + m[9] * v.y) + m[10] * v.z) + m[11]);
+}
+static inline f3 xform_vector(const float m[12], f3 v) {
+    return mk((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z,
+              (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
+}
+
+struct Box {
+    f3 center, half;
+};
+struct Aabb {
+    f3 mn, mx;
+};
+
+// FL/RayTracingHelper.hlsli:251-265
+static inline Box aabb_to_box(Aabb a) {
+    Box b;
+    b.center = (a.mn + a.mx) * 0.5f;
+    b.half = a.mx - b.center;
+    return b;
+}
+static inline Aabb box_to_aabb(Box b) { return Aabb{b.center - b.half, b.center + b.half}; }
+
+void invert_affine(const float t[12], float out[12]);
+Aabb transform_aabb(Aabb box, const float m[12]);
+
+}  // namespace orc
+
+struct orc_blas {
+    uint32_t n = 0;
+    std::vector<rt_primitive> prims;        // load order
+    std::vector<rt_primitive_meta> meta;    // load order
+    float aabb[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> morton, sorted_morton, perm;
+    std::vector<rt_hierarchy_node> hier;
+    std::vector<uint8_t> blob;
+    // convenience views into blob
+    const rt_aabb_node *nodes() const { return reinterpret_cast<const rt_aabb_node *>(blob.data() + 16); }
+    const rt_primitive *sorted_prims() const {
+        return reinterpret_cast<const rt_primitive *>(blob.data() + reinterpret_cast<const rt_bvh_offsets *>(blob.data())->offsetToVertices);
+    }
+    const rt_primitive_meta *sorted_meta() const {
+        return reinterpret_cast<const rt_primitive_meta *>(blob.data() + reinterpret_cast<const rt_bvh_offsets *>(blob.data())->offsetToPrimitiveMetaData);
+    }
+};
+
+struct orc_tlas {
+    uint32_t n = 0;
+    std::vector<uint32_t> morton, sorted_morton, perm;
+    std::vector<rt_hierarchy_node> hier;
+    std::vector<uint8_t> blob;
+    const rt_aabb_node *nodes() const { return reinterpret_cast<const rt_aabb_node *>(blob.data() + 16); }
+    const rt_bvh_metadata *metadata() const {
+        return reinterpret_cast<const rt_bvh_metadata *>(blob.data() + reinterpret_cast<const rt_bvh_offsets *>(blob.data())->offsetToVertices);
+    }
+};
+
+namespace orc {
+
+struct HitInfo {
+    bool hit = false;
+    float t = 0;
+    float bary[2] = {0, 0};
+    uint32_t primitiveIndex = RT_NO_HIT, instanceIndex = 0, geometryIndex = 0, instanceId = 0, leafSlot = 0;
+    uint32_t hitGroupContribution = 0;  // instanceContribution + rayContribution + geom*multiplier
+};
+
+struct TraceCounters {
+    uint64_t internal = 0, leaf = 0, inst = 0, max_stack = 0;
+};
+
+// Fallback_TraceRay without the shader call-out: FL/TraverseShader.hlsli:21-73.
+HitInfo trace_ray(const orc_tlas *t, f3 origin, float tmin, f3 dir, float tmax, uint32_t rayFlags, uint32_t mask,
+                  uint32_t rayContribution, uint32_t geomMultiplier, TraceCounters *ctr);
+
+}  // namespace orc

@@ -1,0 +1,262 @@
+// oracle_trace.cpp — CPU restatement of the Fallback Layer's two-level BVH2 traversal.
+// TEST INFRASTRUCTURE (see oracle.h).  Follows FL/TraverseFunction.hlsli:173-282,438-460,520-799
+// and FL/TraverseShader.hlsli:21-73 ("FL/" = externals/D3D12RaytracingFallback/src/).
+#include <atomic>
+#include <thread>
+
+#include "oracle_internal.h"
+
+namespace orc {
+
+struct RayData {  // FL/TraverseFunction.hlsli:429-460
+    f3 invDir, originTimesInvDir, shear;
+    int kx, ky, kz;
+};
+
+static RayData get_ray_data(f3 o, f3 d) {
+    RayData r;
+    r.invDir = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // rcp()
+    r.originTimesInvDir = o * r.invDir;
+    f3 a = vabs(d);
+    int z = (a.x > a.y && a.x > a.z) ? 0 : (a.y > a.z ? 1 : 2);  // GetIndexOfBiggestChannel
+    r.kx = (z + 1) % 3;
+    r.ky = (z + 2) % 3;
+    r.kz = z;
+    if (d[r.kz] < 0.0f) std::swap(r.kx, r.ky);
+    r.shear = mk(d[r.kx] / d[r.kz], d[r.ky] / d[r.kz], 1.0f / d[r.kz]);
+    return r;
+}
+
+// RayBoxTest: FL/TraverseFunction.hlsli:173-191
+static bool ray_box(float &resultT, float closestT, const RayData &rd, const rt_aabb_node &n) {
+    f3 c = mk(n.center[0], n.center[1], n.center[2]), h = mk(n.halfDim[0], n.halfDim[1], n.halfDim[2]);
+    f3 rel = c * rd.invDir - rd.originTimesInvDir;
+    f3 ha = h * vabs(rd.invDir);
+    f3 maxL = rel + ha, minL = rel - ha;
+    float minT = fmaxf(fmaxf(minL.x, minL.y), minL.z);
+    float maxT = fminf(fminf(maxL.x, maxL.y), maxL.z);
+    resultT = fmaxf(minT, 0.0f);
+    return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
+}
+
+// RayTriangleIntersect: FL/TraverseFunction.hlsli:200-282 (Woop/Benthin/Wald 2013).
+// Returns true and updates hitT/bary only on acceptance; U,V,W are "precise" (unfused).
+static bool ray_triangle(float &hitT, float bary[2], uint32_t instanceFlags, uint32_t rayFlags, f3 o, const RayData &rd,
+                         f3 v0, f3 v1, f3 v2) {
+    bool useCulling = !(instanceFlags & RT_INSTANCE_FLAG_TRIANGLE_CULL_DISABLE);
+    bool flipFaces = (instanceFlags & RT_INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE) != 0;
+    uint32_t backFlag = flipFaces ? RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES : RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES;
+    uint32_t frontFlag = flipFaces ? RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES : RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES;
+    bool cullBack = useCulling && (rayFlags & backFlag);
+    bool cullFront = useCulling && (rayFlags & frontFlag);
+
+    f3 a0 = v0 - o, b0 = v1 - o, c0 = v2 - o;
+    float Ax = a0[rd.kx], Ay = a0[rd.ky], Az = a0[rd.kz];
+    float Bx = b0[rd.kx], By = b0[rd.ky], Bz = b0[rd.kz];
+    float Cx = c0[rd.kx], Cy = c0[rd.ky], Cz = c0[rd.kz];
+    Ax = Ax - rd.shear.x * Az, Ay = Ay - rd.shear.y * Az;
+    Bx = Bx - rd.shear.x * Bz, By = By - rd.shear.y * Bz;
+    Cx = Cx - rd.shear.x * Cz, Cy = Cy - rd.shear.y * Cz;
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
+    float det = (U + V) + W;
+    if (cullFront) {
+        if (U > 0.0f || V > 0.0f || W > 0.0f) return false;
+    } else if (cullBack) {
+        if (U < 0.0f || V < 0.0f || W < 0.0f) return false;
+    } else {
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    }
+    if (det == 0.0f) return false;
+    Az = rd.shear.z * Az;
+    Bz = rd.shear.z * Bz;
+    Cz = rd.shear.z * Cz;
+    const float T = (U * Az + V * Bz) + W * Cz;
+    if (cullFront) {
+        if (T > 0.0f || T < hitT * det) return false;
+    } else if (cullBack) {
+        if (T < 0.0f || T > hitT * det) return false;
+    } else {
+        float s = fabsf(T);
+        if ((T > 0.0f) != (det > 0.0f)) s = -s;
+        if (s < 0.0f || s > hitT * fabsf(det)) return false;
+    }
+    const float rcpDet = 1.0f / det;
+    bary[0] = V * rcpDet;
+    bary[1] = W * rcpDet;
+    hitT = T * rcpDet;
+    return true;
+}
+
+HitInfo trace_ray(const orc_tlas *tl, f3 origin, float tmin, f3 dir, float tmax, uint32_t rayFlags, uint32_t mask,
+                  uint32_t rayContribution, uint32_t geomMultiplier, TraceCounters *ctr) {
+    HitInfo hit;
+    float tCurrent = tmax;  // Fallback_TraceRayBegin: RayTCurrent() = TMax
+    if (tl->n == 0) return hit;
+
+    // The reference stack holds TRAVERSAL_MAX_STACK_DEPTH = 32 entries and overflows silently
+    // (FL/TraverseFunction.hlsli:15-16).  The oracle uses a growable stack and records the depth.
+    std::vector<uint32_t> stack;
+    stack.reserve(64);
+    const rt_aabb_node *tnodes = tl->nodes();
+    const rt_bvh_metadata *tmeta = tl->metadata();
+
+    RayData world = get_ray_data(origin, dir);
+    RayData cur = world;
+    f3 curOrigin = origin;
+    bool bottom = false;
+    uint32_t nodesToProcess[2] = {0, 0};
+    const rt_aabb_node *nodes = tnodes;
+    const orc_blas *blas = nullptr;
+    uint32_t instanceIndex = 0, instanceFlags = 0, instanceOffset = 0, instanceId = 0;
+    bool endSearch = false;
+
+    float unusedT;
+    if (ray_box(unusedT, tCurrent, world, tnodes[0])) {
+        stack.push_back(0);
+        nodesToProcess[0]++;
+    }
+    while (nodesToProcess[0] != 0) {
+        do {
+            uint32_t nodeIndex = stack.back();
+            stack.pop_back();
+            nodesToProcess[bottom]--;
+            const rt_aabb_node &node = nodes[nodeIndex];
+            if (node.flags & RT_NODE_LEAF_FLAG) {
+                uint32_t leafIndex = node.flags & ~(RT_NODE_LEAF_FLAG | RT_NODE_PROCEDURAL_FLAG);
+                if (!bottom) {
+                    if (ctr) ctr->inst++;
+                    const rt_bvh_metadata &md = tmeta[leafIndex];
+                    instanceIndex = md.instanceIndex;
+                    instanceOffset = RT_INSTANCE_HIT_GROUP(md.instanceDesc);
+                    instanceId = RT_INSTANCE_ID(md.instanceDesc);
+                    if (RT_INSTANCE_MASK(md.instanceDesc) & mask) {
+                        bottom = true;
+                        stack.push_back(0);
+                        blas = reinterpret_cast<const orc_blas *>(uintptr_t(md.instanceDesc.blas));
+                        nodes = blas->nodes();
+                        instanceFlags = RT_INSTANCE_FLAGS(md.instanceDesc);
+                        curOrigin = xform_point(md.instanceDesc.transform, origin);
+                        f3 objDir = xform_vector(md.instanceDesc.transform, dir);
+                        cur = get_ray_data(curOrigin, objDir);
+                        nodesToProcess[1] = 1;
+                    }
+                } else {
+                    if (ctr) ctr->leaf++;
+                    const rt_primitive_meta &pm = blas->sorted_meta()[leafIndex];
+                    bool geomOpaque = (pm.geometryFlags & RT_GEOMETRY_FLAG_OPAQUE) != 0;
+                    bool opaque = geomOpaque;  // IsOpaque(): FL/TraverseFunction.hlsli:119-134
+                    if (instanceFlags & RT_INSTANCE_FLAG_FORCE_OPAQUE) opaque = true;
+                    else if (instanceFlags & RT_INSTANCE_FLAG_FORCE_NON_OPAQUE) opaque = false;
+                    if (rayFlags & RT_RAY_FLAG_FORCE_OPAQUE) opaque = true;
+                    else if (rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
+                    bool culled = (opaque && (rayFlags & RT_RAY_FLAG_CULL_OPAQUE)) || (!opaque && (rayFlags & RT_RAY_FLAG_CULL_NON_OPAQUE));
+                    if (!culled) {
+                        const float *v = blas->sorted_prims()[leafIndex].v;
+                        float t0 = tCurrent, bary[2];
+                        bool ok = ray_triangle(t0, bary, instanceFlags, rayFlags, curOrigin, cur, mk(v[0], v[1], v[2]),
+                                               mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]));
+                        // TestLeafNodeIntersections :385
+                        if (ok && t0 < tCurrent && t0 > tmin) {
+                            // The app registers a no-op any-hit shader only for the shadow hit group and all
+                            // geometry is OPAQUE (libs/DXRFramework/Helpers/BottomLevelASGenerator.cpp:109-110);
+                            // a non-opaque hit with a no-op any-hit shader is accepted as well, so commit.
+                            tCurrent = t0;
+                            hit.hit = true;
+                            hit.t = t0;
+                            hit.bary[0] = bary[0], hit.bary[1] = bary[1];
+                            hit.primitiveIndex = pm.primitiveIndex;
+                            hit.geometryIndex = pm.geometryContributionToHitGroupIndex;
+                            hit.instanceIndex = instanceIndex;
+                            hit.instanceId = instanceId;
+                            hit.leafSlot = leafIndex;
+                            hit.hitGroupContribution = rayContribution + pm.geometryContributionToHitGroupIndex * geomMultiplier + instanceOffset;
+                            if (rayFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) endSearch = true;
+                        }
+                    }
+                    if (endSearch) {
+                        nodesToProcess[1] = 0;
+                        nodesToProcess[0] = 0;
+                    }
+                }
+            } else {
+                if (ctr) ctr->internal++;
+                uint32_t l = node.flags & 0x00ffffffu, r = node.right;
+                float lt, rt;
+                bool lh = ray_box(lt, tCurrent, cur, nodes[l]);
+                bool rh = ray_box(rt, tCurrent, cur, nodes[r]);
+                if (lh && rh) {
+                    bool rightFirst = rt < lt;  // ties: left first (:776-778)
+                    // StackPush2(selector, A=left, B=right): store0 = selector ? A : B; popped last-in first
+                    stack.push_back(rightFirst ? l : r);
+                    stack.push_back(rightFirst ? r : l);
+                    nodesToProcess[bottom] += 2;
+                } else if (lh || rh) {
+                    stack.push_back(rh ? r : l);
+                    nodesToProcess[bottom] += 1;
+                }
+            }
+            if (ctr && stack.size() > ctr->max_stack) ctr->max_stack = stack.size();
+        } while (nodesToProcess[bottom] != 0);
+        bottom = false;
+        cur = world;
+        curOrigin = origin;
+        nodes = tnodes;
+    }
+    return hit;
+}
+
+}  // namespace orc
+
+using namespace orc;
+
+template <class F>
+static void parallel_for(uint64_t n, int threads, F f) {
+    if (threads <= 1 || n < 2) {
+        f(0, n, 0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    std::atomic<uint64_t> next{0};
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(4096, n / (uint64_t(threads) * 8) + 1));
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t] {
+            for (;;) {
+                uint64_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                f(b, std::min(n, b + chunk), t);
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+extern "C" void orc_trace(const orc_tlas *t, const rt_ray *rays, uint64_t n, uint32_t ray_flags, uint32_t instance_mask,
+                          rt_hit *hits, rt_trace_stats *stats, int threads) {
+    int nt = threads <= 1 ? 1 : threads;
+    std::vector<TraceCounters> ctrs(nt);
+    parallel_for(n, threads, [&](uint64_t b, uint64_t e, int tid) {
+        for (uint64_t i = b; i < e; ++i) {
+            const rt_ray &r = rays[i];
+            HitInfo h = trace_ray(t, mk(r.origin[0], r.origin[1], r.origin[2]), r.tmin, mk(r.direction[0], r.direction[1], r.direction[2]),
+                                  r.tmax, ray_flags, instance_mask, 0, 0, &ctrs[tid]);
+            rt_hit &o = hits[i];
+            o.t = h.hit ? h.t : r.tmax;
+            o.bary[0] = h.bary[0], o.bary[1] = h.bary[1];
+            o.primitive_index = h.hit ? h.primitiveIndex : RT_NO_HIT;
+            o.instance_index = h.instanceIndex;
+            o.geometry_index = h.geometryIndex;
+            o.instance_id = h.instanceId;
+            o.leaf_slot = h.leafSlot;
+        }
+    });
+    if (stats) {
+        stats->rays += n;
+        for (auto &c : ctrs) {
+            stats->internal_visits += c.internal;
+            stats->leaf_visits += c.leaf;
+            stats->instance_visits += c.inst;
+            if (c.max_stack > stats->max_stack) stats->max_stack = c.max_stack;
+        }
+    }
+}
