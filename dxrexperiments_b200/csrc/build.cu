@@ -1,0 +1,851 @@
+// build.cu — LBVH acceleration-structure build for sm_100a.
+//
+// B200-native replacement of the Fallback Layer's GpuBvh2Builder pass chain
+// (externals/D3D12RaytracingFallback/src/GpuBVH2Builder.cpp:137-328): load -> scene AABB -> 30-bit Morton
+// codes -> sort -> rearrange -> Karras hierarchy -> bottom-up AABB fit, for BLAS (triangles) and TLAS
+// (instances).  Differences in HOW (results are bit-identical to the CPU restatement):
+//   * scene AABB is one fused pass (block reduce + ordered-int atomics) instead of ceil(log8 N) dispatches;
+//   * the O(log^2 N)-pass bitonic sort becomes a 4-pass stable LSD radix sort, which yields exactly the
+//     order BitonicSortCommon.hlsli:37-47 defines (ascending key, ties by ascending index);
+//   * the fit pass also emits this library's traversal section (64-byte nodes with both child boxes,
+//     48-byte triangles) so no separate packing pass re-reads the tree.
+// This file is compiled with -fmad=false: every float op below is the IEEE operation written.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------ utilities
+__device__ __forceinline__ uint32_t enc_f32(float f) {  // monotonic float -> uint
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(uint32_t e) {
+    uint32_t b = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+    return __uint_as_float(b);
+}
+
+struct Aabb3 {
+    float mn[3], mx[3];
+};
+
+__device__ __forceinline__ void block_reduce_aabb(float mn[3], float mx[3], uint32_t *enc /* 6 words */) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&enc[k], enc_f32(mn[k]));
+            atomicMax(&enc[3 + k], enc_f32(mx[k]));
+        }
+    }
+}
+
+__global__ void k_init_aabb(uint32_t *enc) {
+    if (threadIdx.x < 3) enc[threadIdx.x] = enc_f32(FLT_MAX);
+    else if (threadIdx.x < 6) enc[threadIdx.x] = enc_f32(-FLT_MAX);
+}
+__global__ void k_decode_aabb(const uint32_t *enc, float *out) {
+    // + 0.0f canonicalises -0 to +0 (fminf(-0,+0) is unspecified on the CPU side).
+    if (threadIdx.x < 6) out[threadIdx.x] = dec_f32(enc[threadIdx.x]) + 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------ load triangles
+// FL/BottomLevelLoadTriangles.hlsli:88-126 + LoadPrimitivesBindings.h:72-79, fused with the scene AABB
+// (FL/CalculateSceneAABBFromPrimitives.hlsl:16-40).
+struct LoadGeom {
+    const uint8_t *vb;
+    const void *ib;
+    uint32_t stride, index_format, num_tris, prim_offset, geom_index, flags, has_xf;
+    float xf[12];
+};
+
+__global__ void __launch_bounds__(kThreads) k_load_triangles(LoadGeom g, rt_primitive *prims, rt_primitive_meta *meta,
+                                                             uint32_t *aabb_enc) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (t < g.num_tris) {
+        uint32_t idx[3];
+        if (g.index_format == 32) {
+            const uint32_t *ib = static_cast<const uint32_t *>(g.ib);
+            idx[0] = ib[3 * t], idx[1] = ib[3 * t + 1], idx[2] = ib[3 * t + 2];
+        } else if (g.index_format == 16) {
+            const uint16_t *ib = static_cast<const uint16_t *>(g.ib);
+            idx[0] = ib[3 * t], idx[1] = ib[3 * t + 1], idx[2] = ib[3 * t + 2];
+        } else {
+            idx[0] = 3 * t, idx[1] = 3 * t + 1, idx[2] = 3 * t + 2;
+        }
+        uint32_t out = g.prim_offset + t;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(prims + out);
+        dst[0] = 1;  // TRIANGLE_TYPE
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float *p = reinterpret_cast<const float *>(g.vb + size_t(idx[k]) * g.stride);
+            f3 v = mk3(p[0], p[1], p[2]);
+            if (g.has_xf) v = xform_point(g.xf, v);
+            dst[1 + 3 * k] = __float_as_uint(v.x);
+            dst[2 + 3 * k] = __float_as_uint(v.y);
+            dst[3 + 3 * k] = __float_as_uint(v.z);
+            mn[0] = fminf(mn[0], v.x), mn[1] = fminf(mn[1], v.y), mn[2] = fminf(mn[2], v.z);
+            mx[0] = fmaxf(mx[0], v.x), mx[1] = fmaxf(mx[1], v.y), mx[2] = fmaxf(mx[2], v.z);
+        }
+        meta[out].geometryContributionToHitGroupIndex = g.geom_index;
+        meta[out].primitiveIndex = t;
+        meta[out].geometryFlags = g.flags;
+    }
+    block_reduce_aabb(mn, mx, aabb_enc);
+}
+
+// ------------------------------------------------------------------------------------------ Morton codes
+// FL/CalculateMortonCodes.hlsli:73-118 (non-scaled variant).
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {  // bit b -> bit 3b
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton_from_centroid(f3 c, const float *aabb) {
+    const float eps = 0.00001f;
+    float dx = fmaxf(aabb[3] - aabb[0], eps), dy = fmaxf(aabb[4] - aabb[1], eps), dz = fmaxf(aabb[5] - aabb[2], eps);
+    float ux = (c.x - aabb[0]) / dx, uy = (c.y - aabb[1]) / dy, uz = (c.z - aabb[2]) / dz;
+    float ax = fminf(fmaxf(ux * 1024.0f, 0.0f), 1023.0f), ay = fminf(fmaxf(uy * 1024.0f, 0.0f), 1023.0f),
+          az = fminf(fmaxf(uz * 1024.0f, 0.0f), 1023.0f);
+    uint32_t qx = uint32_t(ax), qy = uint32_t(ay), qz = uint32_t(az);
+    // axis order (y, x, z): bit 3b+0 <- y, 3b+1 <- x, 3b+2 <- z
+    return expand10(qy) | (expand10(qx) << 1) | (expand10(qz) << 2);
+}
+
+__global__ void __launch_bounds__(kThreads) k_morton_prims(const rt_primitive *prims, uint32_t n, const float *aabb,
+                                                           uint32_t *codes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *v = prims[i].v;
+    // (v0 + v1 + v2) / 3.0  (CalculateMortonCodesForPrimitives.hlsl:22-25)
+    f3 c = mk3(((v[0] + v[3]) + v[6]) / 3.0f, ((v[1] + v[4]) + v[7]) / 3.0f, ((v[2] + v[5]) + v[8]) / 3.0f);
+    codes[i] = morton_from_centroid(c, aabb);
+}
+
+__global__ void __launch_bounds__(kThreads) k_morton_boxes(const rt_aabb_node *boxes, uint32_t n, const float *aabb,
+                                                           uint32_t *codes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    codes[i] = morton_from_centroid(mk3(boxes[i].center[0], boxes[i].center[1], boxes[i].center[2]), aabb);
+}
+
+// ------------------------------------------------------------------------------------------ radix sort
+// Stable LSD radix sort of (key, value) pairs, 8-bit digits.  Each block owns a contiguous range of tiles,
+// so the digit-major scan is over a fixed 256 x gridDim array whatever N is.
+constexpr int kRadixBits = 8, kRadix = 1 << kRadixBits, kSortThreads = 256, kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *keys, uint32_t n, int shift,
+                                                             uint32_t tiles_per_block, uint32_t *hist /* [256][grid] */) {
+    __shared__ uint32_t s[kRadix];
+    s[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t begin = uint64_t(blockIdx.x) * tiles_per_block * kSortTile;
+    uint64_t end = min(uint64_t(n), begin + uint64_t(tiles_per_block) * kSortTile);
+    for (uint64_t i = begin + threadIdx.x; i < end; i += kSortThreads) atomicAdd(&s[(keys[i] >> shift) & (kRadix - 1)], 1u);
+    __syncthreads();
+    hist[threadIdx.x * gridDim.x + blockIdx.x] = s[threadIdx.x];
+}
+
+// Exclusive scan of `len` words by one block: each thread scans a contiguous segment serially.
+__global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *data, uint32_t len) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t seg = (len + 1023) / 1024;
+    const uint32_t b = threadIdx.x * seg, e = min(len, b + seg);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += data[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_sums[threadIdx.x], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += v;
+        }
+        warp_sums[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[threadIdx.x >> 5] + (incl - sum);
+    for (uint32_t i = b; i < e; ++i) {
+        uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+template <bool IOTA>
+__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t n,
+                                                                int shift, uint32_t tiles_per_block, const uint32_t *offsets,
+                                                                uint32_t *keys_out, uint32_t *vals_out) {
+    __shared__ uint32_t warp_count[kSortWarps][kRadix];
+    __shared__ uint32_t base[kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    base[threadIdx.x] = offsets[threadIdx.x * gridDim.x + blockIdx.x];
+    const uint64_t block_begin = uint64_t(blockIdx.x) * tiles_per_block * kSortTile;
+    for (uint32_t tile = 0; tile < tiles_per_block; ++tile) {
+        const uint64_t tile_begin = block_begin + uint64_t(tile) * kSortTile;
+        if (tile_begin >= n) break;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) warp_count[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
+            const bool valid = i < n;
+            key[r] = valid ? keys_in[i] : 0xffffffffu;
+            val[r] = valid ? (IOTA ? uint32_t(i) : vals_in[i]) : 0u;
+            const uint32_t d = (key[r] >> shift) & (kRadix - 1);
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            rank[r] = 0;
+            if (valid) {
+                const unsigned peers = __match_any_sync(active, d);
+                const int leader = __ffs(peers) - 1;
+                uint32_t prev = 0;
+                if (lane == leader) {
+                    prev = warp_count[warp][d];
+                    warp_count[warp][d] = prev + __popc(peers);
+                }
+                prev = __shfl_sync(peers, prev, leader);
+                rank[r] = prev + __popc(peers & ((1u << lane) - 1));
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        {  // per-digit exclusive prefix over the warps of this tile; advance the running base
+            const int d = threadIdx.x;
+            uint32_t off = 0;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                uint32_t c = warp_count[w][d];
+                warp_count[w][d] = off;
+                off += c;
+            }
+            // base[d] is read by the scatter below and bumped afterwards: keep the old value in a register
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < kSortItems; ++r) {
+                const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
+                if (i < n) {
+                    const uint32_t dd = (key[r] >> shift) & (kRadix - 1);
+                    const uint32_t pos = base[dd] + warp_count[warp][dd] + rank[r];
+                    keys_out[pos] = key[r];
+                    vals_out[pos] = val[r];
+                }
+            }
+            __syncthreads();
+            base[d] += off;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ Karras hierarchy
+// FL/BuildBVHSplits.hlsli:35-143
+struct KarrasDev {
+    const uint32_t *codes;
+    int n;
+    __device__ __forceinline__ int lcp(int a, int b) const {
+        if (a < 0 || b < 0 || a >= n || b >= n) return -1;
+        uint32_t ca = codes[a], cb = codes[b];
+        if (ca != cb) return __clz(int(ca ^ cb));
+        return __clz(a ^ b) + 31;
+    }
+};
+
+__global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, uint32_t n, rt_hierarchy_node *nodes) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= int(n) - 1) return;
+    KarrasDev k{codes, int(n)};
+    int d = k.lcp(idx, idx + 1) - k.lcp(idx, idx - 1);
+    d = min(max(d, -1), 1);
+    int minPrefix = k.lcp(idx, idx - d);
+    long long maxLength = 2;  // 64-bit: idx + maxLength*d must not wrap for large n
+    while (true) {
+        long long j = (long long)idx + maxLength * d;
+        int p = (j < 0 || j >= n) ? -1 : k.lcp(idx, int(j));
+        if (!(p > minPrefix)) break;
+        maxLength *= 4;
+    }
+    long long length = 0;
+    for (long long t = maxLength / 2; t > 0; t /= 2) {
+        long long j = (long long)idx + (length + t) * d;
+        int p = (j < 0 || j >= n) ? -1 : k.lcp(idx, int(j));
+        if (p > minPrefix) length += t;
+    }
+    int j = idx + int(length) * d;
+    int first = min(idx, j), last = max(idx, j);
+    // FindSplit
+    int commonPrefix = k.lcp(first, last);
+    int split = first, step = last - first;
+    do {
+        step = (step + 1) >> 1;
+        int ns = split + step;
+        if (ns < last && k.lcp(first, ns) > commonPrefix) split = ns;
+    } while (step > 1);
+    uint32_t leafOffset = n - 1;
+    uint32_t a = (split == first) ? leafOffset + split : split;
+    uint32_t b = (split + 1 == last) ? leafOffset + split + 1 : split + 1;
+    nodes[idx].left = a;
+    nodes[idx].right = b;
+    nodes[a].parent = idx;
+    nodes[b].parent = idx;
+}
+
+// ------------------------------------------------------------------------------------------ rearrange
+// FL/RearrangeTriangles.hlsl:18-36: out[dst] = in[perm[dst]]; also emits the packed 48-byte triangle.
+__global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_primitive *prims, const rt_primitive_meta *meta,
+                                                             const uint32_t *perm, uint32_t n, rt_primitive *out_prims,
+                                                             rt_primitive_meta *out_meta, rt_packed_tri *packed) {
+    uint32_t dst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dst >= n) return;
+    uint32_t src = perm[dst];
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(prims + src);
+    uint32_t w[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) w[k] = s[k];
+    uint32_t *d = reinterpret_cast<uint32_t *>(out_prims + dst);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) d[k] = w[k];
+    rt_primitive_meta m = meta[src];
+    out_meta[dst] = m;
+    uint4 *p = reinterpret_cast<uint4 *>(packed + dst);
+    p[0] = make_uint4(w[1], w[2], w[3], w[4]);
+    p[1] = make_uint4(w[5], w[6], w[7], w[8]);
+    p[2] = make_uint4(w[9], m.primitiveIndex, m.geometryContributionToHitGroupIndex, m.geometryFlags);
+}
+
+// ------------------------------------------------------------------------------------------ bottom-up fit
+struct Box {
+    float c[3], h[3];
+};
+// AABBtoBoundingBox: FL/RayTracingHelper.hlsli:251-257
+__device__ __forceinline__ Box aabb_to_box(const float mn[3], const float mx[3]) {
+    Box b;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.c[k] = (mn[k] + mx[k]) * 0.5f;
+        b.h[k] = mx[k] - b.c[k];
+    }
+    return b;
+}
+__device__ __forceinline__ void store_node(rt_aabb_node *nodes, uint32_t i, const Box &b, uint32_t flags, uint32_t right) {
+    float4 *p = reinterpret_cast<float4 *>(nodes + i);
+    __stcg(p, make_float4(b.c[0], b.c[1], b.c[2], __uint_as_float(flags)));
+    __stcg(p + 1, make_float4(b.h[0], b.h[1], b.h[2], __uint_as_float(right)));
+}
+__device__ __forceinline__ Box load_node_box(const rt_aabb_node *nodes, uint32_t i) {
+    const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
+    float4 a = __ldcg(p), b = __ldcg(p + 1);
+    Box r;
+    r.c[0] = a.x, r.c[1] = a.y, r.c[2] = a.z, r.h[0] = b.x, r.h[1] = b.y, r.h[2] = b.z;
+    return r;
+}
+
+// FL/ComputeAABBs.hlsli:69-175.  One thread per leaf climbs; the second child to arrive at a parent
+// (atomic counter carrying triangle counts) fits the parent.  Children are ordered "smaller subtree
+// left"; on equal counts the reference is arrival-order dependent, pinned here as "keep Karras order".
+// TOP = false: leaf box from the sorted triangle (GetBoxDataFromTriangle, RayTracingHelper.hlsli:273-285).
+// TOP = true : leaf box = load-order instance box permuted by `perm`.
+template <bool TOP>
+__global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy_node *hier, uint32_t *counters,
+                                                  rt_aabb_node *nodes, const rt_primitive *sorted_prims,
+                                                  const rt_aabb_node *inst_boxes, const uint32_t *perm,
+                                                  rt_wide_node *wide, rt_ext_header *ext) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const uint32_t nInternal = n - 1;
+    uint32_t node = nInternal + slot;
+    Box box;
+    if (TOP) {
+        const rt_aabb_node &s = inst_boxes[perm[slot]];
+        box.c[0] = s.center[0], box.c[1] = s.center[1], box.c[2] = s.center[2];
+        box.h[0] = s.halfDim[0], box.h[1] = s.halfDim[1], box.h[2] = s.halfDim[2];
+    } else {
+        const float *v = sorted_prims[slot].v;
+        float mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
+            mx[k] = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
+            mn[k] = fminf(mn[k], mx[k] - 0.001f);  // AABB_Min_Padding
+        }
+        box = aabb_to_box(mn, mx);
+    }
+    store_node(nodes, node, box, slot | RT_NODE_LEAF_FLAG, 1u);
+    if (n == 1) {
+        ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
+        ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
+        return;
+    }
+    uint32_t count = 1;
+    while (true) {
+        const uint32_t parent = hier[node].parent;
+        __threadfence();
+        const uint32_t other = atomicAdd(&counters[parent], count);
+        if (other == 0) return;  // first to arrive: the sibling will fit the parent
+        __threadfence();
+        uint32_t l = hier[parent].left, r = hier[parent].right;
+        const bool isLeft = (l == node);
+        const uint32_t lc = isLeft ? count : other, rc = isLeft ? other : count;
+        const uint32_t sibling = isLeft ? r : l;
+        Box sb = load_node_box(nodes, sibling);
+        Box bl = isLeft ? box : sb, br = isLeft ? sb : box;
+        if (rc < lc) {  // smaller subtree on the left; ties keep the Karras order
+            uint32_t t = l; l = r; r = t;
+            Box tb = bl; bl = br; br = tb;
+        }
+        // GetBoxFromChildBoxes: FL/RayTracingHelper.hlsli:297-307
+        float mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(bl.c[k] - bl.h[k], br.c[k] - br.h[k]);
+            mx[k] = fmaxf(bl.c[k] + bl.h[k], br.c[k] + br.h[k]);
+        }
+        box = aabb_to_box(mn, mx);
+        store_node(nodes, parent, box, l & 0x00ffffffu, r);
+        // traversal section: both child boxes live in the parent
+        const uint32_t lref = l >= nInternal ? (RT_NODE_LEAF_FLAG | (l - nInternal)) : l;
+        const uint32_t rref = r >= nInternal ? (RT_NODE_LEAF_FLAG | (r - nInternal)) : r;
+        float4 *w = reinterpret_cast<float4 *>(wide + parent);
+        w[0] = make_float4(bl.c[0], bl.c[1], bl.c[2], __uint_as_float(lref));
+        w[1] = make_float4(bl.h[0], bl.h[1], bl.h[2], __uint_as_float(rref));
+        w[2] = make_float4(br.c[0], br.c[1], br.c[2], 0.0f);
+        w[3] = make_float4(br.h[0], br.h[1], br.h[2], 0.0f);
+        if (parent == 0) {
+            ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
+            ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
+            return;
+        }
+        count += other;
+        node = parent;
+    }
+}
+
+__global__ void k_write_headers(uint8_t *result, rt_bvh_offsets off, rt_ext_header ext, uint64_t ext_offset) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *reinterpret_cast<rt_bvh_offsets *>(result) = off;
+        rt_ext_header *e = reinterpret_cast<rt_ext_header *>(result + ext_offset);
+        e->magic = ext.magic, e->count = ext.count, e->root_ref = ext.root_ref, e->top_level = ext.top_level;
+        e->off_wide = ext.off_wide, e->off_leaf = ext.off_leaf;
+        e->_pad0 = e->_pad1 = 0;
+        if (ext.count == 0) {
+            // empty TLAS: node 0 is a zero box with zero flags (FL/TopLevelPrepareForComputeAABBs.hlsl:40-48)
+            float4 *p = reinterpret_cast<float4 *>(result + 16);
+            p[0] = make_float4(0, 0, 0, 0);
+            p[1] = make_float4(0, 0, 0, 0);
+            for (int k = 0; k < 3; ++k) e->root_center[k] = 0.0f, e->root_half[k] = 0.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ TLAS load
+// FL/RayTracingHelper.hlsli:309-338 (terms multiplied by literal 0 dropped, see the oracle).
+__device__ void invert_affine(const float *t, float *o) {
+#define T(r, c) t[(r)*4 + (c)]
+    float det = T(0, 0) * T(1, 1) * T(2, 2) - T(0, 0) * T(2, 1) * T(1, 2) - T(1, 0) * T(0, 1) * T(2, 2) +
+                T(1, 0) * T(2, 1) * T(0, 2) + T(2, 0) * T(0, 1) * T(1, 2) - T(2, 0) * T(1, 1) * T(0, 2);
+    float invDet = 1.0f / det;
+    o[0] = invDet * (T(1, 1) * T(2, 2) + T(2, 1) * (0.0f - T(1, 2)));
+    o[4] = invDet * (T(1, 2) * T(2, 0) + T(2, 2) * (0.0f - T(1, 0)));
+    o[8] = invDet * (T(1, 0) * T(2, 1) - T(2, 0) * T(1, 1));
+    o[1] = invDet * (T(2, 1) * T(0, 2) + T(0, 1) * (0.0f - T(2, 2)));
+    o[5] = invDet * (T(2, 2) * T(0, 0) + T(0, 2) * (0.0f - T(2, 0)));
+    o[9] = invDet * (T(2, 0) * T(0, 1) - T(0, 0) * T(2, 1));
+    o[2] = invDet * (T(0, 1) * T(1, 2) + T(1, 1) * (0.0f - T(0, 2)));
+    o[6] = invDet * (T(0, 2) * T(1, 0) + T(1, 2) * (0.0f - T(0, 0)));
+    o[10] = invDet * (T(0, 0) * T(1, 1) - T(1, 0) * T(0, 1));
+    o[3] = invDet * (T(0, 1) * (T(2, 2) * T(1, 3) - T(1, 2) * T(2, 3)) + T(1, 1) * (T(0, 2) * T(2, 3) - T(2, 2) * T(0, 3)) +
+                     T(2, 1) * (T(1, 2) * T(0, 3) - T(0, 2) * T(1, 3)));
+    o[7] = invDet * (T(0, 2) * (T(2, 0) * T(1, 3) - T(1, 0) * T(2, 3)) + T(1, 2) * (T(0, 0) * T(2, 3) - T(2, 0) * T(0, 3)) +
+                     T(2, 2) * (T(1, 0) * T(0, 3) - T(0, 0) * T(1, 3)));
+    o[11] = invDet * (T(0, 3) * (T(2, 0) * T(1, 1) - T(1, 0) * T(2, 1)) + T(1, 3) * (T(0, 0) * T(2, 1) - T(2, 0) * T(0, 1)) +
+                      T(2, 3) * (T(1, 0) * T(0, 1) - T(0, 0) * T(1, 1)));
+#undef T
+}
+
+// FL/TopLevelLoadAABBs.hlsli:58-100 fused with FL/CalculateSceneAABBFromBVHs.hlsl:16-40.
+__global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_desc *descs, uint32_t n, rt_aabb_node *boxes,
+                                                             rt_bvh_metadata *md, uint32_t *aabb_enc) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float smn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, smx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) {
+        rt_instance_desc d = descs[i];
+        const rt_aabb_node *root = reinterpret_cast<const rt_aabb_node *>(reinterpret_cast<const uint8_t *>(uintptr_t(d.blas)) + 16);
+        float bmn[3], bmx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {  // BoundingBoxToAABB
+            bmn[k] = root->center[k] - root->halfDim[k];
+            bmx[k] = root->center[k] + root->halfDim[k];
+        }
+        // TransformAABB: FL/RayTracingHelper.hlsli:340-366
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            f3 v = xform_point(d.transform, mk3((c & 4) ? bmx[0] : bmn[0], (c & 2) ? bmx[1] : bmn[1], (c & 1) ? bmx[2] : bmn[2]));
+            mn[0] = fminf(mn[0], v.x), mn[1] = fminf(mn[1], v.y), mn[2] = fminf(mn[2], v.z);
+            mx[0] = fmaxf(mx[0], v.x), mx[1] = fmaxf(mx[1], v.y), mx[2] = fmaxf(mx[2], v.z);
+        }
+        Box b = aabb_to_box(mn, mx);
+        rt_aabb_node nb;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) nb.center[k] = b.c[k], nb.halfDim[k] = b.h[k];
+        nb.flags = RT_NODE_LEAF_FLAG | i;
+        nb.right = RT_NODE_LEAF_FLAG | i;
+        boxes[i] = nb;
+        // BVHMetadata (116 B): world->object transform, ids, BLAS address, object->world, instance index
+        uint32_t w[29];
+        float inv[12];
+        invert_affine(d.transform, inv);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) w[k] = __float_as_uint(inv[k]);
+        w[12] = d.instance_id_and_mask;
+        w[13] = d.hit_group_and_flags;
+        w[14] = uint32_t(d.blas);
+        w[15] = uint32_t(d.blas >> 32);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) w[16 + k] = __float_as_uint(d.transform[k]);
+        w[28] = i;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(md) + size_t(i) * 116);
+#pragma unroll
+        for (int k = 0; k < 29; ++k) dst[k] = w[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {  // scene AABB from the re-derived corners of the stored box
+            smn[k] = b.c[k] - b.h[k];
+            smx[k] = b.c[k] + b.h[k];
+        }
+    }
+    block_reduce_aabb(smn, smx, aabb_enc);
+}
+
+// FL/RearrangeBVHs.hlsl:50-58 (metadata only; leaf boxes are re-fitted by k_fit<true>) + packed instances.
+__global__ void __launch_bounds__(kThreads) k_rearrange_instances(const rt_bvh_metadata *md, const uint32_t *perm, uint32_t n,
+                                                                  rt_bvh_metadata *out_md, rt_packed_instance *packed) {
+    uint32_t dst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dst >= n) return;
+    uint32_t src = perm[dst];
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(md) + size_t(src) * 116);
+    uint32_t w[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) w[k] = s[k];
+    uint32_t *d = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out_md) + size_t(dst) * 116);
+#pragma unroll
+    for (int k = 0; k < 29; ++k) d[k] = w[k];
+    rt_packed_instance pi;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) pi.w2o[k] = __uint_as_float(w[k]);
+    pi.instance_id_and_mask = w[12];
+    pi.hit_group_and_flags = w[13];
+    pi.instance_index = w[28];
+    const uint8_t *blas = reinterpret_cast<const uint8_t *>(uintptr_t(uint64_t(w[14]) | (uint64_t(w[15]) << 32)));
+    const rt_bvh_offsets *bo = reinterpret_cast<const rt_bvh_offsets *>(blas);
+    const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(bo->totalSize, 64));
+    pi.blas_root_ref = be->root_ref;
+    pi.blas_wide = reinterpret_cast<const rt_wide_node *>(blas + be->off_wide);
+    pi.blas_tris = reinterpret_cast<const rt_packed_tri *>(blas + be->off_leaf);
+    pi._pad[0] = pi._pad[1] = 0;
+    packed[dst] = pi;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct SortPlan {
+    uint32_t blocks, tiles_per_block;
+};
+SortPlan plan_sort(uint32_t n, int num_sms) {
+    uint32_t tiles = (n + kSortTile - 1) / kSortTile;
+    uint32_t max_blocks = uint32_t(num_sms) * 4;
+    SortPlan p;
+    p.blocks = std::max(1u, std::min(tiles, max_blocks));
+    p.tiles_per_block = (tiles + p.blocks - 1) / p.blocks;
+    p.blocks = std::max(1u, (tiles + p.tiles_per_block - 1) / std::max(1u, p.tiles_per_block));
+    return p;
+}
+
+struct Layout {
+    uint64_t aabb_enc, aabb, codes, keysB, valsB, keysC, valsC, hier, counters, hist, elems, meta, total;
+};
+Layout make_layout(uint32_t n, bool top) {
+    Layout L{};
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) {
+        uint64_t r = o;
+        o = align_up(o + bytes, 256);
+        return r;
+    };
+    const uint64_t nn = std::max(n, 1u);
+    L.aabb_enc = take(32);
+    L.aabb = take(32);
+    L.codes = take(4 * nn);
+    L.keysB = take(4 * nn);
+    L.valsB = take(4 * nn);
+    L.keysC = take(4 * nn);
+    L.valsC = take(4 * nn);
+    L.hier = take(12 * (2 * nn - 1));
+    L.counters = take(4 * nn);
+    L.hist = take(4ull * kRadix * 148 * 8);
+    L.elems = take((top ? 32 : 40) * nn);
+    L.meta = take((top ? 116 : 12) * nn);
+    L.total = o;
+    return L;
+}
+
+struct ResultLayout {
+    rt_bvh_offsets off;
+    uint64_t ext, wide, leaf, total;
+};
+ResultLayout make_result_layout(uint32_t n, bool top) {
+    ResultLayout R{};
+    const uint32_t nodes = n == 0 ? 1 : 2 * n - 1;
+    R.off.offsetToBoxes = 16;
+    R.off.offsetToVertices = 16 + 32 * nodes;
+    if (top) {
+        R.off.offsetToPrimitiveMetaData = 0;
+        R.off.totalSize = R.off.offsetToVertices + 116 * n;
+    } else {
+        R.off.offsetToPrimitiveMetaData = R.off.offsetToVertices + 40 * n;
+        R.off.totalSize = R.off.offsetToPrimitiveMetaData + 12 * n;
+    }
+    R.ext = align_up(R.off.totalSize, 64);
+    R.wide = R.ext + 64;
+    R.leaf = R.wide + 64ull * std::max(1u, n > 0 ? n - 1 : 0u);
+    R.total = R.leaf + (top ? 96ull : 48ull) * std::max(n, 1u);
+    return R;
+}
+
+int sort_pairs(rt_context *ctx, uint8_t *scratch, const Layout &L, uint32_t n) {
+    // 30-bit keys -> 4 passes of 8 bits.  codes -> B -> C -> B -> C
+    SortPlan sp = plan_sort(n, ctx->num_sms);
+    uint32_t *codes = reinterpret_cast<uint32_t *>(scratch + L.codes);
+    uint32_t *kB = reinterpret_cast<uint32_t *>(scratch + L.keysB), *vB = reinterpret_cast<uint32_t *>(scratch + L.valsB);
+    uint32_t *kC = reinterpret_cast<uint32_t *>(scratch + L.keysC), *vC = reinterpret_cast<uint32_t *>(scratch + L.valsC);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(scratch + L.hist);
+    const uint32_t *kin = codes, *vin = nullptr;
+    uint32_t *kout = kB, *vout = vB;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = pass * kRadixBits;
+        k_radix_hist<<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, n, shift, sp.tiles_per_block, hist);
+        k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(hist, kRadix * sp.blocks);
+        if (pass == 0)
+            k_radix_scatter<true><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, kout, vout);
+        else
+            k_radix_scatter<false><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, kout, vout);
+        ctx->launches += 3;
+        kin = kout, vin = vout;
+        if (kout == kB) kout = kC, vout = vC; else kout = kB, vout = vB;
+    }
+    RT_LAUNCH_CHECK();
+    return RT_OK;  // sorted pairs are in (kC, vC)
+}
+
+}  // namespace
+
+extern "C" {
+
+uint64_t rt_blob_bytes(uint32_t n, int top_level) { return make_result_layout(n, top_level != 0).off.totalSize; }
+
+int rt_build_scratch_layout(uint32_t n, int top_level, rt_scratch_layout *out) {
+    RT_REQUIRE(out != nullptr, "layout");
+    Layout L = make_layout(n, top_level != 0);
+    out->scene_aabb = L.aabb;
+    out->morton_codes = L.codes;
+    out->sorted_codes = L.keysC;
+    out->sorted_indices = L.valsC;
+    out->hierarchy = L.hier;
+    out->primitives = L.elems;
+    out->metadata = L.meta;
+    out->total = L.total;
+    return RT_OK;
+}
+
+static uint32_t count_prims(const rt_geometry_desc *geoms, uint32_t n_geoms) {
+    uint64_t n = 0;
+    for (uint32_t g = 0; g < n_geoms; ++g) n += (geoms[g].index_format == 0 ? geoms[g].vertex_count : geoms[g].index_count) / 3;
+    return uint32_t(n);
+}
+
+int rt_blas_prebuild(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t /*flags*/, rt_prebuild_info *info) {
+    RT_REQUIRE(ctx && info && (geoms || n_geoms == 0), "null argument");
+    uint32_t n = count_prims(geoms, n_geoms);
+    RT_REQUIRE(n < (1u << 24), "more than 2^24-1 primitives (node indices are 24 bit: RayTracingHelper.hlsli:112-118)");
+    info->result_bytes = make_result_layout(n, false).total;
+    info->scratch_bytes = make_layout(n, false).total;
+    info->update_scratch_bytes = 0;
+    return RT_OK;
+}
+
+int rt_tlas_prebuild(rt_context *ctx, uint32_t n, uint32_t /*flags*/, rt_prebuild_info *info) {
+    RT_REQUIRE(ctx && info, "null argument");
+    RT_REQUIRE(n < (1u << 24), "more than 2^24-1 instances");
+    info->result_bytes = make_result_layout(n, true).total;
+    info->scratch_bytes = make_layout(n, true).total;
+    info->update_scratch_bytes = 0;
+    return RT_OK;
+}
+
+static int build_common(rt_context *ctx, uint32_t n, bool top, uint8_t *scratch, uint8_t *result, const Layout &L,
+                        const ResultLayout &R) {
+    cudaStream_t st = ctx->stream;
+    float *aabb = reinterpret_cast<float *>(scratch + L.aabb);
+    uint32_t *codes = reinterpret_cast<uint32_t *>(scratch + L.codes);
+    const int grid = rt_div_up(n, kThreads);
+    k_decode_aabb<<<1, 32, 0, st>>>(reinterpret_cast<uint32_t *>(scratch + L.aabb_enc), aabb);
+    if (top)
+        k_morton_boxes<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_aabb_node *>(scratch + L.elems), n, aabb, codes);
+    else
+        k_morton_prims<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_primitive *>(scratch + L.elems), n, aabb, codes);
+    ctx->launches += 2;
+    int rc = sort_pairs(ctx, scratch, L, n);
+    if (rc) return rc;
+    const uint32_t *sorted_codes = reinterpret_cast<uint32_t *>(scratch + L.keysC);
+    const uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + L.valsC);
+    rt_hierarchy_node *hier = reinterpret_cast<rt_hierarchy_node *>(scratch + L.hier);
+    RT_CUDA(cudaMemsetAsync(hier, 0, 12ull * (2ull * n - 1), st));
+    RT_CUDA(cudaMemsetAsync(scratch + L.counters, 0, 4ull * n, st));
+    if (n > 1) {
+        k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier);
+        ctx->launches++;
+    }
+    rt_aabb_node *nodes = reinterpret_cast<rt_aabb_node *>(result + 16);
+    rt_wide_node *wide = reinterpret_cast<rt_wide_node *>(result + R.wide);
+    rt_ext_header *ext = reinterpret_cast<rt_ext_header *>(result + R.ext);
+    if (top) {
+        k_rearrange_instances<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), perm, n,
+                                                         reinterpret_cast<rt_bvh_metadata *>(result + R.off.offsetToVertices),
+                                                         reinterpret_cast<rt_packed_instance *>(result + R.leaf));
+        k_fit<true><<<grid, kThreads, 0, st>>>(n, hier, reinterpret_cast<uint32_t *>(scratch + L.counters), nodes, nullptr,
+                                               reinterpret_cast<rt_aabb_node *>(scratch + L.elems), perm, wide, ext);
+    } else {
+        rt_primitive *sp = reinterpret_cast<rt_primitive *>(result + R.off.offsetToVertices);
+        k_rearrange_tris<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_primitive *>(scratch + L.elems),
+                                                    reinterpret_cast<rt_primitive_meta *>(scratch + L.meta), perm, n, sp,
+                                                    reinterpret_cast<rt_primitive_meta *>(result + R.off.offsetToPrimitiveMetaData),
+                                                    reinterpret_cast<rt_packed_tri *>(result + R.leaf));
+        k_fit<false><<<grid, kThreads, 0, st>>>(n, hier, reinterpret_cast<uint32_t *>(scratch + L.counters), nodes, sp, nullptr,
+                                                perm, wide, ext);
+    }
+    ctx->launches += 2;
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+static int write_headers(rt_context *ctx, uint32_t n, bool top, uint8_t *result, const ResultLayout &R) {
+    rt_ext_header e{};
+    e.magic = RT_EXT_MAGIC;
+    e.count = n;
+    e.root_ref = (n == 1) ? RT_NODE_LEAF_FLAG : 0u;
+    e.top_level = top ? 1u : 0u;
+    e.off_wide = R.wide;
+    e.off_leaf = R.leaf;
+    k_write_headers<<<1, 32, 0, ctx->stream>>>(result, R.off, e, R.ext);
+    ctx->launches++;
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t /*build_flags*/, void *scratch_,
+                  uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
+    RT_REQUIRE(ctx && scratch_ && result_, "null argument");  // E_INVALIDARG: FL/GpuBVH2Builder.cpp:145-148
+    RT_REQUIRE((uintptr_t(result_) & 63) == 0 && (uintptr_t(scratch_) & 63) == 0, "buffers must be 64-byte aligned");
+    uint32_t n = count_prims(geoms, n_geoms);
+    RT_REQUIRE(n > 0, "bottom-level build with zero primitives");
+    RT_REQUIRE(n < (1u << 24), "more than 2^24-1 primitives");
+    Layout L = make_layout(n, false);
+    ResultLayout R = make_result_layout(n, false);
+    if (scratch_bytes < L.total || result_bytes < R.total) {
+        rt_set_error("buffer too small: scratch %llu < %llu or result %llu < %llu", (unsigned long long)scratch_bytes,
+                     (unsigned long long)L.total, (unsigned long long)result_bytes, (unsigned long long)R.total);
+        return RT_ERR_TOO_SMALL;
+    }
+    RT_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *scratch = static_cast<uint8_t *>(scratch_), *result = static_cast<uint8_t *>(result_);
+    cudaStream_t st = ctx->stream;
+    int rc = write_headers(ctx, n, false, result, R);
+    if (rc) return rc;
+    uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
+    k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
+    ctx->launches++;
+    uint32_t offset = 0;
+    for (uint32_t g = 0; g < n_geoms; ++g) {  // one launch per geometry, like FL/LoadPrimitivesPass.cpp:60-170
+        const rt_geometry_desc &d = geoms[g];
+        LoadGeom lg{};
+        lg.vb = static_cast<const uint8_t *>(d.vertex_buffer);
+        lg.ib = d.index_buffer;
+        lg.stride = d.vertex_stride_bytes;
+        lg.index_format = d.index_format;
+        lg.num_tris = (d.index_format == 0 ? d.vertex_count : d.index_count) / 3;
+        RT_REQUIRE(d.vertex_buffer != nullptr || lg.num_tris == 0, "null vertex buffer");
+        RT_REQUIRE(d.index_format == 0 || d.index_format == 16 || d.index_format == 32, "index_format must be 0, 16 or 32");
+        RT_REQUIRE(d.index_format == 0 || d.index_buffer != nullptr, "null index buffer");
+        RT_REQUIRE(d.vertex_stride_bytes >= 12 && d.vertex_stride_bytes % 4 == 0, "vertex stride");
+        lg.prim_offset = offset;
+        lg.geom_index = g;
+        lg.flags = d.flags;
+        lg.has_xf = d.transform3x4 != nullptr;
+        if (lg.has_xf) {
+            RT_CUDA(cudaMemcpyAsync(lg.xf, d.transform3x4, 48, cudaMemcpyDefault, st));
+            RT_CUDA(cudaStreamSynchronize(st));
+        }
+        if (lg.num_tris) {
+            k_load_triangles<<<rt_div_up(lg.num_tris, kThreads), kThreads, 0, st>>>(
+                lg, reinterpret_cast<rt_primitive *>(scratch + L.elems), reinterpret_cast<rt_primitive_meta *>(scratch + L.meta), aabb_enc);
+            ctx->launches++;
+        }
+        offset += lg.num_tris;
+    }
+    RT_LAUNCH_CHECK();
+    return build_common(ctx, n, false, scratch, result, L, R);
+}
+
+int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, uint32_t /*build_flags*/, void *scratch_,
+                  uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
+    RT_REQUIRE(ctx && result_, "null argument");
+    RT_REQUIRE(n == 0 || (descs && scratch_), "null argument");
+    RT_REQUIRE((uintptr_t(result_) & 63) == 0 && (uintptr_t(scratch_) & 63) == 0, "buffers must be 64-byte aligned");
+    RT_REQUIRE(n < (1u << 24), "more than 2^24-1 instances");
+    Layout L = make_layout(n, true);
+    ResultLayout R = make_result_layout(n, true);
+    if ((n > 0 && scratch_bytes < L.total) || result_bytes < R.total) {
+        rt_set_error("buffer too small: scratch %llu < %llu or result %llu < %llu", (unsigned long long)scratch_bytes,
+                     (unsigned long long)L.total, (unsigned long long)result_bytes, (unsigned long long)R.total);
+        return RT_ERR_TOO_SMALL;
+    }
+    RT_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *scratch = static_cast<uint8_t *>(scratch_), *result = static_cast<uint8_t *>(result_);
+    cudaStream_t st = ctx->stream;
+    int rc = write_headers(ctx, n, true, result, R);
+    if (rc || n == 0) return rc;
+    uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
+    k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
+    k_load_instances<<<rt_div_up(n, kThreads), kThreads, 0, st>>>(descs, n, reinterpret_cast<rt_aabb_node *>(scratch + L.elems),
+                                                                 reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), aabb_enc);
+    ctx->launches += 2;
+    RT_LAUNCH_CHECK();
+    return build_common(ctx, n, true, scratch, result, L, R);
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// common.cuh — shared device/host helpers of librt_core.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/rt_core.h"
+
+#define RT_STR2(x) #x
+#define RT_STR(x) RT_STR2(x)
+
+// ---------------------------------------------------------------------------------------------
+// error handling
+void rt_set_error(const char *fmt, ...);
+
+#define RT_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rt_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return RT_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define RT_REQUIRE(cond, msg)                                   \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            rt_set_error("invalid argument: %s (%s)", msg, #cond); \
+            return RT_ERR_INVALID_ARG;                          \
+        }                                                       \
+    } while (0)
+
+#define RT_LAUNCH_CHECK()                                                                \
+    do {                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                             \
+        if (e_ != cudaSuccess) {                                                         \
+            rt_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return RT_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context
+
+struct rt_workspace {  // wavefront queues, grown on demand (pipeline.cu)
+    void *base = nullptr;
+    uint64_t bytes = 0;
+};
+
+struct rt_context {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    uint64_t launches = 0;
+
+    rt_per_frame_constants frame{};
+    float *output[2] = {nullptr, nullptr};
+    uint64_t pitch[2] = {0, 0};
+    const void *tlas = nullptr;
+
+    rt_workspace ws;
+    uint32_t *status = nullptr;          // device word: bit0 = traversal stack overflow
+    unsigned long long *ray_counts = nullptr;  // device: primary, secondary, shadow
+    // stage timing (optional)
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+    bool ev_ready = false;
+    double t_primary = 0, t_secondary = 0, t_shadow = 0;
+    uint64_t n_secondary_timed = 0;
+};
+
+struct rt_hit_record_dev {  // device copy of rt_hit_record
+    const float *vb;        // rt_vertex[] viewed as floats (stride 6)
+    const uint32_t *ib;
+    rt_material_params mat;
+};
+
+struct rt_program {
+    rt_context *ctx = nullptr;
+    rt_program_kind kind = RT_PROGRAM_PROGRESSIVE;
+    uint32_t hit_group_count = 0, miss_count = 0;
+    // host mirror + device table of hit records indexed by instance * hit_group_count + ray_type
+    rt_hit_record_dev *host_recs = nullptr;
+    rt_hit_record_dev *dev_recs = nullptr;
+    uint32_t n_recs = 0, cap_recs = 0;
+    bool dirty = true;
+    const float *env_texels = nullptr;
+    uint32_t env_size = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// layout of the library's traversal section appended to every result buffer
+
+#define RT_EXT_MAGIC 0x58425452u /* "RTBX" */
+
+struct rt_ext_header {  // 64 bytes, located at align64(reference blob size)
+    uint32_t magic;
+    uint32_t count;         // number of leaves (triangles or instances)
+    uint32_t root_ref;      // reference of the root (leaf ref if count == 1)
+    uint32_t top_level;     // 1 for a TLAS
+    uint64_t off_wide;      // byte offset from the start of the result buffer to the wide nodes
+    uint64_t off_leaf;      // ... to the packed triangles (BLAS) / packed instances (TLAS)
+    float root_center[3];   // root box (TLAS: tested once per ray; BLAS: informational)
+    uint32_t _pad0;
+    float root_half[3];
+    uint32_t _pad1;
+};
+static_assert(sizeof(rt_ext_header) == 64, "ext header");
+
+// Wide node: an internal BVH2 node carrying BOTH child boxes (center/halfDim as the reference stores
+// them) and child references.  64 B = 4 x 16-byte loads.  ref: bit31 set -> leaf slot in the low bits.
+struct __align__(16) rt_wide_node {
+    float lc[3];
+    uint32_t left;
+    float lh[3];
+    uint32_t right;
+    float rc[3];
+    uint32_t _p0;
+    float rh[3];
+    uint32_t _p1;
+};
+static_assert(sizeof(rt_wide_node) == 64, "wide node");
+
+// Packed triangle: 9 floats + PrimitiveMetaData in 48 B = 3 x 16-byte loads.
+struct __align__(16) rt_packed_tri {
+    float v[9];
+    uint32_t primitive_index;
+    uint32_t geometry_index;
+    uint32_t geometry_flags;
+};
+static_assert(sizeof(rt_packed_tri) == 48, "packed tri");
+
+// Packed instance (TLAS leaf): world->object 3x4, ids, and the BLAS traversal pointers. 96 B.
+struct __align__(16) rt_packed_instance {
+    float w2o[12];
+    uint32_t instance_id_and_mask;
+    uint32_t hit_group_and_flags;
+    uint32_t instance_index;
+    uint32_t blas_root_ref;
+    const rt_wide_node *blas_wide;
+    const rt_packed_tri *blas_tris;
+    uint64_t _pad[2];
+};
+static_assert(sizeof(rt_packed_instance) == 96, "packed instance");
+
+static inline __host__ __device__ uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// small device vector helpers (explicitly unfused where bit-parity with the oracle matters)
+
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+// Exact (never contracted) arithmetic: nvcc will not fuse __fmul_rn/__fadd_rn into FMAs.
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ f3 xform_point(const float *m, f3 v) {
+    return mk3(add_(add_(add_(mul_(m[0], v.x), mul_(m[1], v.y)), mul_(m[2], v.z)), m[3]),
+               add_(add_(add_(mul_(m[4], v.x), mul_(m[5], v.y)), mul_(m[6], v.z)), m[7]),
+               add_(add_(add_(mul_(m[8], v.x), mul_(m[9], v.y)), mul_(m[10], v.z)), m[11]));
+}
+__device__ __forceinline__ f3 xform_vector(const float *m, f3 v) {
+    return mk3(add_(add_(mul_(m[0], v.x), mul_(m[1], v.y)), mul_(m[2], v.z)),
+               add_(add_(mul_(m[4], v.x), mul_(m[5], v.y)), mul_(m[6], v.z)),
+               add_(add_(mul_(m[8], v.x), mul_(m[9], v.y)), mul_(m[10], v.z)));
+}
+
+static inline int rt_div_up(uint64_t a, uint64_t b) { return int((a + b - 1) / b); }

@@ -1,0 +1,662 @@
+// pipeline.cu — wavefront ray-generation / closest-hit / miss pipeline for sm_100a.
+//
+// Replaces the Fallback Layer's uber-shader state machine (FL/UberShaderRayTracingProgram.cpp:213-272,
+// FL/StateMachineLib.hlsl, dxrfallbackcompiler.dll) for the two shader libraries of the application:
+//   assets/shaders/ProgressiveRaytracing.hlsl (RayGen :11-39, shade :80-148, closest-hit/miss :150-164)
+//   assets/shaders/RealtimeRaytracing.hlsl    (RayGen :22-46, shadeAOV :65-103, closest-hit/miss :105-126)
+// The recursion "TraceRay inside closest-hit" becomes explicit stages with compacted ray queues:
+//
+//   K1 primary   : raygen + closest-hit traversal, 8x4 pixel tile per warp            -> hit records
+//   K2 shade0    : miss -> environment -> output; hit -> depth-0 shade(), emits 2 shadow rays (4 in the AO
+//                  debug view) and up to 2 secondary rays per hit pixel into compacted queues
+//   K3 secondary : closest-hit traversal of the incoherent secondary rays (the headline metric)
+//   K4 shadow0   : any-hit traversal of the depth-0 shadow rays
+//   K5 shade1    : depth-1 shade() of every secondary hit, emits its 2 shadow rays (compacted)
+//   K6 shadow1   : any-hit traversal of the depth-1 shadow rays
+//   K7 resolve   : recombines exactly the expression tree of shade()/shadeAOV() and accumulates
+//
+// Random numbers are a pure function of (pixel, frameCount) and are re-derived at each depth exactly as the
+// shaders re-initialise their seed, so no RNG state travels through the queues.
+#include <cstdio>
+
+#include "shade.cuh"
+#include "trace.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+struct Launch {
+    rt_per_frame_constants f;
+    uint32_t width, height;  // full launch dimensions
+    uint32_t x0, y0, rw, rh; // pixel rectangle handled by this dispatch
+    float jitterScale;
+    uint32_t realtime;
+    uint32_t shadowsPerHit;  // 2, or 4 in the ambient-occlusion debug view
+};
+
+struct WS {
+    float4 *hitA;       // [P]  primary hit: t, u, v, primitive
+    uint32_t *hitRec;   // [P]  hit-group record index
+    uint32_t *counters; // [0] hit slots, [1] depth-1 shadow pairs
+    uint4 *slotInfo;    // [P]  pixel (region-linear), record, flags, -
+    float4 *S0, *S1, *S2;
+    float *S3;
+    rt_ray *shadowQ0;   // [4P]
+    uint8_t *vis0;
+    rt_ray *secQ;       // [2P]
+    float4 *secHitA;
+    uint32_t *secRec;
+    uint32_t *secShadow; // [2P] index of the depth-1 shadow pair, or ~0
+    float4 *T0, *T1, *T2;
+    rt_ray *shadowQ1;   // [4P]
+    uint8_t *vis1;
+};
+
+enum : uint32_t {
+    SLOT_DEBUG2_DIR = 1u,    // debug == 2 and the directional light was selected
+    SLOT_DEBUG2_POINT = 2u,  // debug == 2 and the point light was selected
+    SLOT_HAS_SPEC = 4u,
+    SLOT_HAS_DIFFUSE = 8u,
+    SLOT_UNIFORM = 16u,
+    SLOT_AO = 32u,
+};
+
+__device__ __forceinline__ void store_ray(rt_ray *q, f3 o, float tmin, f3 d, float tmax) {
+    float4 *p = reinterpret_cast<float4 *>(q);
+    p[0] = make_float4(o.x, o.y, o.z, tmin);
+    p[1] = make_float4(d.x, d.y, d.z, tmax);
+}
+
+__device__ __forceinline__ uint32_t warp_alloc(bool want, uint32_t *counter) {
+    const unsigned active = __ballot_sync(0xffffffffu, want);
+    if (!want) return 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, uint32_t(__popc(active)));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(active & ((1u << lane) - 1));
+}
+
+__device__ __forceinline__ void warp_count_add(unsigned long long *dst, uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tilesX = (L.rw + 7) / 8;
+    const uint32_t tile = blockIdx.x * (kBlock / 32) + warp;
+    const uint32_t lx = (tile % tilesX) * 8 + (lane & 7), ly = (tile / tilesX) * 4 + (lane >> 3);
+    if (lx >= L.rw || ly >= L.rh) return;
+    const uint32_t x = L.x0 + lx, y = L.y0 + ly;
+    f3 o, d;
+    primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
+    TraceAccel A = resolve_tlas(tlas);
+    TraceHit h;
+    trace_ray<false, false>(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, 0, h,
+                            nullptr, status);
+    const uint32_t p = ly * L.rw + lx;
+    ws.hitA[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    ws.hitRec[p] = h.record;
+}
+
+// ------------------------------------------------------------------------------------------------ light helpers
+// evaluateDirectionalLight / evaluatePointLight without the visibility factor
+// (S/RaytracingCommon.hlsli:126-147); the shadow ray is queued instead of traced.
+struct LightEval {
+    f3 dirPre;      // color.rgb * color.a * NoL
+    f3 dirL;
+    f3 pointPre;    // color.rgb * color.a * NoL
+    f3 pointL;
+    float pointDist, falloff;
+};
+__device__ __forceinline__ LightEval eval_lights(const rt_per_frame_constants &f, f3 p, f3 n) {
+    LightEval e;
+    const rt_directional_light &dl = f.directionalLight;
+    e.dirL = normalize3(-mk3(dl.forwardDir[0], dl.forwardDir[1], dl.forwardDir[2]));
+    float NoL = saturatef(dot3(n, e.dirL));
+    e.dirPre = mk3(dl.color[0], dl.color[1], dl.color[2]) * dl.color[3] * NoL;
+    const rt_point_light &pl = f.pointLight;
+    f3 path = mk3(pl.worldPos[0], pl.worldPos[1], pl.worldPos[2]) - p;
+    e.pointDist = length3(path);
+    e.pointL = normalize3(path);
+    float NoLp = saturatef(dot3(n, e.pointL));
+    e.falloff = 1.0f / (2 * RT_M_PI * e.pointDist * e.pointDist);
+    e.pointPre = mk3(pl.color[0], pl.color[1], pl.color[2]) * pl.color[3] * NoLp;
+    return e;
+}
+
+__device__ __forceinline__ void write_pixel(const Launch &L, float *out, uint64_t pitch, uint32_t x, uint32_t y, f3 c, bool accumulate) {
+    float4 *px = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(out) + size_t(y) * pitch) + x;
+    float4 cur = make_float4(fmaxf(c.x, 0.0f), fmaxf(c.y, 0.0f), fmaxf(c.z, 0.0f), 1.0f);
+    if (accumulate) {  // RayGen: S/ProgressiveRaytracing.hlsl:36-38
+        const uint32_t n = L.f.cameraParams.accumCount;
+        float4 prev = *px;
+        const float fn = float(n), fn1 = float(n + 1);
+        cur = make_float4((fn * prev.x + cur.x) / fn1, (fn * prev.y + cur.y) / fn1, (fn * prev.z + cur.z) / fn1,
+                          (fn * prev.w + cur.w) / fn1);
+    }
+    *px = cur;
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+__global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+                                                          uint32_t n_recs, const float *env, uint32_t envSize, float *out0,
+                                                          uint64_t pitch0, float *out1, uint64_t pitch1,
+                                                          unsigned long long *rayCounts) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t P = L.rw * L.rh;
+    const bool inRange = p < P;
+    bool isHit = false;
+    float4 hA = make_float4(0, 0, 0, 0);
+    uint32_t x = 0, y = 0;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
+    if (inRange) {
+        x = L.x0 + p % L.rw, y = L.y0 + p / L.rw;
+        primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
+        hA = ws.hitA[p];
+        isHit = __float_as_uint(hA.w) != RT_NO_HIT;
+        if (!isHit) {  // PrimaryMiss
+            f3 c = sample_env(env, envSize, d) * L.f.options.environmentStrength;
+            if (L.realtime) {
+                write_pixel(L, out0, pitch0, x, y, c, false);
+                write_pixel(L, out1, pitch1, x, y, mk3(0, 0, 0), false);
+            } else {
+                write_pixel(L, out0, pitch0, x, y, c, true);
+            }
+        }
+    }
+    const uint32_t slot = warp_alloc(isHit, &ws.counters[0]);
+    uint32_t nShadow = 0, nSecondary = 0;
+    if (isHit) {
+        uint32_t rec = ws.hitRec[p];
+        if (rec >= n_recs) rec = 0;
+        const rt_hit_record_dev &R = recs[rec];
+        const uint32_t prim = __float_as_uint(hA.w);
+        const f3 N = normalize3(interpolate_normal(R, prim, hA.y, hA.z));
+        const f3 pos = o + hA.x * d;  // HitWorldPosition
+        const rt_debug_options &opt = L.f.options;
+        uint32_t flags = 0;
+        if (!L.realtime && opt.showAmbientOcclusionOnly) {
+            // evaluateAO: S/RaytracingCommon.hlsli:98-124 — 4 shadow rays, tMax 10
+            flags = SLOT_AO;
+            uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
+            float nol[4], pdf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f3 dir;
+                if (opt.cosineHemisphereSampling) {
+                    dir = cos_hemisphere(seed, N);
+                    nol[i] = saturatef(dot3(N, dir));
+                    pdf[i] = nol[i] / RT_M_PI;
+                } else {
+                    dir = uniform_hemisphere(seed, N);
+                    nol[i] = saturatef(dot3(N, dir));
+                    pdf[i] = 1.0f / (2.0f * RT_M_PI);
+                }
+                store_ray(&ws.shadowQ0[4 * size_t(slot) + i], pos, RT_RAY_EPSILON, dir, 10.0f);
+            }
+            nShadow = 4;
+            ws.S0[slot] = make_float4(nol[0], nol[1], nol[2], nol[3]);
+            ws.S1[slot] = make_float4(pdf[0], pdf[1], pdf[2], pdf[3]);
+        } else {
+            uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
+            LightEval le = eval_lights(L.f, pos, N);
+            bool useDir = true, usePoint = true;
+            if (!L.realtime && opt.debug == 2) {
+                if (next_rand(seed) < 0.5f) usePoint = false, flags |= SLOT_DEBUG2_DIR;
+                else useDir = false, flags |= SLOT_DEBUG2_POINT;
+            }
+            const size_t sq = size_t(L.shadowsPerHit) * slot;
+            store_ray(&ws.shadowQ0[sq + 0], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
+            store_ray(&ws.shadowQ0[sq + 1], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
+            for (uint32_t k = 2; k < L.shadowsPerHit; ++k) store_ray(&ws.shadowQ0[sq + k], pos, 0.0f, le.dirL, -1.0f);
+            nShadow = (useDir ? 1 : 0) + (usePoint ? 1 : 0);
+            // indirect diffuse: S/ProgressiveRaytracing.hlsl:57-78,107-110
+            float uniformNoL = 0.0f;
+            bool hasDiffuse = !L.realtime && !opt.noIndirectDiffuse;
+            f3 dDir = mk3(0, 0, 1);
+            if (hasDiffuse) {
+                if (opt.cosineHemisphereSampling) dDir = cos_hemisphere(seed, N);
+                else {
+                    dDir = uniform_hemisphere(seed, N);
+                    uniformNoL = saturatef(dot3(N, dDir));
+                    flags |= SLOT_UNIFORM;
+                }
+                flags |= SLOT_HAS_DIFFUSE;
+            }
+            store_ray(&ws.secQ[2 * size_t(slot) + 0], pos, RT_RAY_EPSILON, dDir, hasDiffuse ? RT_RAY_MAX_T : -1.0f);
+            // indirect specular: S/ProgressiveRaytracing.hlsl:114-131
+            f3 fres = mk3(0, 0, 0), sDir = mk3(0, 0, 1);
+            float pdf = 1.0f, brdf = 0.0f;
+            const bool hasSpec = (R.mat.type == 1 || R.mat.type == 2) && R.mat.reflectivity > 0.001f;
+            if (hasSpec) {
+                float exponent = expf((1.0f - R.mat.roughness) * 12.0f);
+                f3 mirror = reflect3(d, N);
+                sDir = phong_lobe(seed, mirror, exponent, pdf, brdf);
+                fres = fresnel_schlick(d, N, mk3(R.mat.specular[0], R.mat.specular[1], R.mat.specular[2]));
+                flags |= SLOT_HAS_SPEC;
+            }
+            store_ray(&ws.secQ[2 * size_t(slot) + 1], pos, RT_RAY_EPSILON, sDir, hasSpec ? RT_RAY_MAX_T : -1.0f);
+            nSecondary = (hasDiffuse ? 1 : 0) + (hasSpec ? 1 : 0);
+            ws.S0[slot] = make_float4(le.dirPre.x, le.dirPre.y, le.dirPre.z, le.falloff);
+            ws.S1[slot] = make_float4(le.pointPre.x, le.pointPre.y, le.pointPre.z, pdf);
+            ws.S2[slot] = make_float4(fres.x, fres.y, fres.z, brdf);
+            ws.S3[slot] = uniformNoL;
+        }
+        ws.slotInfo[slot] = make_uint4(p, rec, flags, 0);
+    }
+    warp_count_add(&rayCounts[0], inRange ? 1u : 0u);
+    warp_count_add(&rayCounts[1], nSecondary);
+    warp_count_add(&rayCounts[2], nShadow);
+}
+
+// ------------------------------------------------------------------------------------------------ K3 / K4 / K6
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult,
+                                                        float4 *hitA, uint32_t *hitRec, uint8_t *vis, uint32_t *status) {
+    const uint32_t n = count[0] * mult;
+    TraceAccel A = resolve_tlas(tlas);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+        const float4 a = rp[0], b = rp[1];
+        TraceHit h;
+        if (b.w < 0.0f) {  // inactive slot
+            if (ANY) vis[i] = 1;
+            else hitA[i] = make_float4(0, 0, 0, __uint_as_float(RT_NO_HIT)), hitRec[i] = 0xffffffffu;
+            continue;
+        }
+        if (ANY) {
+            // shootShadowRay: S/RaytracingCommon.hlsli:84-96 (ray contribution 1, miss index 1)
+            bool hit = trace_ray<true, false>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w,
+                                              RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER, 0xFF, 1, 0,
+                                              h, nullptr, status);
+            vis[i] = hit ? 0 : 1;
+        } else {
+            // shootSecondaryRay: flags 0 (no culling), contribution 0
+            trace_ray<false, false>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0xFF, 0, 0, h, nullptr, status);
+            hitA[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            hitRec[i] = h.record;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+// Depth-1 shade()/shadeAOV() of a secondary hit.  At depth 1 shootSecondaryRay returns 0 and shadow rays
+// are still traced (MAX_SHADOW_RAY_DEPTH 2); the Phong-lobe sample is still drawn (and its 0*brdf/pdf
+// term kept literally, so a zero pdf produces the same NaN as the shader).
+__global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+                                                            uint32_t n_recs, const float *env, uint32_t envSize,
+                                                            unsigned long long *rayCounts) {
+    const uint32_t n = ws.counters[0] * 2;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t r = base + threadIdx.x;
+        bool wantShadow = false;
+        f3 pos = mk3(0, 0, 0);
+        LightEval le;
+        uint32_t kind = 0, rec = 0;
+        f3 specTerm = mk3(0, 0, 0);
+        bool useDir = true, usePoint = true;
+        if (r < n) {
+            const float4 *rp = reinterpret_cast<const float4 *>(ws.secQ + r);
+            const float4 a = rp[0], b = rp[1];
+            if (b.w >= 0.0f) {
+                const float4 hA = ws.secHitA[r];
+                const f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+                if (__float_as_uint(hA.w) == RT_NO_HIT) {
+                    kind = 1;
+                    f3 c = sample_env(env, envSize, d) * L.f.options.environmentStrength;
+                    ws.T0[r] = make_float4(c.x, c.y, c.z, __uint_as_float(kind));
+                } else {
+                    kind = 2;
+                    rec = ws.secRec[r];
+                    if (rec >= n_recs) rec = 0;
+                    const rt_hit_record_dev &R = recs[rec];
+                    const f3 N = normalize3(interpolate_normal(R, __float_as_uint(hA.w), hA.y, hA.z));
+                    pos = o + hA.x * d;
+                    const uint32_t pix = ws.slotInfo[r >> 1].x;
+                    const uint32_t x = L.x0 + pix % L.rw, y = L.y0 + pix / L.rw;
+                    uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
+                    le = eval_lights(L.f, pos, N);
+                    if (!L.realtime && L.f.options.debug == 2) {
+                        if (next_rand(seed) < 0.5f) usePoint = false, kind |= 16u;
+                        else useDir = false, kind |= 32u;
+                    }
+                    f3 fres = mk3(0, 0, 0), spec = mk3(0, 0, 0);
+                    if ((R.mat.type == 1 || R.mat.type == 2) && R.mat.reflectivity > 0.001f) {
+                        float exponent = expf((1.0f - R.mat.roughness) * 12.0f);
+                        float pdf, brdf;
+                        f3 mirror = reflect3(d, N);
+                        (void)phong_lobe(seed, mirror, exponent, pdf, brdf);
+                        spec = spec + mk3(0, 0, 0) * brdf / pdf;
+                        fres = fresnel_schlick(d, N, mk3(R.mat.specular[0], R.mat.specular[1], R.mat.specular[2]));
+                    }
+                    specTerm = R.mat.reflectivity * spec * fres;
+                    wantShadow = true;
+                }
+            } else {
+                ws.T0[r] = make_float4(0, 0, 0, __uint_as_float(0u));
+            }
+        }
+        const uint32_t sh = warp_alloc(wantShadow, &ws.counters[1]);
+        if (wantShadow) {
+            store_ray(&ws.shadowQ1[2 * size_t(sh) + 0], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
+            store_ray(&ws.shadowQ1[2 * size_t(sh) + 1], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
+            ws.secShadow[r] = sh;
+            ws.T0[r] = make_float4(le.dirPre.x, le.dirPre.y, le.dirPre.z, __uint_as_float(kind));
+            ws.T1[r] = make_float4(le.pointPre.x, le.pointPre.y, le.pointPre.z, le.falloff);
+            ws.T2[r] = make_float4(specTerm.x, specTerm.y, specTerm.z, __uint_as_float(rec));
+        }
+        warp_count_add(&rayCounts[2], wantShadow ? ((useDir ? 1u : 0u) + (usePoint ? 1u : 0u)) : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+__device__ __forceinline__ f3 secondary_radiance(const Launch &L, const WS &ws, const rt_hit_record_dev *recs, uint32_t r) {
+    const float4 t0 = ws.T0[r];
+    const uint32_t kind = __float_as_uint(t0.w);
+    if ((kind & 15u) == 0) return mk3(0, 0, 0);
+    if ((kind & 15u) == 1) return mk3(t0.x, t0.y, t0.z);
+    const float4 t1 = ws.T1[r], t2 = ws.T2[r];
+    const uint32_t sh = ws.secShadow[r];
+    const float v0 = float(ws.vis1[2 * size_t(sh) + 0]), v1 = float(ws.vis1[2 * size_t(sh) + 1]);
+    const rt_material_params &m = recs[__float_as_uint(t2.w)].mat;
+    f3 direct = mk3(0, 0, 0);
+    const f3 dirC = mk3(t0.x, t0.y, t0.z) * v0;
+    const f3 pointC = mk3(t1.x, t1.y, t1.z) * v1 * t1.w;
+    if (kind & 16u) direct = direct + dirC * 2.0f;
+    else if (kind & 32u) direct = direct + pointC * 2.0f;
+    else {
+        direct = direct + dirC;
+        direct = direct + pointC;
+    }
+    const f3 albedo = mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
+    const f3 specTerm = mk3(t2.x, t2.y, t2.z);
+    if (L.realtime) return albedo * direct / RT_M_PI + specTerm;  // shadeAOV return value
+    const f3 diffuseComponent = (direct + mk3(0, 0, 0)) / RT_M_PI;
+    return (mk3(m.emissive[0], m.emissive[1], m.emissive[2]) * m.emissive[3] + albedo * diffuseComponent) + specTerm;
+}
+
+__global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs, float *out0,
+                                                    uint64_t pitch0, float *out1, uint64_t pitch1) {
+    const uint32_t n = ws.counters[0];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const uint4 info = ws.slotInfo[s];
+        const uint32_t x = L.x0 + info.x % L.rw, y = L.y0 + info.x / L.rw;
+        const rt_material_params &m = recs[info.y].mat;
+        const uint32_t flags = info.z;
+        f3 color;
+        if (flags & SLOT_AO) {
+            const float4 nol = ws.S0[s], pdf = ws.S1[s];
+            const uint8_t *v = ws.vis0 + 4 * size_t(s);
+            float vis = 0.0f;
+            vis += float(v[0]) * nol.x / pdf.x;
+            vis += float(v[1]) * nol.y / pdf.y;
+            vis += float(v[2]) * nol.z / pdf.z;
+            vis += float(v[3]) * nol.w / pdf.w;
+            const float ao = vis / 4.0f;
+            write_pixel(L, out0, pitch0, x, y, mk3(ao, ao, ao), true);
+            continue;
+        }
+        const float4 s0 = ws.S0[s], s1 = ws.S1[s], s2 = ws.S2[s];
+        const size_t sq = size_t(L.shadowsPerHit) * s;
+        const float v0 = float(ws.vis0[sq + 0]), v1 = float(ws.vis0[sq + 1]);
+        f3 direct = mk3(0, 0, 0);
+        const f3 dirC = mk3(s0.x, s0.y, s0.z) * v0;
+        const f3 pointC = mk3(s1.x, s1.y, s1.z) * v1 * s0.w;
+        if (flags & SLOT_DEBUG2_DIR) direct = direct + dirC * 2.0f;
+        else if (flags & SLOT_DEBUG2_POINT) direct = direct + pointC * 2.0f;
+        else {
+            direct = direct + dirC;
+            direct = direct + pointC;
+        }
+        f3 indirect = mk3(0, 0, 0);
+        if (flags & SLOT_HAS_DIFFUSE) {
+            const f3 rad = secondary_radiance(L, ws, recs, 2 * s + 0);
+            f3 c = mk3(0, 0, 0);
+            if (flags & SLOT_UNIFORM) {
+                const float pdfU = 1.0f / (2.0f * RT_M_PI);
+                c = c + rad * ws.S3[s] / pdfU;
+            } else {
+                c = c + rad * RT_M_PI;
+            }
+            indirect = indirect + c / 1.0f;
+        }
+        f3 spec = mk3(0, 0, 0);
+        const f3 fres = mk3(s2.x, s2.y, s2.z);
+        if (flags & SLOT_HAS_SPEC) {
+            const f3 refl = secondary_radiance(L, ws, recs, 2 * s + 1);
+            spec = spec + refl * s2.w / s1.w;
+        }
+        const f3 albedo = mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
+        if (L.realtime) {
+            // aov.directLighting / aov.indirectSpecular: S/RealtimeRaytracing.hlsl:95-100
+            write_pixel(L, out0, pitch0, x, y, albedo * direct / RT_M_PI, false);
+            write_pixel(L, out1, pitch1, x, y, m.reflectivity * spec * fres, false);
+            continue;
+        }
+        const rt_debug_options &opt = L.f.options;
+        const f3 diffuseComponent = (direct + indirect) / RT_M_PI;
+        if (opt.showIndirectDiffuseOnly) color = albedo * indirect / RT_M_PI;
+        else if (opt.showIndirectSpecularOnly) color = m.reflectivity * spec * fres;
+        else if (opt.showFresnelTerm) color = fres;
+        else if (opt.showGBufferAlbedoOnly) color = albedo;
+        else if (opt.showDirectLightingOnly) color = albedo * direct / RT_M_PI;
+        else color = (mk3(m.emissive[0], m.emissive[1], m.emissive[2]) * m.emissive[3] + albedo * diffuseComponent) + m.reflectivity * spec * fres;
+        write_pixel(L, out0, pitch0, x, y, color, true);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ standalone kernels
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_trace_rays(const void *tlas, const rt_ray *rays, uint64_t n, uint32_t rayFlags, uint32_t mask,
+                                                       rt_hit *hits, unsigned long long *stats, uint32_t *status) {
+    TraceAccel A = resolve_tlas(tlas);
+    TraceCtr c{0, 0, 0, 0};
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+        const float4 a = rp[0], b = rp[1];
+        TraceHit h;
+        if (rayFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH)
+            trace_ray<true, STATS>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, rayFlags, mask, 0, 0, h, &c, status);
+        else
+            trace_ray<false, STATS>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, rayFlags, mask, 0, 0, h, &c, status);
+        uint4 *hp = reinterpret_cast<uint4 *>(hits + i);
+        hp[0] = make_uint4(__float_as_uint(h.t), __float_as_uint(h.u), __float_as_uint(h.v), h.prim);
+        hp[1] = make_uint4(h.inst_index, h.geom_index, h.inst_id, h.leaf_slot);
+    }
+    if (STATS) {
+        atomicAdd(&stats[1], (unsigned long long)c.internal);
+        atomicAdd(&stats[2], (unsigned long long)c.leaf);
+        atomicAdd(&stats[3], (unsigned long long)c.inst);
+        atomicMax(&stats[4], (unsigned long long)c.max_stack);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)n);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_primary_rays(const __grid_constant__ Launch L, rt_ray *rays) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L.width * L.height) return;
+    f3 o, d;
+    primary_ray(L.f, L.width, L.height, p % L.width, p / L.width, L.jitterScale, o, d);
+    store_ray(rays + p, o, 0.0f, d, RT_RAY_MAX_T);
+}
+
+__global__ void k_scale(float *buf, uint64_t n, float s) {
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) buf[i] *= s;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws) {
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) {
+        uint64_t r = o;
+        o = align_up(o + bytes, 256);
+        return r;
+    };
+    const uint64_t oHitA = take(16 * P), oHitRec = take(4 * P), oCnt = take(256), oSlot = take(16 * P), oS0 = take(16 * P),
+                   oS1 = take(16 * P), oS2 = take(16 * P), oS3 = take(4 * P), oSQ0 = take(32 * 4 * P), oV0 = take(4 * P),
+                   oSec = take(32 * 2 * P), oSecH = take(16 * 2 * P), oSecR = take(4 * 2 * P), oSecS = take(4 * 2 * P),
+                   oT0 = take(16 * 2 * P), oT1 = take(16 * 2 * P), oT2 = take(16 * 2 * P), oSQ1 = take(32 * 4 * P), oV1 = take(4 * P);
+    if (ctx->ws.bytes < o) {
+        if (ctx->ws.base) {
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            RT_CUDA(cudaFree(ctx->ws.base));
+            ctx->ws.base = nullptr;
+            ctx->ws.bytes = 0;
+        }
+        RT_CUDA(cudaMalloc(&ctx->ws.base, o));
+        ctx->ws.bytes = o;
+    }
+    uint8_t *b = static_cast<uint8_t *>(ctx->ws.base);
+    ws.hitA = (float4 *)(b + oHitA), ws.hitRec = (uint32_t *)(b + oHitRec), ws.counters = (uint32_t *)(b + oCnt);
+    ws.slotInfo = (uint4 *)(b + oSlot), ws.S0 = (float4 *)(b + oS0), ws.S1 = (float4 *)(b + oS1), ws.S2 = (float4 *)(b + oS2);
+    ws.S3 = (float *)(b + oS3), ws.shadowQ0 = (rt_ray *)(b + oSQ0), ws.vis0 = b + oV0, ws.secQ = (rt_ray *)(b + oSec);
+    ws.secHitA = (float4 *)(b + oSecH), ws.secRec = (uint32_t *)(b + oSecR), ws.secShadow = (uint32_t *)(b + oSecS);
+    ws.T0 = (float4 *)(b + oT0), ws.T1 = (float4 *)(b + oT1), ws.T2 = (float4 *)(b + oT2), ws.shadowQ1 = (rt_ray *)(b + oSQ1);
+    ws.vis1 = b + oV1;
+    return RT_OK;
+}
+
+int upload_records(rt_program *prog) {
+    if (!prog->dirty) return RT_OK;
+    rt_context *ctx = prog->ctx;
+    if (prog->n_recs) {
+        RT_CUDA(cudaMemcpyAsync(prog->dev_recs, prog->host_recs, sizeof(rt_hit_record_dev) * prog->n_recs, cudaMemcpyHostToDevice, ctx->stream));
+        // host_recs is pageable: the copy is staged before the call returns, so later edits are safe
+    }
+    prog->dirty = false;
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t x1,
+                            uint32_t y1) {
+    RT_REQUIRE(ctx && prog && prog->ctx == ctx, "context/program");
+    RT_REQUIRE(ctx->tlas != nullptr, "no TLAS bound (rt_set_tlas)");
+    RT_REQUIRE(ctx->output[0] != nullptr, "no output bound to slot 0 (rt_set_output)");
+    RT_REQUIRE(prog->kind != RT_PROGRAM_REALTIME || ctx->output[1] != nullptr, "realtime program needs output slot 1");
+    RT_REQUIRE(x0 < x1 && y0 < y1 && x1 <= width && y1 <= height, "pixel rectangle");
+    RT_REQUIRE(ctx->pitch[0] >= uint64_t(width) * 16, "output pitch");
+    RT_REQUIRE(prog->n_recs > 0, "no hit records bound (rt_bindings_set_hit_record)");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const bool realtime = prog->kind == RT_PROGRAM_REALTIME;
+    // RayGen early-out: S/ProgressiveRaytracing.hlsl:13-15
+    if (!realtime && ctx->frame.cameraParams.accumCount >= ctx->frame.options.maxIterations) return RT_OK;
+
+    Launch L;
+    L.f = ctx->frame;
+    L.width = width, L.height = height;
+    L.x0 = x0, L.y0 = y0, L.rw = x1 - x0, L.rh = y1 - y0;
+    L.jitterScale = realtime ? 10.0f : 30.0f;  // S/ProgressiveRaytracing.hlsl:26, S/RealtimeRaytracing.hlsl:34
+    L.realtime = realtime ? 1u : 0u;
+    L.shadowsPerHit = (!realtime && L.f.options.showAmbientOcclusionOnly) ? 4u : 2u;
+    const uint64_t P = uint64_t(L.rw) * L.rh;
+    WS ws;
+    int rc = ensure_workspace(ctx, P, ws);
+    if (rc) return rc;
+    rc = upload_records(prog);
+    if (rc) return rc;
+
+    cudaStream_t st = ctx->stream;
+    const bool timing = ctx->timing;
+    if (timing && !ctx->ev_ready) {
+        for (auto &e : ctx->ev) RT_CUDA(cudaEventCreate(&e));
+        ctx->ev_ready = true;
+    }
+    RT_CUDA(cudaMemsetAsync(ws.counters, 0, 256, st));
+    const uint32_t tiles = ((L.rw + 7) / 8) * ((L.rh + 3) / 4);
+    const int qgrid = ctx->num_sms * 16;
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[0], st));
+    k_primary<<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status);
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[1], st));
+    k_shade_primary<<<rt_div_up(P, kBlock), kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
+                                                             ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
+    k_trace_queue<false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status);
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
+    k_trace_queue<true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status);
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
+    k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
+    k_trace_queue<true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status);
+    if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
+    k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
+    ctx->launches += 7;
+    RT_LAUNCH_CHECK();
+    if (timing) {
+        RT_CUDA(cudaEventSynchronize(ctx->ev[6]));
+        float ms = 0;
+        RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        ctx->t_primary += ms;
+        RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        ctx->t_secondary += ms;
+        RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+        ctx->t_shadow += ms;
+        RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+        ctx->t_shadow += ms;
+    }
+    return RT_OK;
+}
+
+int rt_dispatch_rays(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t /*depth*/) {
+    // Depth is ignored exactly as the compute fallback does (FL/UberShaderRayTracingProgram.cpp:268-272).
+    return rt_dispatch_rays_region(ctx, prog, width, height, 0, 0, width, height);
+}
+
+static int trace_common(rt_context *ctx, const void *tlas, const rt_ray *rays, uint64_t n, uint32_t flags, uint32_t mask, rt_hit *hits,
+                        rt_trace_stats *stats) {
+    RT_REQUIRE(ctx && tlas && (n == 0 || (rays && hits)), "null argument");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return RT_OK;
+    const int grid = int(std::min<uint64_t>(rt_div_up(n, kBlock), uint64_t(ctx->num_sms) * 16));
+    if (stats)
+        k_trace_rays<true><<<grid, kBlock, 0, ctx->stream>>>(tlas, rays, n, flags, mask, hits, reinterpret_cast<unsigned long long *>(stats), ctx->status);
+    else
+        k_trace_rays<false><<<grid, kBlock, 0, ctx->stream>>>(tlas, rays, n, flags, mask, hits, nullptr, ctx->status);
+    ctx->launches++;
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+int rt_trace_rays(rt_context *ctx, const void *tlas, const rt_ray *rays, uint64_t n, uint32_t flags, uint32_t mask, rt_hit *hits) {
+    return trace_common(ctx, tlas, rays, n, flags, mask, hits, nullptr);
+}
+int rt_trace_rays_stats(rt_context *ctx, const void *tlas, const rt_ray *rays, uint64_t n, uint32_t flags, uint32_t mask, rt_hit *hits,
+                        rt_trace_stats *stats_dev) {
+    RT_REQUIRE(stats_dev != nullptr, "stats");
+    return trace_common(ctx, tlas, rays, n, flags, mask, hits, stats_dev);
+}
+
+int rt_generate_primary_rays(rt_context *ctx, const rt_per_frame_constants *frame, uint32_t width, uint32_t height, float jitter_scale,
+                             rt_ray *rays) {
+    RT_REQUIRE(ctx && frame && rays && width && height, "null argument");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    Launch L{};
+    L.f = *frame;
+    L.width = width, L.height = height, L.rw = width, L.rh = height;
+    L.jitterScale = jitter_scale;
+    k_primary_rays<<<rt_div_up(uint64_t(width) * height, kBlock), kBlock, 0, ctx->stream>>>(L, rays);
+    ctx->launches++;
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+int rt_scale_buffer(rt_context *ctx, float *buf, uint64_t count, float scale) {
+    RT_REQUIRE(ctx && (buf || count == 0), "null argument");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (count == 0) return RT_OK;
+    k_scale<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(buf, count, scale);
+    ctx->launches++;
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+}  // extern "C"

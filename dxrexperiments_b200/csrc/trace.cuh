@@ -1,0 +1,266 @@
+// trace.cuh — two-level BVH2 traversal for sm_100a (pure SIMT; B200 has no RT cores).
+//
+// Semantics follow Fallback_TraceRay / Traverse (externals/D3D12RaytracingFallback/src/TraverseShader.hlsli:21-73,
+// TraverseFunction.hlsli:520-799): depth-first, children tested when their parent is visited, near child
+// first (left on ties), closest hit committed when t < tCommitted && t > tMin, optional
+// ACCEPT_FIRST_HIT_AND_END_SEARCH.  What differs is HOW:
+//   * nodes carry both child boxes (64 B, four 16-byte loads) so an internal visit is one dependent fetch
+//     instead of the reference's three; leaves are referenced directly from their parent, so a leaf visit
+//     is three 16-byte loads of a 48-byte triangle that already holds its metadata;
+//   * the near child stays in a register instead of being pushed and popped;
+//   * the per-thread stack is 64 entries (the reference's 32 overflows silently on deep LBVHs).
+// The ray/triangle arithmetic is written with unfused intrinsics so t and barycentrics are bit-identical to
+// the CPU restatement; the ray/box test uses fused multiply-adds exactly as the restatement does.
+#pragma once
+#include "common.cuh"
+
+#define RT_STACK_SIZE 64
+
+struct TraceAccel {  // resolved view of a TLAS result buffer
+    const rt_wide_node *wide;
+    const rt_packed_instance *inst;
+    uint32_t root_ref, count;
+    float root_c[3], root_h[3];
+};
+
+struct TraceHit {
+    float t, u, v;
+    uint32_t prim, inst_index, geom_index, inst_id, leaf_slot, record;  // prim == RT_NO_HIT on miss
+};
+
+struct TraceCtr {
+    uint32_t internal, leaf, inst, max_stack;
+};
+
+struct RayPre {  // GetRayData: TraverseFunction.hlsli:438-460
+    float ox, oy, oz;
+    float ix, iy, iz;     // 1/d
+    float oix, oiy, oiz;  // o * (1/d)
+    float sx, sy, sz;     // shear
+    int kx, ky, kz;
+};
+
+__device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+__device__ __forceinline__ RayPre make_ray_pre(float ox, float oy, float oz, float dx, float dy, float dz) {
+    RayPre r;
+    r.ox = ox, r.oy = oy, r.oz = oz;
+    r.ix = div_(1.0f, dx), r.iy = div_(1.0f, dy), r.iz = div_(1.0f, dz);
+    r.oix = mul_(ox, r.ix), r.oiy = mul_(oy, r.iy), r.oiz = mul_(oz, r.iz);
+    float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    int kz = (ax > ay && ax > az) ? 0 : (ay > az ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    float dk = pick(dx, dy, dz, kz);
+    if (dk < 0.0f) {
+        int t = kx;
+        kx = ky;
+        ky = t;
+    }
+    r.kx = kx, r.ky = ky, r.kz = kz;
+    r.sx = div_(pick(dx, dy, dz, kx), dk);
+    r.sy = div_(pick(dx, dy, dz, ky), dk);
+    r.sz = div_(1.0f, dk);
+    return r;
+}
+
+// RayBoxTest: TraverseFunction.hlsli:173-191 (fused multiply-adds, as pinned in oracle_trace.cpp).
+__device__ __forceinline__ bool ray_box(float &tOut, float tClosest, const RayPre &r, float cx, float cy, float cz, float hx,
+                                        float hy, float hz) {
+    float aix = fabsf(r.ix), aiy = fabsf(r.iy), aiz = fabsf(r.iz);
+    float rx = __fmaf_rn(cx, r.ix, -r.oix), ry = __fmaf_rn(cy, r.iy, -r.oiy), rz = __fmaf_rn(cz, r.iz, -r.oiz);
+    float maxx = __fmaf_rn(hx, aix, rx), maxy = __fmaf_rn(hy, aiy, ry), maxz = __fmaf_rn(hz, aiz, rz);
+    float minx = __fmaf_rn(-hx, aix, rx), miny = __fmaf_rn(-hy, aiy, ry), minz = __fmaf_rn(-hz, aiz, rz);
+    float tmin = fmaxf(fmaxf(minx, miny), minz);
+    float tmax = fminf(fminf(maxx, maxy), maxz);
+    tOut = fmaxf(tmin, 0.0f);
+    return tOut < fminf(tmax, tClosest);
+}
+
+// RayTriangleIntersect: TraverseFunction.hlsli:200-282 (Woop/Benthin/Wald 2013), unfused arithmetic.
+// cull: 0 none, 1 cull back-facing, 2 cull front-facing (already resolved against the instance flags).
+__device__ __forceinline__ bool ray_triangle(float &hitT, float &bu, float &bv, int cull, const RayPre &r, const float4 &p0,
+                                             const float4 &p1, float v2z) {
+    // p0 = (v0.x, v0.y, v0.z, v1.x)  p1 = (v1.y, v1.z, v2.x, v2.y)
+    float a0x = sub_(p0.x, r.ox), a0y = sub_(p0.y, r.oy), a0z = sub_(p0.z, r.oz);
+    float b0x = sub_(p0.w, r.ox), b0y = sub_(p1.x, r.oy), b0z = sub_(p1.y, r.oz);
+    float c0x = sub_(p1.z, r.ox), c0y = sub_(p1.w, r.oy), c0z = sub_(v2z, r.oz);
+    float Ax = pick(a0x, a0y, a0z, r.kx), Ay = pick(a0x, a0y, a0z, r.ky), Az = pick(a0x, a0y, a0z, r.kz);
+    float Bx = pick(b0x, b0y, b0z, r.kx), By = pick(b0x, b0y, b0z, r.ky), Bz = pick(b0x, b0y, b0z, r.kz);
+    float Cx = pick(c0x, c0y, c0z, r.kx), Cy = pick(c0x, c0y, c0z, r.ky), Cz = pick(c0x, c0y, c0z, r.kz);
+    Ax = sub_(Ax, mul_(r.sx, Az)), Ay = sub_(Ay, mul_(r.sy, Az));
+    Bx = sub_(Bx, mul_(r.sx, Bz)), By = sub_(By, mul_(r.sy, Bz));
+    Cx = sub_(Cx, mul_(r.sx, Cz)), Cy = sub_(Cy, mul_(r.sy, Cz));
+    float U = sub_(mul_(Cx, By), mul_(Cy, Bx));
+    float V = sub_(mul_(Ax, Cy), mul_(Ay, Cx));
+    float W = sub_(mul_(Bx, Ay), mul_(By, Ax));
+    float det = add_(add_(U, V), W);
+    if (cull == 2) {
+        if (U > 0.0f || V > 0.0f || W > 0.0f) return false;
+    } else if (cull == 1) {
+        if (U < 0.0f || V < 0.0f || W < 0.0f) return false;
+    } else {
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    }
+    if (det == 0.0f) return false;
+    Az = mul_(r.sz, Az), Bz = mul_(r.sz, Bz), Cz = mul_(r.sz, Cz);
+    float T = add_(add_(mul_(U, Az), mul_(V, Bz)), mul_(W, Cz));
+    if (cull == 2) {
+        if (T > 0.0f || T < mul_(hitT, det)) return false;
+    } else if (cull == 1) {
+        if (T < 0.0f || T > mul_(hitT, det)) return false;
+    } else {
+        float s = fabsf(T);
+        if ((T > 0.0f) != (det > 0.0f)) s = -s;
+        if (s < 0.0f || s > mul_(hitT, fabsf(det))) return false;
+    }
+    float rcpDet = div_(1.0f, det);
+    bu = mul_(V, rcpDet);
+    bv = mul_(W, rcpDet);
+    hitT = mul_(T, rcpDet);
+    return true;
+}
+
+__device__ __forceinline__ TraceAccel resolve_tlas(const void *tlas_result) {
+    const uint8_t *base = static_cast<const uint8_t *>(tlas_result);
+    const rt_bvh_offsets *off = reinterpret_cast<const rt_bvh_offsets *>(base);
+    const rt_ext_header *e = reinterpret_cast<const rt_ext_header *>(base + align_up(off->totalSize, 64));
+    TraceAccel a;
+    a.wide = reinterpret_cast<const rt_wide_node *>(base + e->off_wide);
+    a.inst = reinterpret_cast<const rt_packed_instance *>(base + e->off_leaf);
+    a.root_ref = e->root_ref;
+    a.count = e->count;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.root_c[k] = e->root_center[k], a.root_h[k] = e->root_half[k];
+    return a;
+}
+
+#define RT_SENTINEL 0x7fffffffu  // never a valid internal index (indices are < 2^24)
+
+// Fallback_TraceRay without shader call-outs.  ANY = RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH.
+// rayContribution / geomMultiplier feed the hit-group record index exactly as TraverseFunction.hlsli:684-687.
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float oy, float oz, float tmin, float dx, float dy,
+                                          float dz, float tmax, uint32_t rayFlags, uint32_t mask, uint32_t rayContribution,
+                                          uint32_t geomMultiplier, TraceHit &hit, TraceCtr *ctr, uint32_t *status) {
+    hit.prim = RT_NO_HIT;
+    hit.t = tmax;
+    hit.u = hit.v = 0.0f;
+    hit.inst_index = hit.geom_index = hit.inst_id = hit.leaf_slot = hit.record = 0;
+    if (A.count == 0) return false;
+
+    uint32_t stack[RT_STACK_SIZE];
+    int sp = 0;
+    float tCur = tmax;
+
+    RayPre world = make_ray_pre(ox, oy, oz, dx, dy, dz);
+    RayPre cur = world;
+    const rt_wide_node *nodes = A.wide;
+    const rt_packed_tri *tris = nullptr;
+    bool bottom = false;
+    int blasBase = -1;  // stack height at which the current BLAS was entered
+    uint32_t instIndex = 0, instFlags = 0, instOffset = 0, instId = 0;
+    int cull = 0;
+
+    float tUnused;
+    if (!ray_box(tUnused, tCur, world, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2])) return false;
+
+    uint32_t ref = A.root_ref;
+    while (true) {
+        if (ref & RT_NODE_LEAF_FLAG) {
+            const uint32_t slot = ref & 0x00ffffffu;
+            if (!bottom) {
+                // TLAS leaf: TraverseFunction.hlsli:598-634
+                if (STATS) ctr->inst++;
+                const uint4 *ip = reinterpret_cast<const uint4 *>(A.inst + slot);
+                const uint4 m3 = __ldg(ip + 3);  // id|mask, hitgroup|flags, instance index, blas root ref
+                instIndex = m3.z;
+                instOffset = m3.y & 0x00ffffffu;
+                instId = m3.x & 0x00ffffffu;
+                ref = RT_SENTINEL;
+                if ((m3.x >> 24) & mask) {
+                    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(ip));
+                    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(ip + 1));
+                    const float4 r2 = __ldg(reinterpret_cast<const float4 *>(ip + 2));
+                    const uint4 m4 = __ldg(ip + 4);
+                    instFlags = m3.y >> 24;
+                    // cull mode: TraverseFunction.hlsli:215-220
+                    {
+                        bool useCulling = !(instFlags & RT_INSTANCE_FLAG_TRIANGLE_CULL_DISABLE);
+                        bool flip = (instFlags & RT_INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE) != 0;
+                        uint32_t backFlag = flip ? RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES : RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES;
+                        uint32_t frontFlag = flip ? RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES : RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES;
+                        cull = (useCulling && (rayFlags & frontFlag)) ? 2 : ((useCulling && (rayFlags & backFlag)) ? 1 : 0);
+                    }
+                    const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                    f3 o2 = xform_point(m, mk3(ox, oy, oz));
+                    f3 d2 = xform_vector(m, mk3(dx, dy, dz));
+                    cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                    nodes = reinterpret_cast<const rt_wide_node *>(uintptr_t(uint64_t(m4.x) | (uint64_t(m4.y) << 32)));
+                    tris = reinterpret_cast<const rt_packed_tri *>(uintptr_t(uint64_t(m4.z) | (uint64_t(m4.w) << 32)));
+                    bottom = true;
+                    blasBase = sp;
+                    ref = m3.w;  // BLAS root (pushed without a box test, as the reference does)
+                }
+            } else {
+                // BLAS leaf: TraverseFunction.hlsli:635-735
+                if (STATS) ctr->leaf++;
+                const float4 *tp = reinterpret_cast<const float4 *>(tris + slot);
+                const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                const uint32_t gflags = __float_as_uint(p2.w);
+                bool opaque = (gflags & RT_GEOMETRY_FLAG_OPAQUE) != 0;  // IsOpaque(): :119-134
+                if (instFlags & RT_INSTANCE_FLAG_FORCE_OPAQUE) opaque = true;
+                else if (instFlags & RT_INSTANCE_FLAG_FORCE_NON_OPAQUE) opaque = false;
+                if (rayFlags & RT_RAY_FLAG_FORCE_OPAQUE) opaque = true;
+                else if (rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
+                const bool culled = (opaque && (rayFlags & RT_RAY_FLAG_CULL_OPAQUE)) || (!opaque && (rayFlags & RT_RAY_FLAG_CULL_NON_OPAQUE));
+                ref = RT_SENTINEL;
+                if (!culled) {
+                    float t0 = tCur, bu, bv;
+                    if (ray_triangle(t0, bu, bv, cull, cur, p0, p1, p2.x) && t0 < tCur && t0 > tmin) {
+                        tCur = t0;
+                        hit.t = t0, hit.u = bu, hit.v = bv;
+                        hit.prim = __float_as_uint(p2.y);
+                        hit.geom_index = __float_as_uint(p2.z);
+                        hit.inst_index = instIndex;
+                        hit.inst_id = instId;
+                        hit.leaf_slot = slot;
+                        hit.record = rayContribution + hit.geom_index * geomMultiplier + instOffset;
+                        if (ANY) return true;
+                    }
+                }
+            }
+        } else {
+            // internal node: TraverseFunction.hlsli:737-786 with both child boxes in the node
+            if (STATS) ctr->internal++;
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            float lt, rt;
+            const bool lh = ray_box(lt, tCur, cur, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z);
+            const bool rh = ray_box(rt, tCur, cur, n2.x, n2.y, n2.z, n3.x, n3.y, n3.z);
+            const uint32_t l = __float_as_uint(n0.w), r = __float_as_uint(n1.w);
+            if (lh && rh) {
+                const bool rightFirst = rt < lt;  // ties: left first
+                if (sp < RT_STACK_SIZE) stack[sp++] = rightFirst ? l : r;
+                else atomicOr(status, 1u);
+                if (STATS) ctr->max_stack = max(ctr->max_stack, uint32_t(sp) + 1);
+                ref = rightFirst ? r : l;
+            } else if (lh || rh) {
+                ref = rh ? r : l;
+            } else {
+                ref = RT_SENTINEL;
+            }
+        }
+        if (ref == RT_SENTINEL) {
+            // pop; leaving a BLAS restores the world-space ray (TraverseFunction.hlsli:788-791)
+            if (bottom && sp == blasBase) {
+                bottom = false;
+                cur = world;
+                nodes = A.wide;
+                blasBase = -1;
+            }
+            if (sp == 0) break;
+            ref = stack[--sp];
+        }
+    }
+    return hit.prim != RT_NO_HIT;
+}

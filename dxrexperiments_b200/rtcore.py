@@ -1,0 +1,375 @@
+"""ctypes binding of the C ABI in ``include/rt_core.h`` (``librt_core.so``).
+
+This is the only way Python reaches the CUDA kernels.  There is no fallback of any kind: if the shared
+library is missing, or was built without every symbol the header declares, importing fails; if no CUDA
+device is present, :class:`Context` raises :class:`RtError`.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from . import types as T
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "librt_core.so")
+HEADER_PATH = os.path.join(_DIR, "..", "include", "rt_core.h")
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"rt_core error {code}: {message}")
+        self.code = code
+
+
+def declared_symbols(header_path: str = HEADER_PATH):
+    """Every function name declared in rt_core.h (used by the symbol-coverage test)."""
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", text)))
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C dxrexperiments_b200/csrc).  rt_core has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing:
+        raise ImportError(f"{LIB_PATH} lacks symbols declared in rt_core.h: {missing}")
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    pp = C.POINTER(vp)
+    sig = {
+        "rt_last_error": (C.c_char_p, []),
+        "rt_version": (C.c_char_p, []),
+        "rt_context_create": (i32, [i32, pp]),
+        "rt_context_destroy": (i32, [vp]),
+        "rt_context_set_stream": (i32, [vp, vp]),
+        "rt_sync": (i32, [vp]),
+        "rt_get_status": (i32, [vp]),
+        "rt_launch_count": (u64, [vp]),
+        "rt_malloc": (i32, [vp, u64, pp]),
+        "rt_free": (i32, [vp, vp]),
+        "rt_memset": (i32, [vp, vp, i32, u64]),
+        "rt_upload": (i32, [vp, vp, vp, u64]),
+        "rt_download": (i32, [vp, vp, vp, u64]),
+        "rt_host_alloc_pinned": (i32, [u64, pp]),
+        "rt_host_free_pinned": (i32, [vp]),
+        "rt_blas_prebuild": (i32, [vp, vp, u32, u32, vp]),
+        "rt_blas_build": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
+        "rt_tlas_prebuild": (i32, [vp, u32, u32, vp]),
+        "rt_tlas_build": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
+        "rt_build_scratch_layout": (i32, [u32, i32, vp]),
+        "rt_blob_bytes": (u64, [u32, i32]),
+        "rt_program_create": (i32, [vp, i32, u32, u32, pp]),
+        "rt_program_destroy": (i32, [vp]),
+        "rt_bindings_set_hit_record": (i32, [vp, u32, u32, vp, vp, vp]),
+        "rt_bindings_set_miss_record": (i32, [vp, u32, vp, u32]),
+        "rt_set_frame_constants": (i32, [vp, vp]),
+        "rt_set_output": (i32, [vp, u32, vp, u64]),
+        "rt_set_tlas": (i32, [vp, vp]),
+        "rt_dispatch_rays": (i32, [vp, vp, u32, u32, u32]),
+        "rt_dispatch_rays_region": (i32, [vp, vp, u32, u32, u32, u32, u32, u32]),
+        "rt_get_ray_counts": (i32, [vp, vp, i32]),
+        "rt_enable_stage_timing": (i32, [vp, i32]),
+        "rt_get_stage_timing": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), i32]),
+        "rt_denoise": (i32, [vp, vp, vp, vp, vp, u32, u32, vp]),
+        "rt_trace_rays": (i32, [vp, vp, vp, u64, u32, u32, vp]),
+        "rt_trace_rays_stats": (i32, [vp, vp, vp, u64, u32, u32, vp, vp]),
+        "rt_generate_primary_rays": (i32, [vp, vp, u32, u32, C.c_float, vp]),
+        "rt_scale_buffer": (i32, [vp, vp, u64, C.c_float]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class ScratchLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("scene_aabb", "morton_codes", "sorted_codes", "sorted_indices", "hierarchy",
+                                          "primitives", "metadata", "total")]
+
+
+def check(code):
+    if code != 0:
+        raise RtError(code, lib.rt_last_error().decode())
+
+
+class Buffer:
+    """A device allocation owned by a context."""
+
+    def __init__(self, ctx, nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib.rt_malloc(ctx.handle, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, host: np.ndarray, offset: int = 0):
+        host = np.ascontiguousarray(host)
+        assert offset + host.nbytes <= self.nbytes
+        check(lib.rt_upload(self.ctx.handle, self.ptr + offset, host.ctypes.data, host.nbytes))
+        self.ctx.sync()  # host is pageable here; keep it alive until the copy is done
+        return self
+
+    def download(self, dtype=np.uint8, count=None, offset: int = 0) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        if count is None:
+            count = (self.nbytes - offset) // dtype.itemsize
+        out = np.empty(count, dtype=dtype)
+        check(lib.rt_download(self.ctx.handle, out.ctypes.data, self.ptr + offset, out.nbytes))
+        return out
+
+    def zero(self):
+        check(lib.rt_memset(self.ctx.handle, self.ptr, 0, self.nbytes))
+        return self
+
+    def free(self):
+        if self.ptr:
+            lib.rt_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx.handle:
+                self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device: int = 0, stream: int = None):
+        h = C.c_void_p()
+        check(lib.rt_context_create(device, C.byref(h)))
+        self.handle = h.value
+        self.device = device
+        if stream is not None:
+            check(lib.rt_context_set_stream(self.handle, stream))
+
+    def close(self):
+        if self.handle:
+            lib.rt_context_destroy(self.handle)
+            self.handle = None
+
+    def sync(self):
+        check(lib.rt_sync(self.handle))
+
+    def status(self):
+        check(lib.rt_get_status(self.handle))
+
+    def launches(self) -> int:
+        return int(lib.rt_launch_count(self.handle))
+
+    def alloc(self, nbytes) -> Buffer:
+        return Buffer(self, nbytes)
+
+    def upload(self, host: np.ndarray) -> Buffer:
+        host = np.ascontiguousarray(host)
+        return Buffer(self, max(host.nbytes, 16)).upload(host)
+
+    # ---------------------------------------------------------------- acceleration structures
+    def build_blas(self, geoms, build_flags: int = 0, keep_scratch: bool = False):
+        """geoms: list of dicts {vertices: Buffer|ptr, vertex_count, stride, indices: Buffer|ptr|None, index_count,
+        index_format, transform: Buffer|ptr|None, flags}."""
+        descs = (T.GeometryDesc * len(geoms))()
+        for d, g in zip(descs, geoms):
+            d.vertex_buffer = _ptr(g["vertices"])
+            d.vertex_count = g["vertex_count"]
+            d.vertex_stride_bytes = g.get("stride", 24)
+            d.index_buffer = _ptr(g.get("indices"))
+            d.index_count = g.get("index_count", 0)
+            d.index_format = g.get("index_format", 32 if g.get("indices") is not None else 0)
+            d.transform3x4 = _ptr(g.get("transform"))
+            d.flags = g.get("flags", T.GEOMETRY_FLAG_OPAQUE)
+        info = T.PrebuildInfo()
+        check(lib.rt_blas_prebuild(self.handle, descs, len(geoms), build_flags, C.byref(info)))
+        scratch = self.alloc(info.scratch_bytes)
+        result = self.alloc(info.result_bytes)
+        check(lib.rt_blas_build(self.handle, descs, len(geoms), build_flags, scratch.ptr, scratch.nbytes, result.ptr,
+                                result.nbytes))
+        n = sum((g.get("index_count", 0) if g.get("index_format", 32 if g.get("indices") is not None else 0) else
+                 g["vertex_count"]) // 3 for g in geoms)
+        acc = Accel(self, result, n, top=False, scratch=scratch if keep_scratch else None, keep=list(geoms))
+        if not keep_scratch:
+            self.sync()
+            scratch.free()
+        return acc
+
+    def build_blas_from_mesh(self, mesh, flags=T.GEOMETRY_FLAG_OPAQUE, keep_scratch=False):
+        vb = self.upload(mesh.vertices)
+        ib = self.upload(mesh.indices)
+        acc = self.build_blas([dict(vertices=vb, vertex_count=mesh.vertices.shape[0], stride=24, indices=ib,
+                                    index_count=mesh.indices.size, index_format=32, flags=flags)],
+                              keep_scratch=keep_scratch)
+        acc.vb, acc.ib = vb, ib
+        return acc
+
+    def build_tlas(self, blases, transforms, ids=None, masks=None, hit_groups=None, flags=None, build_flags: int = 0,
+                   keep_scratch: bool = False):
+        n = len(blases)
+        descs = (T.InstanceDesc * max(n, 1))()
+        for i in range(n):
+            tr = np.asarray(transforms[i], np.float32).reshape(12)
+            descs[i].transform[:] = tr.tolist()
+            iid = i if ids is None else ids[i]
+            mask = 0xFF if masks is None else masks[i]
+            hg = 2 * i if hit_groups is None else hit_groups[i]
+            fl = 0 if flags is None else flags[i]
+            descs[i].instance_id_and_mask = (iid & 0xFFFFFF) | ((mask & 0xFF) << 24)
+            descs[i].hit_group_and_flags = (hg & 0xFFFFFF) | ((fl & 0xFF) << 24)
+            descs[i].blas = blases[i].result.ptr
+        host = np.frombuffer(bytes(descs), dtype=np.uint8)[: 64 * n] if n else np.zeros(0, np.uint8)
+        dev_descs = self.upload(host) if n else None
+        info = T.PrebuildInfo()
+        check(lib.rt_tlas_prebuild(self.handle, n, build_flags, C.byref(info)))
+        scratch = self.alloc(info.scratch_bytes)
+        result = self.alloc(info.result_bytes)
+        check(lib.rt_tlas_build(self.handle, dev_descs.ptr if n else None, n, build_flags, scratch.ptr, scratch.nbytes,
+                                result.ptr, result.nbytes))
+        acc = Accel(self, result, n, top=True, scratch=scratch if keep_scratch else None, keep=[dev_descs, list(blases)])
+        if not keep_scratch:
+            self.sync()
+            scratch.free()
+        return acc
+
+    # ---------------------------------------------------------------- wavefront primitives
+    def trace(self, tlas, rays: np.ndarray, ray_flags: int = 0, mask: int = 0xFF, stats: bool = False):
+        rays = np.ascontiguousarray(rays, dtype=T.RAY_DTYPE)
+        n = rays.shape[0]
+        d_rays = self.upload(rays.view(np.uint8).reshape(-1))
+        d_hits = self.alloc(max(32 * n, 32))
+        if stats:
+            d_stats = self.alloc(64).zero()
+            check(lib.rt_trace_rays_stats(self.handle, tlas.result.ptr, d_rays.ptr, n, ray_flags, mask, d_hits.ptr,
+                                          d_stats.ptr))
+            st = d_stats.download(np.uint64, 5)
+        else:
+            check(lib.rt_trace_rays(self.handle, tlas.result.ptr, d_rays.ptr, n, ray_flags, mask, d_hits.ptr))
+            st = None
+        hits = d_hits.download(T.HIT_DTYPE, n)
+        self.status()
+        return (hits, st) if stats else hits
+
+    def primary_rays(self, frame, width, height, jitter_scale=30.0) -> np.ndarray:
+        d = self.alloc(32 * width * height)
+        check(lib.rt_generate_primary_rays(self.handle, C.byref(frame), width, height, jitter_scale, d.ptr))
+        return d.download(T.RAY_DTYPE, width * height)
+
+    def denoise(self, direct: np.ndarray, spec: np.ndarray, params: T.DenoiserParams):
+        h, w = direct.shape[:2]
+        d_dir = self.upload(np.ascontiguousarray(direct, np.float32).reshape(-1))
+        d_spec = self.upload(np.ascontiguousarray(spec, np.float32).reshape(-1))
+        d_tmp = self.alloc(16 * w * h)
+        d_out = self.alloc(16 * w * h)
+        check(lib.rt_denoise(self.handle, d_dir.ptr, d_spec.ptr, d_tmp.ptr, d_out.ptr, w, h, C.byref(params)))
+        out = d_out.download(np.float32).reshape(h, w, 4)
+        tmp = d_tmp.download(np.float32).reshape(h, w, 4)
+        return out, tmp
+
+    def ray_counts(self, reset=False) -> T.RayCounts:
+        c = T.RayCounts()
+        check(lib.rt_get_ray_counts(self.handle, C.byref(c), 1 if reset else 0))
+        return c
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, Buffer):
+        return x.ptr
+    return int(x)
+
+
+class Accel:
+    """A built acceleration structure: the result buffer plus (optionally) the scratch of its build."""
+
+    def __init__(self, ctx, result: Buffer, n: int, top: bool, scratch=None, keep=None):
+        self.ctx, self.result, self.n, self.top, self.scratch, self._keep = ctx, result, n, top, scratch, keep
+
+    def blob(self) -> np.ndarray:
+        nbytes = int(lib.rt_blob_bytes(self.n, 1 if self.top else 0))
+        return self.result.download(np.uint8, nbytes)
+
+    def scratch_layout(self) -> ScratchLayout:
+        L = ScratchLayout()
+        check(lib.rt_build_scratch_layout(self.n, 1 if self.top else 0, C.byref(L)))
+        return L
+
+    def stage(self, name: str) -> np.ndarray:
+        """Download an intermediate build product (needs keep_scratch=True)."""
+        assert self.scratch is not None, "build with keep_scratch=True"
+        L = self.scratch_layout()
+        n = self.n
+        spec = {"scene_aabb": (np.float32, 6), "morton_codes": (np.uint32, n), "sorted_codes": (np.uint32, n),
+                "sorted_indices": (np.uint32, n), "hierarchy": (T.HIER_DTYPE, max(2 * n - 1, 0)),
+                "primitives": (T.PRIM_DTYPE, n), "metadata": (T.META_DTYPE, n)}[name]
+        return self.scratch.download(spec[0], spec[1], offset=getattr(L, name))
+
+
+class Program:
+    """rt_program + its bindings: the compiled-in counterpart of RtProgram / RtBindings / RtState."""
+
+    def __init__(self, ctx: Context, kind: int, hit_group_count: int = 2, miss_count: int = 2):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib.rt_program_create(ctx.handle, kind, hit_group_count, miss_count, C.byref(h)))
+        self.handle = h.value
+        self.hit_group_count = hit_group_count
+        self._keep = []
+
+    def set_hit_record(self, ray_type, instance, vb: Buffer, ib: Buffer, material: T.MaterialParams):
+        check(lib.rt_bindings_set_hit_record(self.handle, ray_type, instance, vb.ptr, ib.ptr, C.byref(material)))
+        self._keep += [vb, ib]
+
+    def set_env(self, texels: np.ndarray):
+        if texels is None:
+            check(lib.rt_bindings_set_miss_record(self.handle, 0, None, 0))
+            return
+        tex = np.ascontiguousarray(texels, np.float32)
+        buf = self.ctx.upload(tex.reshape(-1))
+        self._keep.append(buf)
+        check(lib.rt_bindings_set_miss_record(self.handle, 0, buf.ptr, tex.shape[1]))
+
+    def close(self):
+        if self.handle:
+            lib.rt_program_destroy(self.handle)
+            self.handle = None
+
+
+PROGRESSIVE, REALTIME = 0, 1
+
+
+class Renderer:
+    """Convenience host for tests/bench: one scene (instances of meshes), one program, fp32 outputs on the device."""
+
+    def __init__(self, ctx: Context, meshes, transforms, materials, env_texels, kind=PROGRESSIVE, width=256, height=256):
+        self.ctx, self.width, self.height, self.kind = ctx, width, height, kind
+        self.blases = [ctx.build_blas_from_mesh(m) for m in meshes]
+        self.tlas = ctx.build_tlas(self.blases, transforms)
+        self.program = Program(ctx, kind)
+        for i, (b, mat) in enumerate(zip(self.blases, materials)):
+            for ray_type in range(2):
+                self.program.set_hit_record(ray_type, i, b.vb, b.ib, mat)
+        self.program.set_env(env_texels)
+        self.out = [ctx.alloc(16 * width * height).zero() for _ in range(2 if kind == REALTIME else 1)]
+
+    def dispatch(self, frame: T.PerFrameConstants, region=None):
+        # global root arguments are (re)bound per dispatch, as render() does (ProgressiveRaytracingPipeline.cpp:236-242)
+        for slot, o in enumerate(self.out):
+            check(lib.rt_set_output(self.ctx.handle, slot, o.ptr, 16 * self.width))
+        check(lib.rt_set_tlas(self.ctx.handle, self.tlas.result.ptr))
+        check(lib.rt_set_frame_constants(self.ctx.handle, C.byref(frame)))
+        if region is None:
+            check(lib.rt_dispatch_rays(self.ctx.handle, self.program.handle, self.width, self.height, 3))
+        else:
+            x0, y0, x1, y1 = region
+            check(lib.rt_dispatch_rays_region(self.ctx.handle, self.program.handle, self.width, self.height, x0, y0, x1, y1))
+
+    def image(self, slot=0) -> np.ndarray:
+        return self.out[slot].download(np.float32).reshape(self.height, self.width, 4)

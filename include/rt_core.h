@@ -1,0 +1,172 @@
+/*
+ * rt_core.h — C ABI of the B200 ray-tracing core (librt_core.so).
+ *
+ * This is the drop-in boundary: the DXRFramework-style host classes (RtContext, RtModel, RtScene,
+ * RtProgram, RtBindings, RtState, the two RaytracingPipelines and the DenoiseCompositor) call
+ * these entry points where the reference calls the COM interfaces of the D3D12 Raytracing
+ * Fallback Layer (externals/D3D12RaytracingFallback/Include/D3D12RaytracingFallback.h:46-171).
+ * Each function cites the reference interface it replaces.  Paths are relative to /root/reference.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and the POD structs of rt_types.h; no CUDA / torch / C++ types.
+ *   - return value: 0 (RT_OK) on success, a negative rt_status otherwise; rt_last_error() returns a
+ *     thread-local description of the last failure (the reference throws: FL/Util.h:14-27).
+ *   - every device pointer argument is a CUDA device address valid in the context's device.
+ *   - all work is stream-ordered on the context's stream (default: a private non-blocking stream;
+ *     rt_context_set_stream adopts the caller's, e.g. torch's current stream).  Nothing here
+ *     synchronises the host except rt_sync, rt_download, rt_get_ray_counts and rt_get_status.
+ *   - a context is thread-compatible, not thread-safe (the reference records on one command list).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with RT_ERR_CUDA.
+ */
+#ifndef RT_CORE_H
+#define RT_CORE_H
+
+#include "rt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID_ARG = -1, /* E_INVALIDARG in the reference */
+    RT_ERR_CUDA = -2,        /* a CUDA runtime call failed (device removed / out of memory / no device) */
+    RT_ERR_TOO_SMALL = -3,   /* scratch or result buffer smaller than rt_*_prebuild reported */
+    RT_ERR_UNSUPPORTED = -4,
+    RT_ERR_OVERFLOW = -5     /* traversal stack overflow was detected on the device (see rt_get_status) */
+} rt_status;
+
+typedef struct rt_context rt_context;
+typedef struct rt_program rt_program;
+
+typedef enum rt_program_kind {
+    RT_PROGRAM_PROGRESSIVE = 0, /* assets/shaders/ProgressiveRaytracing.hlsl */
+    RT_PROGRAM_REALTIME = 1     /* assets/shaders/RealtimeRaytracing.hlsl */
+} rt_program_kind;
+
+/* D3D12_RAYTRACING_ACCELERATION_STRUCTURE_PREBUILD_INFO */
+typedef struct rt_prebuild_info {
+    uint64_t result_bytes;
+    uint64_t scratch_bytes;
+    uint64_t update_scratch_bytes;
+} rt_prebuild_info;
+
+/* Byte offsets of the intermediate build products inside the scratch buffer of the LAST build of
+ * that size; white-box parity tests download them after rt_blas_build / rt_tlas_build. */
+typedef struct rt_scratch_layout {
+    uint64_t scene_aabb;     /* 6 floats {min xyz, max xyz}                          (FL/SceneAABBCalculator.cpp) */
+    uint64_t morton_codes;   /* n x u32, load order                                  (FL/CalculateMortonCodes.hlsli) */
+    uint64_t sorted_codes;   /* n x u32                                               (FL/BitonicSort.cpp)           */
+    uint64_t sorted_indices; /* n x u32: sorted slot -> load-order primitive          (FL/BitonicSort.cpp)           */
+    uint64_t hierarchy;      /* (2n-1) x rt_hierarchy_node                            (FL/BuildBVHSplits.hlsli)      */
+    uint64_t primitives;     /* n x rt_primitive, load order (BLAS only)              (FL/BottomLevelLoadTriangles.hlsli) */
+    uint64_t metadata;       /* n x rt_primitive_meta, load order (BLAS only)                                         */
+    uint64_t total;
+} rt_scratch_layout;
+
+const char *rt_last_error(void);
+/* Library version string; also proves the native library (not a fallback) is what got loaded. */
+const char *rt_version(void);
+
+/* ---- context: RtContext::create / D3D12CreateRaytracingFallbackDevice (libs/DXRFramework/RtContext.cpp:12-29) */
+int rt_context_create(int device_ordinal, rt_context **out);
+int rt_context_destroy(rt_context *ctx);
+int rt_context_set_stream(rt_context *ctx, void *cuda_stream /* cudaStream_t */);
+int rt_sync(rt_context *ctx); /* DeviceResources::WaitForGpu */
+int rt_get_status(rt_context *ctx); /* syncs; RT_ERR_OVERFLOW if any traversal overflowed its stack */
+/* Number of kernel launches issued through this context since creation (bench.py's gpu_launches). */
+uint64_t rt_launch_count(const rt_context *ctx);
+
+/* ---- buffers: CreateBuffer / AllocateUploadBuffer (libs/DXRFramework/Helpers/DirectXRaytracingHelper.h) */
+int rt_malloc(rt_context *ctx, uint64_t bytes, void **dev);
+int rt_free(rt_context *ctx, void *dev);
+int rt_memset(rt_context *ctx, void *dev, int value, uint64_t bytes);
+int rt_upload(rt_context *ctx, void *dev, const void *host, uint64_t bytes);   /* async if host is pinned */
+int rt_download(rt_context *ctx, void *host, const void *dev, uint64_t bytes); /* synchronises */
+int rt_host_alloc_pinned(uint64_t bytes, void **host);
+int rt_host_free_pinned(void *host);
+
+/* ---- acceleration structures
+ * ID3D12RaytracingFallbackDevice::GetRaytracingAccelerationStructurePrebuildInfo and
+ * ID3D12RaytracingFallbackCommandList::BuildRaytracingAccelerationStructure
+ * (FL/FallbackLayer.cpp:317-338, FL/GpuBVH2Builder.cpp:137-205,349-455), as called by
+ * RtModel::build (libs/DXRFramework/RtModel.cpp:86-118) and RtScene::build (RtScene.cpp:18-52).
+ *
+ * The result buffer receives the reference's blob ([BVHOffsets][2N-1 AABBNode][N Primitive]
+ * [N PrimitiveMetaData], or the TLAS layout) followed, 64-byte aligned, by this library's
+ * traversal section (rt_core's own wide nodes; opaque to callers).  A TLAS refers to its BLASes
+ * by the device address of their result buffers (rt_instance_desc.blas), the analogue of the
+ * Fallback Layer's WRAPPED_GPU_POINTER.  Buffers must stay alive while anything refers to them. */
+int rt_blas_prebuild(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags,
+                     rt_prebuild_info *info);
+int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags,
+                  void *scratch, uint64_t scratch_bytes, void *result, uint64_t result_bytes);
+int rt_tlas_prebuild(rt_context *ctx, uint32_t n_instances, uint32_t build_flags, rt_prebuild_info *info);
+/* instance_descs: DEVICE array of n rt_instance_desc (ELEMENTS_LAYOUT_ARRAY). */
+int rt_tlas_build(rt_context *ctx, const rt_instance_desc *instance_descs, uint32_t n_instances, uint32_t build_flags,
+                  void *scratch, uint64_t scratch_bytes, void *result, uint64_t result_bytes);
+int rt_build_scratch_layout(uint32_t n_elements, int top_level, rt_scratch_layout *layout);
+/* Size in bytes of the reference-format blob at the head of a result buffer holding n elements. */
+uint64_t rt_blob_bytes(uint32_t n_elements, int top_level);
+
+/* ---- programs and shader-table bindings
+ * RtProgram::create / RtState (libs/DXRFramework/RtProgram.h:38-128, RtState.h:18-30) and
+ * RtBindings::apply (RtBindings.cpp:100-164).  Shaders are compiled into the library, so a program
+ * is chosen by kind; the entry-point names given to RtProgram::Desc are validated on the host side. */
+int rt_program_create(rt_context *ctx, rt_program_kind kind, uint32_t hit_group_count, uint32_t miss_count,
+                      rt_program **out);
+int rt_program_destroy(rt_program *prog);
+/* Hit record of (ray_type, instance): VB SRV, IB SRV, 16 dwords MaterialParams
+ * (src/ProgressiveRaytracingPipeline.cpp:220-227).  vertex_buffer: rt_vertex[], index_buffer: uint32[]. */
+int rt_bindings_set_hit_record(rt_program *prog, uint32_t ray_type, uint32_t instance, const void *vertex_buffer,
+                               const void *index_buffer, const rt_material_params *material);
+/* Miss record of ray_type: the environment cube (6 x size x size RGBA fp32 device texels), or NULL. */
+int rt_bindings_set_miss_record(rt_program *prog, uint32_t ray_type, const float *env_cube_texels, uint32_t size);
+
+/* ---- per-dispatch state: SetComputeRootConstantBufferView / RootDescriptorTable /
+ * SetTopLevelAccelerationStructure (src/ProgressiveRaytracingPipeline.cpp:236-242) */
+int rt_set_frame_constants(rt_context *ctx, const rt_per_frame_constants *frame);
+/* slot 0: gOutput (progressive) / gDirectLightingOutput (realtime); slot 1: gIndirectSpecularOutput.
+ * RGBA fp32, pitch in bytes (>= width*16).  The reference's targets are R16G16B16A16_FLOAT
+ * (src/DXRExperimentsApp.cpp:28); fp32 is a declared deviation. */
+int rt_set_output(rt_context *ctx, uint32_t slot, float *rgba, uint64_t pitch_bytes);
+int rt_set_tlas(rt_context *ctx, const void *tlas_result);
+
+/* RtContext::raytrace -> DispatchRays (libs/DXRFramework/RtContext.cpp:192-222,
+ * FL/UberShaderRayTracingProgram.cpp:213-272).  `depth` is accepted and ignored, as in the reference. */
+int rt_dispatch_rays(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t depth);
+/* Same, restricted to the pixel rectangle [x0,x1) x [y0,y1) of the width x height launch: screen-tile
+ * sharding across GPUs.  Pixels outside the rectangle are not touched. */
+int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0,
+                            uint32_t y0, uint32_t x1, uint32_t y1);
+/* Rays traced by all dispatches since the last reset (synchronises). */
+int rt_get_ray_counts(rt_context *ctx, rt_ray_counts *counts, int reset);
+/* Optional per-stage device timing (CUDA events around the trace kernels; synchronises the host once per
+ * dispatch while enabled, so it is for profiling runs, not for the headline measurement).  Times are
+ * accumulated milliseconds: primary closest-hit, incoherent secondary closest-hit, shadow any-hit. */
+int rt_enable_stage_timing(rt_context *ctx, int enable);
+int rt_get_stage_timing(rt_context *ctx, double *primary_ms, double *secondary_ms, double *shadow_ms, int reset);
+
+/* DenoiseCompositor::dispatch (src/DenoiseCompositor.cpp:109-148): pass H (joint = direct, input =
+ * indirect specular -> tmp) then pass V (-> out, + direct, exposure, Reinhard, gamma).  RGBA fp32, tightly packed. */
+int rt_denoise(rt_context *ctx, const float *direct, const float *indirect_specular, float *tmp, float *out,
+               uint32_t width, uint32_t height, const rt_denoiser_params *params);
+
+/* ---- wavefront primitives exposed for parity tests and benchmarks */
+/* Fallback_TraceRay without shader call-outs (FL/TraverseShader.hlsli:21-73): n rays -> n hits. */
+int rt_trace_rays(rt_context *ctx, const void *tlas_result, const rt_ray *rays, uint64_t n, uint32_t ray_flags,
+                  uint32_t instance_mask, rt_hit *hits);
+/* Same with per-ray work counters accumulated into *stats (device memory, 5 x u64 = rt_trace_stats). */
+int rt_trace_rays_stats(rt_context *ctx, const void *tlas_result, const rt_ray *rays, uint64_t n, uint32_t ray_flags,
+                        uint32_t instance_mask, rt_hit *hits, rt_trace_stats *stats_dev);
+/* RayGen's camera rays (ProgressiveRaytracing.hlsl:17-31) written out as records. */
+int rt_generate_primary_rays(rt_context *ctx, const rt_per_frame_constants *frame, uint32_t width, uint32_t height,
+                             float jitter_scale, rt_ray *rays);
+/* buf[i] *= scale  (i < count floats): turns a rank's running mean into its share of the global mean
+ * before the NCCL sum of the accumulation buffers. */
+int rt_scale_buffer(rt_context *ctx, float *buf, uint64_t count, float scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_CORE_H */

@@ -30,9 +30,14 @@ static RayData get_ray_data(f3 o, f3 d) {
 // RayBoxTest: FL/TraverseFunction.hlsli:173-191
 static bool ray_box(float &resultT, float closestT, const RayData &rd, const rt_aabb_node &n) {
     f3 c = mk(n.center[0], n.center[1], n.center[2]), h = mk(n.halfDim[0], n.halfDim[1], n.halfDim[2]);
-    f3 rel = c * rd.invDir - rd.originTimesInvDir;
-    f3 ha = h * vabs(rd.invDir);
-    f3 maxL = rel + ha, minL = rel - ha;
+    // The HLSL expressions are not `precise`, so the shader compiler is free to contract them into
+    // mads; they are pinned here as fused multiply-adds (what both DXC->driver and nvcc emit) so that
+    // the CUDA traversal can be compared box test for box test.
+    f3 ai = vabs(rd.invDir);
+    f3 rel = mk(fmaf(c.x, rd.invDir.x, -rd.originTimesInvDir.x), fmaf(c.y, rd.invDir.y, -rd.originTimesInvDir.y),
+                fmaf(c.z, rd.invDir.z, -rd.originTimesInvDir.z));
+    f3 maxL = mk(fmaf(h.x, ai.x, rel.x), fmaf(h.y, ai.y, rel.y), fmaf(h.z, ai.z, rel.z));
+    f3 minL = mk(fmaf(-h.x, ai.x, rel.x), fmaf(-h.y, ai.y, rel.y), fmaf(-h.z, ai.z, rel.z));
     float minT = fmaxf(fmaxf(minL.x, minL.y), minL.z);
     float maxT = fminf(fminf(maxL.x, maxL.y), maxL.z);
     resultT = fmaxf(minT, 0.0f);

@@ -1,0 +1,129 @@
+"""GPU parity: LBVH build (rt_blas_build / rt_tlas_build through the C ABI) against the CPU oracle.
+
+North-star criterion 1: Morton codes and the sort permutation are BIT-EXACT.  The hierarchy and the
+whole reference-format blob (boxes, sorted primitives, metadata) are compared bit-exactly as well.
+"""
+import numpy as np
+import pytest
+
+from dxrexperiments_b200 import scenes, types as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh_cases():
+    rng = np.random.Generator(np.random.PCG64(5))
+    dup = scenes.triangle_soup(3000, seed=3, extent=2.0, edge=0.5)            # many duplicate Morton codes
+    dup.vertices["position"][: 3 * 500] = np.tile(dup.vertices["position"][:3], (500, 1))  # 500 identical triangles
+    flat = scenes.quad((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1))       # zero-extent axis (epsilon path)
+    return {
+        "cornell": scenes.cornell_box(),
+        "icosphere3": scenes.icosphere(3),
+        "bunny4": scenes.bunny_scale(4),
+        "soup5000": scenes.triangle_soup(5000, seed=42),
+        "duplicates": dup,
+        "flat_quad": flat,
+        "one_triangle": scenes.Mesh(scenes.icosphere(0).vertices, scenes.icosphere(0).indices[:3].copy()),
+        "two_triangles": scenes.Mesh(scenes.icosphere(0).vertices, scenes.icosphere(0).indices[:6].copy()),
+        "soup_70k": scenes.triangle_soup(70001, seed=int(rng.integers(1 << 30))),
+    }
+
+
+MESHES = _mesh_cases()
+
+
+@pytest.mark.parametrize("name", sorted(MESHES))
+def test_blas_stages_and_blob_bit_exact(name, ctx, orc):
+    mesh = MESHES[name]
+    ref = orc.Blas.from_mesh(mesh)
+    acc = ctx.build_blas_from_mesh(mesh, keep_scratch=True)
+    ctx.sync()
+    assert acc.n == ref.n == mesh.num_triangles
+    np.testing.assert_array_equal(acc.stage("primitives").view(np.uint8), ref.unsorted_prims().view(np.uint8))
+    np.testing.assert_array_equal(acc.stage("scene_aabb"), ref.scene_aabb())
+    np.testing.assert_array_equal(acc.stage("morton_codes"), ref.morton())          # criterion 1
+    np.testing.assert_array_equal(acc.stage("sorted_codes"), ref.sorted_morton())
+    np.testing.assert_array_equal(acc.stage("sorted_indices"), ref.perm())           # criterion 1
+    if ref.n > 1:
+        h_gpu, h_ref = acc.stage("hierarchy"), ref.hierarchy()
+        np.testing.assert_array_equal(h_gpu["left"][: ref.n - 1], h_ref["left"][: ref.n - 1])
+        np.testing.assert_array_equal(h_gpu["right"][: ref.n - 1], h_ref["right"][: ref.n - 1])
+        np.testing.assert_array_equal(h_gpu["parent"][1:], h_ref["parent"][1:])
+    np.testing.assert_array_equal(acc.blob(), ref.blob())
+
+
+def test_blas_index_formats_transform_and_multi_geometry(ctx, orc):
+    """R16 / R32 / no index buffer, a 3x4 transform and two geometries in one BLAS (UT:617-776)."""
+    verts, idx16 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 1]], np.float32), np.array([0, 1, 2, 2, 1, 3], np.uint16)
+    soup = scenes.triangle_soup(100, seed=9, extent=5.0)
+    soup_pos = np.ascontiguousarray(soup.vertices["position"])
+    xf = np.array([0.5, 0, 0, 1, 0, 2, 0, -3, 0.25, 0, 1, 0.5], np.float32)
+    ogeoms = [dict(vertices=verts, stride=12, indices=idx16, flags=1),
+              dict(vertices=soup_pos, stride=12, indices=None, transform=xf, flags=0),
+              dict(vertices=verts, stride=12, indices=idx16.astype(np.uint32), flags=1)]
+    ref = orc.Blas(ogeoms)
+    d_verts, d_idx16, d_idx32 = ctx.upload(verts), ctx.upload(idx16), ctx.upload(idx16.astype(np.uint32))
+    d_soup, d_xf = ctx.upload(soup_pos), ctx.upload(xf)
+    acc = ctx.build_blas([
+        dict(vertices=d_verts, vertex_count=4, stride=12, indices=d_idx16, index_count=6, index_format=16, flags=1),
+        dict(vertices=d_soup, vertex_count=300, stride=12, indices=None, index_format=0, transform=d_xf, flags=0),
+        dict(vertices=d_verts, vertex_count=4, stride=12, indices=d_idx32, index_count=6, index_format=32, flags=1)],
+        keep_scratch=True)
+    ctx.sync()
+    assert acc.n == ref.n == 104
+    np.testing.assert_array_equal(acc.stage("sorted_indices"), ref.perm())
+    np.testing.assert_array_equal(acc.blob(), ref.blob())
+    meta = T.parse_blas_blob(acc.blob())["meta"]
+    assert set(meta["geom"].tolist()) == {0, 1, 2}
+    assert sorted(meta["prim"][meta["geom"] == 1].tolist()) == list(range(100))
+
+
+@pytest.mark.parametrize("n_inst", [1, 2, 50, 1000])
+def test_tlas_blob_bit_exact(n_inst, ctx, orc):
+    """TLAS over instances with random rigid transforms (UT:778-935 use 1 and 50)."""
+    mesh = scenes.icosphere(2)
+    xf = scenes.random_rigid_transforms(n_inst, seed=10)
+    ids = [(7 * i + 3) & 0xFFFFFF for i in range(n_inst)]
+    masks = [(i % 255) + 1 for i in range(n_inst)]
+    flags = [i % 4 for i in range(n_inst)]
+    ob = orc.Blas.from_mesh(mesh)
+    ot = orc.Tlas([ob] * n_inst, xf, ids=ids, masks=masks, flags=flags)
+    gb = ctx.build_blas_from_mesh(mesh)
+    gt = ctx.build_tlas([gb] * n_inst, xf, ids=ids, masks=masks, flags=flags, keep_scratch=True)
+    ctx.sync()
+    np.testing.assert_array_equal(gt.stage("sorted_codes"), ot.sorted_morton())
+    np.testing.assert_array_equal(gt.stage("sorted_indices"), ot.perm())
+    g, o = T.parse_tlas_blob(gt.blob()), T.parse_tlas_blob(ot.blob())
+    np.testing.assert_array_equal(g["header"], o["header"])
+    np.testing.assert_array_equal(g["nodes"].view(np.uint8), o["nodes"].view(np.uint8))
+    for f in ("w2o", "id_mask", "hg_flags", "o2w", "instance_index"):  # "blas" holds an address: differs by design
+        np.testing.assert_array_equal(g["meta"][f], o["meta"][f])
+    assert (g["meta"]["blas"] == gb.result.ptr).all()
+
+
+def test_empty_tlas(ctx, orc):
+    """TraceEmptyAccelerationStructure (UT:4000-4008): header + one zero box, every ray misses."""
+    gt = ctx.build_tlas([], [])
+    ot = orc.Tlas([], [])
+    np.testing.assert_array_equal(gt.blob(), ot.blob())
+    from helpers import ut_rays
+    hits = ctx.trace(gt, ut_rays())
+    assert (hits["primitive_index"] == T.NO_HIT).all()
+
+
+def test_build_argument_errors(ctx, rt):
+    import ctypes as C
+    info = T.PrebuildInfo()
+    mesh = scenes.icosphere(1)
+    vb, ib = ctx.upload(mesh.vertices), ctx.upload(mesh.indices)
+    d = (T.GeometryDesc * 1)()
+    d[0].vertex_buffer, d[0].vertex_count, d[0].vertex_stride_bytes = vb.ptr, mesh.vertices.shape[0], 24
+    d[0].index_buffer, d[0].index_count, d[0].index_format = ib.ptr, mesh.indices.size, 32
+    rt.check(rt.lib.rt_blas_prebuild(ctx.handle, d, 1, 0, C.byref(info)))
+    scratch, result = ctx.alloc(info.scratch_bytes), ctx.alloc(info.result_bytes)
+    # result too small -> RT_ERR_TOO_SMALL; null destination -> E_INVALIDARG (FL/GpuBVH2Builder.cpp:145-148)
+    assert rt.lib.rt_blas_build(ctx.handle, d, 1, 0, scratch.ptr, scratch.nbytes, result.ptr, 64) == -3
+    assert rt.lib.rt_blas_build(ctx.handle, d, 1, 0, scratch.ptr, scratch.nbytes, None, 0) == -1
+    d[0].index_format = 8
+    assert rt.lib.rt_blas_build(ctx.handle, d, 1, 0, scratch.ptr, scratch.nbytes, result.ptr, result.nbytes) == -1
+    assert b"index_format" in rt.lib.rt_last_error()
