@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the B200 ray-tracing core.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json configs[1], "C2"): the bunny-scale synthetic mesh (displaced icosphere, 81 922 triangles)
+at 1920x1080, 16 spp of the progressive pipeline.  One STEP = one 16-spp progressive frame = 16 DispatchRays.
+Metric: Mrays/s = all rays actually traced (primary + incoherent secondary + shadow, counted on the device) per
+second of device time, whole job over all ranks.
+
+N > 1: the frame shards by SAMPLE INDEX: rank r renders samples r, r+N, ... with frameCount = the global
+sample index, every rank holds a replicated BVH, and one NCCL reduce sums the scaled accumulation buffers onto
+rank 0.  Per-GPU work is fixed (16 spp each), so scaling is "weak"; the reduce is inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dxrexperiments_b200 import scenes, types as T  # noqa: E402
+
+METRIC = "Mrays/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--subdiv", type=int, default=6, help="icosphere subdivisions of the bunny-scale mesh (6 -> 81 920 tris)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, mesh):
+    return {
+        "workload": f"C2 bunny-scale synthetic mesh ({mesh.num_triangles} tris) {args.width}x{args.height} "
+                    f"{args.spp} spp progressive (Phong, 2 lights, 1 indirect-diffuse + 1 Phong-lobe bounce)",
+        "width": args.width, "height": args.height, "spp_per_step": args.spp, "triangles": mesh.num_triangles,
+        "l2": "per-frame ray queues (~0.45 KB/pixel, ~0.9 GB per 1080p frame) exceed the 126 MB L2 and are rewritten "
+              "every frame; the ~12 MB BVH is meant to stay L2-resident",
+    }
+
+
+def frame_for(setup, args, jitters, sample_global, sample_local):
+    return scenes.make_frame(setup, args.width, args.height, frame_count=sample_global, accum_count=sample_local,
+                             jitter=jitters[sample_global % len(jitters)])
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's algorithm on the host CPU: the oracle port (there is no oracle/_ref — the reference is
+    Windows/D3D12-only), all host threads, each step = 1 spp of the same 1080p frame (a bounded sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    mesh = scenes.bunny_scale(args.subdiv)
+    cores = os.cpu_count() or 1
+    setup = scenes.FrameSetup(camera=scenes.BUNNY_CAMERA)
+    env = scenes.sky_cube(64)
+    blas = oracle.Blas.from_mesh(mesh)
+    tlas = oracle.Tlas([blas], [scenes.IDENTITY_3X4])
+    recs = oracle.Records([mesh], [scenes.make_material()])
+    jit = scenes.jitter_sequence(setup.seed, 1024, args.width, args.height)
+    acc = np.zeros((args.height, args.width, 4), np.float32)
+
+    def step(i, counts):
+        oracle.render_progressive(tlas, recs, env, frame_for(setup, args, jit, i, 0), args.width, args.height, acc,
+                                  threads=cores, counts=counts)
+
+    for i in range(args.warmup):
+        step(i, None)
+    counts = T.RayCounts()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i, counts)
+    dt = time.perf_counter() - t0
+    rays = counts.primary + counts.secondary + counts.shadow
+    value = rays / dt / 1e6
+    sample = f"{args.steps} x 1 spp of the {args.width}x{args.height} frame ({rays} rays), {cores} threads, row-parallel"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh),
+           "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+class TorchBuffer:
+    """A torch CUDA tensor exposed to the C ABI as a raw device pointer (torch = device memory plumbing)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.ptr = tensor.data_ptr()
+        self.nbytes = tensor.numel() * tensor.element_size()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from dxrexperiments_b200 import rtcore as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — rt_core has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = rt.Context(local_rank, stream=stream.cuda_stream)
+
+    W, H, SPP = args.width, args.height, args.spp
+    mesh = scenes.bunny_scale(args.subdiv)
+    setup = scenes.FrameSetup(camera=scenes.BUNNY_CAMERA)
+    env = scenes.sky_cube(64)
+    mat = scenes.make_material()
+    jit = scenes.jitter_sequence(setup.seed, 1024, W, H)
+
+    out_t = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+    renderer = rt.Renderer(ctx, [mesh], [scenes.IDENTITY_3X4], [mat], env, rt.PROGRESSIVE, W, H, outputs=[TorchBuffer(out_t)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step(step_index):
+        # rank r renders global samples r, r + world, ...; RNG is a pure function of (pixel, frameCount)
+        for s in range(SPP):
+            renderer.dispatch(frame_for(setup, args, jit, s * world + rank, s))
+        if world > 1:
+            rt.check(rt.lib.rt_scale_buffer(ctx.handle, out_t.data_ptr(), out_t.numel(), 1.0 / world))
+            dist.reduce(out_t, dst=0, op=dist.ReduceOp.SUM)
+
+    for i in range(args.warmup):
+        step(i)
+    ctx.status()
+
+    # ---- headline: K steps, device timed, barrier + synchronize on both sides, max over ranks
+    ctx.ray_counts(reset=True)
+    launches0 = ctx.launches()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
+    launches = ctx.launches() - launches0  # this rank's own kernels; NCCL's reduce kernels are not counted
+    rc = ctx.ray_counts(reset=True)
+    rays = np.array([rc.primary, rc.secondary, rc.shadow], dtype=np.float64)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    r = torch.tensor(rays, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    rays = r.cpu().numpy()
+    value = rays.sum() / (ms * 1e-3) / 1e6
+
+    # ---- e2e: the same step through the C ABI with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(args, ctx, rt, torch, dist, stream, mesh, setup, env, mat, jit, world, rank)
+
+    # ---- roofline of the dominant kernel (rank 0 of a 1-GPU run: single-GPU kernel property)
+    roofline, stages = None, None
+    if rank == 0:
+        roofline, stages = measure_roofline(args, ctx, renderer, setup, jit, world, rank)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = measure_cpu_baseline(args, mesh, setup, env, jit)
+
+    ctx.status()
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh),
+               "rays_per_step": {"primary": rays[0] / args.steps, "secondary_incoherent": rays[1] / args.steps,
+                                 "shadow": rays[2] / args.steps},
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "stages": stages,
+               "cpu_baseline": cpu_baseline,
+               "parallelism": f"sample-index sharding x{world}, replicated BVH, 1 NCCL reduce/frame" if world > 1 else "single GPU"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_e2e(args, ctx, rt, torch, dist, stream, mesh, setup, env, mat, jit, world, rank):
+    """Step through the reference-facing C ABI starting from HOST memory: pinned VB/IB/instance descs -> device,
+    BLAS + TLAS build, 16 dispatches, accumulated frame -> pinned host."""
+    W, H, SPP = args.width, args.height, args.spp
+    vb_h = torch.from_numpy(mesh.vertices.view(np.uint8).reshape(-1).copy()).pin_memory()
+    ib_h = torch.from_numpy(mesh.indices.view(np.uint8).reshape(-1).copy()).pin_memory()
+    vb_d, ib_d = torch.empty_like(vb_h, device="cuda"), torch.empty_like(ib_h, device="cuda")
+    img_h = torch.empty(H * W * 4, dtype=torch.float32).pin_memory()
+    out_t = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+
+    desc = (T.GeometryDesc * 1)()
+    desc[0].vertex_buffer, desc[0].vertex_count, desc[0].vertex_stride_bytes = vb_d.data_ptr(), mesh.vertices.shape[0], 24
+    desc[0].index_buffer, desc[0].index_count, desc[0].index_format = ib_d.data_ptr(), mesh.indices.size, 32
+    desc[0].flags = T.GEOMETRY_FLAG_OPAQUE
+    binfo, tinfo = T.PrebuildInfo(), T.PrebuildInfo()
+    rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, 0, C.byref(binfo)))
+    rt.check(rt.lib.rt_tlas_prebuild(ctx.handle, 1, 0, C.byref(tinfo)))
+    bscr = torch.empty(binfo.scratch_bytes, dtype=torch.uint8, device="cuda")
+    bres = torch.empty(binfo.result_bytes, dtype=torch.uint8, device="cuda")
+    tscr = torch.empty(tinfo.scratch_bytes, dtype=torch.uint8, device="cuda")
+    tres = torch.empty(tinfo.result_bytes, dtype=torch.uint8, device="cuda")
+    inst = (T.InstanceDesc * 1)()
+    inst[0].transform[:] = scenes.IDENTITY_3X4.tolist()
+    inst[0].instance_id_and_mask = 0xFF << 24
+    inst[0].hit_group_and_flags = 0
+    inst[0].blas = bres.data_ptr()
+    inst_h = torch.from_numpy(np.frombuffer(bytes(inst), dtype=np.uint8).copy()).pin_memory()
+    inst_d = torch.empty_like(inst_h, device="cuda")
+    env_d = torch.from_numpy(np.ascontiguousarray(env, np.float32).reshape(-1)).cuda()
+    prog = rt.Program(ctx, rt.PROGRESSIVE)
+    for ray_type in range(2):
+        rt.check(rt.lib.rt_bindings_set_hit_record(prog.handle, ray_type, 0, vb_d.data_ptr(), ib_d.data_ptr(), C.byref(mat)))
+    rt.check(rt.lib.rt_bindings_set_miss_record(prog.handle, 0, env_d.data_ptr(), env.shape[1]))
+
+    def step(i):
+        vb_d.copy_(vb_h, non_blocking=True)
+        ib_d.copy_(ib_h, non_blocking=True)
+        inst_d.copy_(inst_h, non_blocking=True)
+        rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, 0, bscr.data_ptr(), bscr.numel(), bres.data_ptr(), bres.numel()))
+        rt.check(rt.lib.rt_tlas_build(ctx.handle, inst_d.data_ptr(), 1, 0, tscr.data_ptr(), tscr.numel(), tres.data_ptr(), tres.numel()))
+        rt.check(rt.lib.rt_set_tlas(ctx.handle, tres.data_ptr()))
+        rt.check(rt.lib.rt_set_output(ctx.handle, 0, out_t.data_ptr(), 16 * W))
+        for s in range(SPP):
+            f = frame_for(setup, args, jit, s * world + rank, s)
+            rt.check(rt.lib.rt_set_frame_constants(ctx.handle, C.byref(f)))
+            rt.check(rt.lib.rt_dispatch_rays(ctx.handle, prog.handle, W, H, 3))
+        if world > 1:
+            rt.check(rt.lib.rt_scale_buffer(ctx.handle, out_t.data_ptr(), out_t.numel(), 1.0 / world))
+            dist.reduce(out_t, dst=0, op=dist.ReduceOp.SUM)
+        img_h.copy_(out_t, non_blocking=True)
+
+    for i in range(max(1, min(args.warmup, 2))):
+        step(i)
+    ctx.ray_counts(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    rc = ctx.ray_counts(reset=True)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    r = torch.tensor([float(rc.primary + rc.secondary + rc.shadow)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    assert float(img_h.sum()) > 0.0
+    return {"value": float(r.item()) / (float(t.item()) * 1e-3) / 1e6, "unit": METRIC,
+            "h2d_bytes_per_step": int(vb_h.numel() + ib_h.numel() + inst_h.numel()), "d2h_bytes_per_step": int(img_h.numel() * 4),
+            "ms_per_step": float(t.item()) / args.steps,
+            "includes": "pinned H2D of VB/IB/instance descs, BLAS+TLAS build, 16 dispatches, D2H of the accumulated frame"}
+
+
+def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
+    """Algorithmic bytes (48 + 64*n_int + 48*n_leaf per ray) / CUDA-event time of each trace stage."""
+    SPP = args.spp
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    # 1) instrumented pass (untimed): exact node visits / triangle tests of the very same rays
+    ctx.enable_trace_stats(True)
+    ctx.trace_stats(reset=True)
+    for s in range(SPP):
+        renderer.dispatch(frame_for(setup, args, jit, s * world + rank, s))
+    st = ctx.trace_stats(reset=True)
+    ctx.enable_trace_stats(False)
+    # 2) timed pass with CUDA events around each trace kernel, on the launching stream
+    ctx.enable_stage_timing(True)
+    ctx.stage_timing(reset=True)
+    reps = max(1, args.steps)
+    for _ in range(reps):
+        for s in range(SPP):
+            renderer.dispatch(frame_for(setup, args, jit, s * world + rank, s))
+    tp, ts, tsh = ctx.stage_timing(reset=True)
+    ctx.enable_stage_timing(False)
+    names = ["primary (k_primary)", "secondary_incoherent (k_trace_queue<closest>)", "shadow (k_trace_queue<any>, 2 launches/frame)"]
+    times = [tp, ts, tsh]
+    launches_per_frame = [1, 1, 2]
+    stages = {}
+    for name, s, t, lpf in zip(names, st, times, launches_per_frame):
+        n_launch = reps * SPP * lpf
+        bytes_total = 48.0 * s.rays + 64.0 * s.internal_visits + 48.0 * s.leaf_visits  # over SPP instrumented frames
+        bytes_per_launch = bytes_total / (SPP * lpf)
+        ms_per_launch = t / n_launch
+        stages[name] = {"rays_per_launch": s.rays / (SPP * lpf), "n_int_per_ray": s.internal_visits / max(s.rays, 1),
+                        "n_leaf_per_ray": s.leaf_visits / max(s.rays, 1), "max_stack": int(s.max_stack),
+                        "ms_per_launch": ms_per_launch, "algorithmic_bytes_per_launch": bytes_per_launch,
+                        "achieved_gbs": bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else None,
+                        "mrays_per_s": s.rays / (SPP * lpf) / (ms_per_launch * 1e-3) / 1e6 if ms_per_launch > 0 else None,
+                        "share_of_trace_time": t / max(sum(times), 1e-12)}
+    dom = max(stages, key=lambda k: stages[k]["share_of_trace_time"])
+    d = stages[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["achieved_gbs"] / peak if d["achieved_gbs"] else None, "traffic": load_ncu_traffic(),
+                "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes/ray (48 + 64*n_int + 48*n_leaf, SURVEY 8d) x rays per launch / "
+                        "CUDA-event launch time; the BVH is L2-resident so achieved may legitimately exceed DRAM traffic"}
+    return roofline, stages
+
+
+def load_ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if present."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def measure_cpu_baseline(args, mesh, setup, env, jit):
+    import oracle
+    cores = os.cpu_count() or 1
+    blas = oracle.Blas.from_mesh(mesh)
+    tlas = oracle.Tlas([blas], [scenes.IDENTITY_3X4])
+    recs = oracle.Records([mesh], [scenes.make_material()])
+    acc = np.zeros((args.height, args.width, 4), np.float32)
+    counts = T.RayCounts()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        oracle.render_progressive(tlas, recs, env, frame_for(setup, args, jit, n, 0), args.width, args.height, acc,
+                                  threads=cores, counts=counts)
+        n += 1
+        if time.perf_counter() - t0 > 10.0 or n >= 4:
+            break
+    dt = time.perf_counter() - t0
+    rays = counts.primary + counts.secondary + counts.shadow
+    return {"value": rays / dt / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": f"{n} x 1 spp of the {args.width}x{args.height} frame ({rays} rays) in {dt:.1f} s, row-parallel over {cores} threads"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

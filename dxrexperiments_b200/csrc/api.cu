@@ -225,7 +225,28 @@ int rt_get_ray_counts(rt_context *ctx, rt_ray_counts *counts, int reset) {
     RT_CUDA(cudaMemcpyAsync(h, ctx->ray_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     counts->primary = h[0], counts->secondary = h[1], counts->shadow = h[2];
-    if (reset) RT_CUDA(cudaMemsetAsync(ctx->ray_counts, 0, 256, ctx->stream));
+    if (reset) RT_CUDA(cudaMemsetAsync(ctx->ray_counts, 0, 64, ctx->stream));
+    return RT_OK;
+}
+
+int rt_enable_trace_stats(rt_context *ctx, int enable) {
+    RT_REQUIRE(ctx != nullptr, "ctx");
+    ctx->collect_stats = enable != 0;
+    return RT_OK;
+}
+
+int rt_get_trace_stats(rt_context *ctx, rt_trace_stats *primary, rt_trace_stats *secondary, rt_trace_stats *shadow, int reset) {
+    RT_REQUIRE(ctx != nullptr, "ctx");
+    unsigned long long h[32];
+    RT_CUDA(cudaMemcpyAsync(h, ctx->ray_counts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    rt_trace_stats *out[3] = {primary, secondary, shadow};
+    for (int s = 0; s < 3; ++s)
+        if (out[s]) {
+            const unsigned long long *p = h + 8 * (s + 1);
+            out[s]->rays = p[0], out[s]->internal_visits = p[1], out[s]->leaf_visits = p[2], out[s]->instance_visits = p[3], out[s]->max_stack = p[4];
+        }
+    if (reset) RT_CUDA(cudaMemsetAsync(ctx->ray_counts + 8, 0, 192, ctx->stream));
     return RT_OK;
 }
 

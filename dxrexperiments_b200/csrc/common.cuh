@@ -62,9 +62,10 @@ struct rt_context {
 
     rt_workspace ws;
     uint32_t *status = nullptr;          // device word: bit0 = traversal stack overflow
-    unsigned long long *ray_counts = nullptr;  // device: primary, secondary, shadow
+    unsigned long long *ray_counts = nullptr;  // device u64[32]: [0..2] rays traced; [8..12], [16..20], [24..28] rt_trace_stats of the primary / secondary / shadow stages
     // stage timing (optional)
     bool timing = false;
+    bool collect_stats = false;  // instrumented trace kernels (rt_enable_trace_stats)
     cudaEvent_t ev[8] = {};
     bool ev_ready = false;
     double t_primary = 0, t_secondary = 0, t_shadow = 0;

@@ -85,23 +85,48 @@ __device__ __forceinline__ void warp_count_add(unsigned long long *dst, uint32_t
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
 }
 
+__device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, unsigned long long *stats) {
+    // block-level reduction would be cheaper; this path only runs in instrumented (untimed) passes
+    uint32_t v[4] = {rays, c.internal, c.leaf, c.inst};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    uint32_t m = c.max_stack;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (v[k]) atomicAdd(&stats[k], (unsigned long long)v[k]);
+        atomicMax(&stats[4], (unsigned long long)m);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K1
-__global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status) {
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status,
+                                                    unsigned long long *stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tilesX = (L.rw + 7) / 8;
     const uint32_t tile = blockIdx.x * (kBlock / 32) + warp;
     const uint32_t lx = (tile % tilesX) * 8 + (lane & 7), ly = (tile / tilesX) * 4 + (lane >> 3);
-    if (lx >= L.rw || ly >= L.rh) return;
-    const uint32_t x = L.x0 + lx, y = L.y0 + ly;
-    f3 o, d;
-    primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
-    TraceAccel A = resolve_tlas(tlas);
-    TraceHit h;
-    trace_ray<false, false>(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, 0, h,
-                            nullptr, status);
-    const uint32_t p = ly * L.rw + lx;
-    ws.hitA[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-    ws.hitRec[p] = h.record;
+    const bool inside = lx < L.rw && ly < L.rh;
+    TraceCtr ctr{0, 0, 0, 0};
+    if (inside) {
+        const uint32_t x = L.x0 + lx, y = L.y0 + ly;
+        f3 o, d;
+        primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
+        TraceAccel A = resolve_tlas(tlas);
+        TraceHit h;
+        trace_ray<false, STATS>(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, 0, h,
+                                &ctr, status);
+        const uint32_t p = ly * L.rw + lx;
+        ws.hitA[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+        ws.hitRec[p] = h.record;
+    }
+    if (STATS) flush_stats(ctr, inside ? 1u : 0u, stats);
 }
 
 // ------------------------------------------------------------------------------------------------ light helpers
@@ -256,11 +281,14 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ K3 / K4 / K6
-template <bool ANY>
+template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult,
-                                                        float4 *hitA, uint32_t *hitRec, uint8_t *vis, uint32_t *status) {
+                                                        float4 *hitA, uint32_t *hitRec, uint8_t *vis, uint32_t *status,
+                                                        unsigned long long *stats) {
     const uint32_t n = count[0] * mult;
     TraceAccel A = resolve_tlas(tlas);
+    TraceCtr ctr{0, 0, 0, 0};
+    uint32_t traced = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
         const float4 a = rp[0], b = rp[1];
@@ -272,17 +300,19 @@ __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const 
         }
         if (ANY) {
             // shootShadowRay: S/RaytracingCommon.hlsli:84-96 (ray contribution 1, miss index 1)
-            bool hit = trace_ray<true, false>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w,
+            bool hit = trace_ray<true, STATS>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w,
                                               RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER, 0xFF, 1, 0,
-                                              h, nullptr, status);
+                                              h, &ctr, status);
             vis[i] = hit ? 0 : 1;
         } else {
             // shootSecondaryRay: flags 0 (no culling), contribution 0
-            trace_ray<false, false>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0xFF, 0, 0, h, nullptr, status);
+            trace_ray<false, STATS>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0xFF, 0, 0, h, &ctr, status);
             hitA[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
             hitRec[i] = h.record;
         }
+        if (STATS) traced++;
     }
+    if (STATS) flush_stats(ctr, traced, stats);
 }
 
 // ------------------------------------------------------------------------------------------------ K5
@@ -575,18 +605,24 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     const uint32_t tiles = ((L.rw + 7) / 8) * ((L.rh + 3) / 4);
     const int qgrid = ctx->num_sms * 16;
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[0], st));
-    k_primary<<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status);
+    unsigned long long *sPrim = ctx->ray_counts + 8, *sSec = ctx->ray_counts + 16, *sShadow = ctx->ray_counts + 24;
+    const bool stats = ctx->collect_stats;
+    if (stats) k_primary<true><<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status, sPrim);
+    else k_primary<false><<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status, sPrim);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[1], st));
     k_shade_primary<<<rt_div_up(P, kBlock), kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
                                                              ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
-    k_trace_queue<false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status);
+    if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
+    else k_trace_queue<false, false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
-    k_trace_queue<true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status);
+    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
+    else k_trace_queue<true, false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
     k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
-    k_trace_queue<true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status);
+    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
+    else k_trace_queue<true, false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;

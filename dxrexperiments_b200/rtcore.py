@@ -73,6 +73,8 @@ def _load():
         "rt_dispatch_rays": (i32, [vp, vp, u32, u32, u32]),
         "rt_dispatch_rays_region": (i32, [vp, vp, u32, u32, u32, u32, u32, u32]),
         "rt_get_ray_counts": (i32, [vp, vp, i32]),
+        "rt_enable_trace_stats": (i32, [vp, i32]),
+        "rt_get_trace_stats": (i32, [vp, vp, vp, vp, i32]),
         "rt_enable_stage_timing": (i32, [vp, i32]),
         "rt_get_stage_timing": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), i32]),
         "rt_denoise": (i32, [vp, vp, vp, vp, vp, u32, u32, vp]),
@@ -277,6 +279,24 @@ class Context:
         check(lib.rt_get_ray_counts(self.handle, C.byref(c), 1 if reset else 0))
         return c
 
+    def enable_trace_stats(self, on=True):
+        check(lib.rt_enable_trace_stats(self.handle, 1 if on else 0))
+
+    def trace_stats(self, reset=False):
+        """(primary, secondary, shadow) TraceStats of the instrumented dispatches so far."""
+        out = [T.TraceStats() for _ in range(3)]
+        check(lib.rt_get_trace_stats(self.handle, C.byref(out[0]), C.byref(out[1]), C.byref(out[2]), 1 if reset else 0))
+        return out
+
+    def enable_stage_timing(self, on=True):
+        check(lib.rt_enable_stage_timing(self.handle, 1 if on else 0))
+
+    def stage_timing(self, reset=False):
+        """Accumulated device milliseconds of the (primary, secondary, shadow) trace kernels."""
+        p, s, sh = C.c_double(), C.c_double(), C.c_double()
+        check(lib.rt_get_stage_timing(self.handle, C.byref(p), C.byref(s), C.byref(sh), 1 if reset else 0))
+        return p.value, s.value, sh.value
+
 
 def _ptr(x):
     if x is None:
@@ -348,7 +368,10 @@ PROGRESSIVE, REALTIME = 0, 1
 class Renderer:
     """Convenience host for tests/bench: one scene (instances of meshes), one program, fp32 outputs on the device."""
 
-    def __init__(self, ctx: Context, meshes, transforms, materials, env_texels, kind=PROGRESSIVE, width=256, height=256):
+    def __init__(self, ctx: Context, meshes, transforms, materials, env_texels, kind=PROGRESSIVE, width=256, height=256,
+                 outputs=None):
+        """outputs: optional list of caller-owned device buffers (anything with .ptr, e.g. a wrapped torch tensor)
+        of width*height RGBA fp32, one per output slot; allocated here when omitted."""
         self.ctx, self.width, self.height, self.kind = ctx, width, height, kind
         self.blases = [ctx.build_blas_from_mesh(m) for m in meshes]
         self.tlas = ctx.build_tlas(self.blases, transforms)
@@ -357,7 +380,9 @@ class Renderer:
             for ray_type in range(2):
                 self.program.set_hit_record(ray_type, i, b.vb, b.ib, mat)
         self.program.set_env(env_texels)
-        self.out = [ctx.alloc(16 * width * height).zero() for _ in range(2 if kind == REALTIME else 1)]
+        n_out = 2 if kind == REALTIME else 1
+        self.out = list(outputs) if outputs is not None else [ctx.alloc(16 * width * height).zero() for _ in range(n_out)]
+        assert len(self.out) == n_out
 
     def dispatch(self, frame: T.PerFrameConstants, region=None):
         # global root arguments are (re)bound per dispatch, as render() does (ProgressiveRaytracingPipeline.cpp:236-242)

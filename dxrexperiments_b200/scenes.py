@@ -137,10 +137,14 @@ def bunny_scale(subdivisions: int = 6, seed: int = 1234, amplitude: float = 0.1)
         disp += np.sin(p @ k + ph)
     disp *= amplitude / 6.0 * 2.0
     p = p * (1.0 + disp)[:, None]
-    p = p * 4.0 + np.array([0.0, 4.5, 0.0])  # sits above the ground, in front of the reference camera target
+    # Framed by the reference camera (eye (8,10,30) -> (0,1.5,0)): the model fills about half of a 16:9 frame.  The
+    # ground sits at y = -0.5 so that the reference's point light at the origin lies between the ground and the
+    # model's underside instead of exactly in the ground plane (in-plane shadow rays have a zero direction
+    # component, which turns the y slab of every box test into NaN and makes those rays visit the whole column).
+    p = p * 7.0 + np.array([0.0, 7.6, 0.0])
     n = _smooth_normals(p, s.indices.astype(np.int64))
     body = _pack(p, n, s.indices)
-    ground = quad((-40, 0, 40), (40, 0, 40), (40, 0, -40), (-40, 0, -40))
+    ground = quad((-25, -0.5, 25), (25, -0.5, 25), (25, -0.5, -25), (-25, -0.5, -25))
     return merge([body, ground])
 
 
@@ -282,6 +286,9 @@ def jitter_sequence(seed: int, frames: int, width: int, height: int) -> np.ndarr
     u = rng.random(size=(frames, 2), dtype=np.float32)
     return ((u - np.float32(0.5)) / np.array([width, height], dtype=np.float32)).astype(np.float32)
 
+
+# Camera of the C2/C5 benchmark scene: the bunny-scale model covers ~36 % of a 16:9 frame, the ground ~28 %.
+BUNNY_CAMERA = Camera(eye=(6.0, 10.0, 19.0), at=(0.0, 7.0, 0.0))
 
 REFERENCE_MATERIAL = dict(albedo=(0.95, 0.05, 0.0, 1.0), specular=(0.58, 0.58, 0.58, 1.0), emissive=(0, 0, 0, 0),
                           reflectivity=0.7, roughness=0.5, IoR=0.0, type=1)  # src/DXRExperimentsApp.cpp:98-103

@@ -141,6 +141,11 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
                             uint32_t y0, uint32_t x1, uint32_t y1);
 /* Rays traced by all dispatches since the last reset (synchronises). */
 int rt_get_ray_counts(rt_context *ctx, rt_ray_counts *counts, int reset);
+/* Instrumented traversal: while enabled, dispatches run trace kernels that count node visits and triangle tests
+ * per stage (primary / incoherent secondary / shadow).  These counts are the n_int and n_leaf of the roofline's
+ * algorithmic bytes per ray; instrumented passes are never the ones that are timed. */
+int rt_enable_trace_stats(rt_context *ctx, int enable);
+int rt_get_trace_stats(rt_context *ctx, rt_trace_stats *primary, rt_trace_stats *secondary, rt_trace_stats *shadow, int reset);
 /* Optional per-stage device timing (CUDA events around the trace kernels; synchronises the host once per
  * dispatch while enabled, so it is for profiling runs, not for the headline measurement).  Times are
  * accumulated milliseconds: primary closest-hit, incoherent secondary closest-hit, shadow any-hit. */

@@ -83,7 +83,7 @@ def cornell_case():
 
 
 def bunny_case(subdiv=4):
-    return SceneCase([scenes.bunny_scale(subdiv)])
+    return SceneCase([scenes.bunny_scale(subdiv)], camera=scenes.BUNNY_CAMERA)
 
 
 def two_material_case():
