@@ -21,6 +21,7 @@
 
 #include "shade.cuh"
 #include "trace.cuh"
+#include "trace_persistent.cuh"
 
 namespace {
 
@@ -552,6 +553,17 @@ int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws) {
     return RT_OK;
 }
 
+// Persistent kernels run one wave: as many 128-thread blocks as fit on the device at once.
+template <bool ANY>
+int pgrid(rt_context *ctx) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persistent<ANY>, 128, 0) != cudaSuccess || blocks_per_sm < 1)
+            blocks_per_sm = 4;
+    }
+    return ctx->num_sms * blocks_per_sm;
+}
+
 int upload_records(rt_program *prog) {
     if (!prog->dirty) return RT_OK;
     rt_context *ctx = prog->ctx;
@@ -614,15 +626,15 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
                                                              ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
     if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
-    else k_trace_queue<false, false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
+    else k_trace_persistent<false><<<pgrid<false>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, QueueSink<false>{ws.secHitA, ws.secRec, nullptr}, ctx->status, ws.counters + 4);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
-    else k_trace_queue<true, false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
+    else k_trace_persistent<true><<<pgrid<true>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, QueueSink<true>{nullptr, nullptr, ws.vis0}, ctx->status, ws.counters + 5);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
     k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
-    else k_trace_queue<true, false><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
+    else k_trace_persistent<true><<<pgrid<true>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, QueueSink<true>{nullptr, nullptr, ws.vis1}, ctx->status, ws.counters + 6);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;
