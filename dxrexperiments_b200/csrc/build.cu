@@ -447,12 +447,63 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
     }
 }
 
+// BVH2 -> BVH4 for the traversal kernels.  Thread i opens node i's two children and then, twice, the internal slot
+// with the largest surface area (half-extent product sum), reading the child boxes straight from the BVH2 wide nodes.
+__global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide, uint32_t n_internal, rt_wide4_node *wide4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    float4 c[4], h[4];  // {center, ref}, {half, -}
+    int cnt = 2;
+    {
+        const float4 *w = reinterpret_cast<const float4 *>(wide + i);
+        const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        c[0] = w0, h[0] = w1;
+        c[1] = make_float4(w2.x, w2.y, w2.z, w1.w), h[1] = w3;
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        int best = -1;
+        float bestArea = -1.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt && !(__float_as_uint(c[k].w) & RT_NODE_LEAF_FLAG)) {
+                const float a = h[k].x * h[k].y + h[k].y * h[k].z + h[k].z * h[k].x;
+                if (a > bestArea) bestArea = a, best = k;
+            }
+        }
+        if (best < 0) break;
+        float4 bc = c[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (k == best) bc = c[k];
+        const float4 *w = reinterpret_cast<const float4 *>(wide + __float_as_uint(bc.w));
+        const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k == best) c[k] = w0, h[k] = w1;
+            if (k == cnt) c[k] = make_float4(w2.x, w2.y, w2.z, w1.w), h[k] = w3;
+        }
+        cnt++;
+    }
+    float4 *o = reinterpret_cast<float4 *>(wide4 + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < cnt) {
+            o[2 * k] = c[k];
+            o[2 * k + 1] = make_float4(h[k].x, h[k].y, h[k].z, 0.0f);
+        } else {
+            o[2 * k] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_WIDE4_EMPTY));
+            o[2 * k + 1] = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
+        }
+    }
+}
+
 __global__ void k_write_headers(uint8_t *result, rt_bvh_offsets off, rt_ext_header ext, uint64_t ext_offset) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *reinterpret_cast<rt_bvh_offsets *>(result) = off;
         rt_ext_header *e = reinterpret_cast<rt_ext_header *>(result + ext_offset);
         e->magic = ext.magic, e->count = ext.count, e->root_ref = ext.root_ref, e->top_level = ext.top_level;
-        e->off_wide = ext.off_wide, e->off_leaf = ext.off_leaf;
+        e->off_wide = ext.off_wide, e->off_leaf = ext.off_leaf, e->off_wide4 = ext.off_wide4;
         e->_pad0 = e->_pad1 = 0;
         if (ext.count == 0) {
             // empty TLAS: node 0 is a zero box with zero flags (FL/TopLevelPrepareForComputeAABBs.hlsl:40-48)
@@ -560,7 +611,12 @@ __global__ void __launch_bounds__(kThreads) k_rearrange_instances(const rt_bvh_m
 #pragma unroll
     for (int k = 0; k < 12; ++k) pi.w2o[k] = __uint_as_float(w[k]);
     pi.instance_id_and_mask = w[12];
-    pi.hit_group_and_flags = w[13];
+    // rt_core-private marker (bit 7 of the flags byte, unused by D3D12): world->object is the identity, so the
+    // traversal kernels may keep the world-space ray constants (trace_persistent.cuh).  -0 compares equal to 0.
+    bool ident = true;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) ident = ident && (pi.w2o[k] == ((k == 0 || k == 5 || k == 10) ? 1.0f : 0.0f));
+    pi.hit_group_and_flags = (w[13] & ~RT_PACKED_INSTANCE_IDENTITY) | (ident ? RT_PACKED_INSTANCE_IDENTITY : 0u);
     pi.instance_index = w[28];
     const uint8_t *blas = reinterpret_cast<const uint8_t *>(uintptr_t(uint64_t(w[14]) | (uint64_t(w[15]) << 32)));
     const rt_bvh_offsets *bo = reinterpret_cast<const rt_bvh_offsets *>(blas);
@@ -568,7 +624,8 @@ __global__ void __launch_bounds__(kThreads) k_rearrange_instances(const rt_bvh_m
     pi.blas_root_ref = be->root_ref;
     pi.blas_wide = reinterpret_cast<const rt_wide_node *>(blas + be->off_wide);
     pi.blas_tris = reinterpret_cast<const rt_packed_tri *>(blas + be->off_leaf);
-    pi._pad[0] = pi._pad[1] = 0;
+    pi.blas_wide4 = reinterpret_cast<const rt_wide4_node *>(blas + be->off_wide4);
+    pi._pad = 0;
     packed[dst] = pi;
 }
 
@@ -616,7 +673,7 @@ Layout make_layout(uint32_t n, bool top) {
 
 struct ResultLayout {
     rt_bvh_offsets off;
-    uint64_t ext, wide, leaf, total;
+    uint64_t ext, wide, leaf, wide4, total;
 };
 ResultLayout make_result_layout(uint32_t n, bool top) {
     ResultLayout R{};
@@ -631,9 +688,10 @@ ResultLayout make_result_layout(uint32_t n, bool top) {
         R.off.totalSize = R.off.offsetToPrimitiveMetaData + 12 * n;
     }
     R.ext = align_up(R.off.totalSize, 64);
-    R.wide = R.ext + 64;
+    R.wide = R.ext + sizeof(rt_ext_header);
     R.leaf = R.wide + 64ull * std::max(1u, n > 0 ? n - 1 : 0u);
-    R.total = R.leaf + (top ? 96ull : 48ull) * std::max(n, 1u);
+    R.wide4 = align_up(R.leaf + (top ? 96ull : 48ull) * std::max(n, 1u), 128);
+    R.total = R.wide4 + 128ull * std::max(1u, n > 0 ? n - 1 : 0u);
     return R;
 }
 
@@ -749,6 +807,10 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint8_t *scratch,
                                                 perm, wide, ext);
     }
     ctx->launches += 2;
+    if (n > 1) {
+        k_collapse4<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(wide, n - 1, reinterpret_cast<rt_wide4_node *>(result + R.wide4));
+        ctx->launches++;
+    }
     RT_LAUNCH_CHECK();
     return RT_OK;
 }
@@ -761,6 +823,7 @@ static int write_headers(rt_context *ctx, uint32_t n, bool top, uint8_t *result,
     e.top_level = top ? 1u : 0u;
     e.off_wide = R.wide;
     e.off_leaf = R.leaf;
+    e.off_wide4 = R.wide4;
     k_write_headers<<<1, 32, 0, ctx->stream>>>(result, R.off, e, R.ext);
     ctx->launches++;
     RT_LAUNCH_CHECK();

@@ -96,19 +96,21 @@ struct rt_program {
 
 #define RT_EXT_MAGIC 0x58425452u /* "RTBX" */
 
-struct rt_ext_header {  // 64 bytes, located at align64(reference blob size)
+struct rt_ext_header {  // 128 bytes, located at align64(reference blob size)
     uint32_t magic;
     uint32_t count;         // number of leaves (triangles or instances)
     uint32_t root_ref;      // reference of the root (leaf ref if count == 1)
     uint32_t top_level;     // 1 for a TLAS
-    uint64_t off_wide;      // byte offset from the start of the result buffer to the wide nodes
+    uint64_t off_wide;      // byte offset from the start of the result buffer to the wide (BVH2) nodes
     uint64_t off_leaf;      // ... to the packed triangles (BLAS) / packed instances (TLAS)
     float root_center[3];   // root box (TLAS: tested once per ray; BLAS: informational)
     uint32_t _pad0;
     float root_half[3];
     uint32_t _pad1;
+    uint64_t off_wide4;     // ... to the 4-wide nodes (rt_wide4_node), one per BVH2 internal node, same indexing
+    uint64_t _pad2[7];
 };
-static_assert(sizeof(rt_ext_header) == 64, "ext header");
+static_assert(sizeof(rt_ext_header) == 128, "ext header");
 
 // Wide node: an internal BVH2 node carrying BOTH child boxes (center/halfDim as the reference stores
 // them) and child references.  64 B = 4 x 16-byte loads.  ref: bit31 set -> leaf slot in the low bits.
@@ -123,6 +125,23 @@ struct __align__(16) rt_wide_node {
     uint32_t _p1;
 };
 static_assert(sizeof(rt_wide_node) == 64, "wide node");
+
+// 4-wide node: the (up to) four descendants of BVH2 node i reached by opening, twice, the internal child with the
+// largest surface area (k_collapse4).  wide4[i] exists for EVERY BVH2 internal node i, so no allocation or queue is
+// needed to build it; a traversal that starts at node 0 only ever touches the nodes reachable through wide4 links.
+// One 128-byte line = 8 x 16-byte loads: q[2k] = {center_k.xyz, ref_k}, q[2k+1] = {half_k.xyz, -}.
+// Boxes are the reference's own center/half values, so a child box test is the arithmetic of RayBoxTest unchanged.
+// Empty slot: ref = RT_WIDE4_EMPTY, center 0, half -1 (the slab test then fails for every ray).
+struct __align__(16) rt_wide4_node {
+    struct {
+        float c[3];
+        uint32_t ref;
+        float h[3];
+        uint32_t _p;
+    } child[4];
+};
+static_assert(sizeof(rt_wide4_node) == 128, "wide4 node");
+#define RT_WIDE4_EMPTY 0x7fffffffu
 
 // Packed triangle: 9 floats + PrimitiveMetaData in 48 B = 3 x 16-byte loads.
 struct __align__(16) rt_packed_tri {
@@ -142,9 +161,11 @@ struct __align__(16) rt_packed_instance {
     uint32_t blas_root_ref;
     const rt_wide_node *blas_wide;
     const rt_packed_tri *blas_tris;
-    uint64_t _pad[2];
+    const rt_wide4_node *blas_wide4;
+    uint64_t _pad;
 };
 static_assert(sizeof(rt_packed_instance) == 96, "packed instance");
+#define RT_PACKED_INSTANCE_IDENTITY 0x80000000u /* in rt_packed_instance.hit_group_and_flags only */
 
 static inline __host__ __device__ uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 

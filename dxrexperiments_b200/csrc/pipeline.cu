@@ -554,11 +554,11 @@ int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws) {
 }
 
 // Persistent kernels run one wave: as many 128-thread blocks as fit on the device at once.
-template <bool ANY>
+template <int MODE>
 int pgrid(rt_context *ctx) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persistent<ANY>, 128, 0) != cudaSuccess || blocks_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persistent<MODE>, 128, 0) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 4;
     }
     return ctx->num_sms * blocks_per_sm;
@@ -626,15 +626,15 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
                                                              ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
     if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
-    else k_trace_persistent<false><<<pgrid<false>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, QueueSink<false>{ws.secHitA, ws.secRec, nullptr}, ctx->status, ws.counters + 4);
+    else k_trace_persistent<0><<<pgrid<0>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, TraceSink{ws.secHitA, ws.secRec, nullptr, nullptr}, ctx->status, ws.counters + 4, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
-    else k_trace_persistent<true><<<pgrid<true>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, QueueSink<true>{nullptr, nullptr, ws.vis0}, ctx->status, ws.counters + 5);
+    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, TraceSink{nullptr, nullptr, ws.vis0, nullptr}, ctx->status, ws.counters + 5, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
     k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
-    else k_trace_persistent<true><<<pgrid<true>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, QueueSink<true>{nullptr, nullptr, ws.vis1}, ctx->status, ws.counters + 6);
+    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;
@@ -664,12 +664,23 @@ static int trace_common(rt_context *ctx, const void *tlas, const rt_ray *rays, u
     RT_REQUIRE(ctx && tlas && (n == 0 || (rays && hits)), "null argument");
     RT_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return RT_OK;
-    const int grid = int(std::min<uint64_t>(rt_div_up(n, kBlock), uint64_t(ctx->num_sms) * 16));
-    if (stats)
+    if (stats) {
+        // instrumented: the one-thread-one-ray BVH2 loop in the reference's visit order (its counters are the roofline's n_int / n_leaf)
+        const int grid = int(std::min<uint64_t>(rt_div_up(n, kBlock), uint64_t(ctx->num_sms) * 16));
         k_trace_rays<true><<<grid, kBlock, 0, ctx->stream>>>(tlas, rays, n, flags, mask, hits, reinterpret_cast<unsigned long long *>(stats), ctx->status);
-    else
-        k_trace_rays<false><<<grid, kBlock, 0, ctx->stream>>>(tlas, rays, n, flags, mask, hits, nullptr, ctx->status);
-    ctx->launches++;
+        ctx->launches++;
+    } else {
+        // production traversal (persistent warps over the 4-wide nodes), in chunks of < 2^31 rays
+        uint32_t *counter = ctx->status + 16;
+        for (uint64_t done = 0; done < n;) {
+            const uint32_t chunk = uint32_t(std::min<uint64_t>(n - done, 1u << 30));
+            RT_CUDA(cudaMemsetAsync(counter, 0, 4, ctx->stream));
+            k_trace_persistent<2><<<pgrid<2>(ctx), 128, 0, ctx->stream>>>(tlas, rays + done, nullptr, chunk, TraceSink{nullptr, nullptr, nullptr, hits + done},
+                                                                         ctx->status, counter, flags, mask);
+            ctx->launches++;
+            done += chunk;
+        }
+    }
     RT_LAUNCH_CHECK();
     return RT_OK;
 }

@@ -1,65 +1,128 @@
-// trace_persistent.cuh — persistent-warp queue traversal with dynamic ray replacement.
+// trace_persistent.cuh — persistent-warp traversal with dynamic ray replacement over 4-wide nodes.
 //
 // The plain one-thread-one-ray loop (trace.cuh) runs incoherent rays at ~5 of 32 lanes active: rays in a warp
 // finish after wildly different numbers of node visits and the warp waits for its longest ray
-// (profiles/r1_ncu_trace_baseline.md).  This kernel keeps the same traversal semantics and ORDER (so hits,
-// ties and visit counts are those of the reference restatement) but schedules the work differently:
+// (profiles/r1_ncu_trace_baseline.md).  This kernel computes the same hits (same box and triangle arithmetic, same
+// acceptance rule t < tCommitted && t > tMin) but schedules the work differently:
 //   * persistent warps pull rays from a global counter; when at least kFetchThreshold lanes are idle the warp
 //     refills exactly those lanes (Aila & Laine's "dynamic fetch", warp-synchronous via __ballot_sync);
 //   * internal-node steps and leaf steps are separate warp-wide phases: a lane that reaches a leaf parks until
 //     kLeafThreshold lanes hold one (or nobody can advance), so the triangle test never runs for 1-2 lanes;
-//   * node fetches are four 16-byte loads, triangle fetches three.
+//   * an internal step reads ONE 128-byte rt_wide4_node (eight 16-byte loads) and tests four boxes, i.e. two BVH2
+//     levels per dependent memory round trip — the kernel was latency-bound on the chain of node fetches
+//     (profiles/r1_ncu_trace_persistent.md); hits are ordered near-to-far with a 5-exchange network on integer keys;
+//   * pushed nodes carry their entry distance and are dropped at pop time once a closer hit is committed;
+//   * the ray constants are only recomputed when the instance transform actually changes them.
+// MODE 0: closest hit, ray flags 0 (secondary rays of the pipelines)  -> compact hit records
+// MODE 1: any hit (shadow rays: ACCEPT_FIRST_HIT | SKIP_CLOSEST_HIT)   -> visibility bytes
+// MODE 2: caller-supplied ray flags / instance mask, full rt_hit records (rt_trace_rays)
 #pragma once
 #include "trace.cuh"
 
-constexpr int kFetchThreshold = 8;   // refill when >= this many lanes are idle
-constexpr int kLeafThreshold = 8;    // run a leaf phase when >= this many lanes hold a leaf
+#ifndef RT_FETCH_THRESHOLD
+#define RT_FETCH_THRESHOLD 12
+#endif
+#ifndef RT_LEAF_THRESHOLD
+#define RT_LEAF_THRESHOLD 8
+#endif
+constexpr int kFetchThreshold = RT_FETCH_THRESHOLD;  // refill when >= this many lanes are idle
+constexpr int kLeafThreshold = RT_LEAF_THRESHOLD;    // run a leaf phase when >= this many lanes hold a leaf
 
-template <bool ANY>
-struct QueueSink {  // where results of the ray queue go
-    float4 *hitA;
-    uint32_t *hitRec;
-    uint8_t *vis;
-    __device__ __forceinline__ void miss_inactive(uint32_t i) const {
-        if (ANY) vis[i] = 1;
-        else hitA[i] = make_float4(0, 0, 0, __uint_as_float(RT_NO_HIT)), hitRec[i] = 0xffffffffu;
-    }
+// A ray whose origin and direction hold no -0 and no Inf/NaN maps to ITSELF, bit for bit, under an identity
+// world->object transform (x*1 + y*0 + z*0 (+0) == x), so its world-space constants stay valid inside the BLAS.
+__device__ __forceinline__ bool plain_float(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return b != 0x80000000u && (b & 0x7f800000u) != 0x7f800000u;
+}
+
+struct TraceSink {  // where results go; only the members of the kernel's MODE are used
+    float4 *hitA;       // MODE 0: t, u, v, primitive
+    uint32_t *hitRec;   // MODE 0: hit-group record index
+    uint8_t *vis;       // MODE 1: 1 = unoccluded
+    rt_hit *hits;       // MODE 2
 };
 
-template <bool ANY>
-__global__ void __launch_bounds__(128) k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult,
-                                                          QueueSink<ANY> sink, uint32_t *status, uint32_t *nextRay) {
-    const uint32_t n = count[0] * mult;
+#ifndef RT_PERSIST_MIN_BLOCKS
+#define RT_PERSIST_MIN_BLOCKS 8
+#endif
+#ifndef RT_PERSIST_LDG256
+#define RT_PERSIST_LDG256 1  // fetch 4-wide nodes with four 256-bit loads instead of eight 128-bit ones
+#endif
+#ifndef RT_PERSIST_WIDE4
+#define RT_PERSIST_WIDE4 1  // 1: traverse the 4-wide nodes (rt_wide4_node); 0: the BVH2 wide nodes (A/B measurements)
+#endif
+
+// Sorting key of a child hit: the entry distance (>= 0, so its bits order like the float) with the slot number in
+// the two lowest mantissa bits; a miss sorts last.
+__device__ __forceinline__ uint32_t hit_key(bool hit, float t, uint32_t slot) {
+    return hit ? ((__float_as_uint(t) & 0x7ffffffcu) | slot) : 0xffffffffu;
+}
+__device__ __forceinline__ void key_cas(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo, b = hi;
+}
+__device__ __forceinline__ uint32_t ref_of(uint32_t key, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    const uint32_t lo = (key & 1u) ? r1 : r0, hi = (key & 1u) ? r3 : r2;
+    return (key & 2u) ? hi : lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, RT_PERSIST_MIN_BLOCKS)
+k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult, TraceSink sink, uint32_t *status,
+                   uint32_t *nextRay, uint32_t userFlags, uint32_t userMask) {
+    constexpr bool GENERAL = MODE == 2;
+    const uint32_t n = count ? count[0] * mult : mult;  // standalone launches pass the ray count in `mult`
     const TraceAccel A = resolve_tlas(tlas);
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t rayFlags = ANY ? (RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER) : 0u;
-    constexpr uint32_t rayContribution = ANY ? 1u : 0u;  // shadow rays use hit group 1 (S/RaytracingCommon.hlsli:94)
+    const uint32_t rayFlags = GENERAL ? userFlags
+                                      : (MODE == 1 ? (RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER) : 0u);
+    const bool ANY = GENERAL ? (userFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0 : (MODE == 1);
+    const uint32_t instMask = GENERAL ? userMask : 0xFFu;  // InstanceInclusionMask is 0xFF for every ray of the pipelines
+    constexpr uint32_t rayContribution = MODE == 1 ? 1u : 0u;  // shadow rays use hit group 1 (S/RaytracingCommon.hlsli:94)
 
     uint32_t stack[RT_STACK_SIZE];
+#if RT_PERSIST_WIDE4
+    uint32_t stackT[MODE == 1 ? 1 : RT_STACK_SIZE];  // entry distance of each pushed node (culled at pop)
+#endif
     // per-lane ray state
     bool alive = false;
     uint32_t rayIdx = 0, ref = RT_SENTINEL;
     int sp = 0, blasBase = -1;
     bool bottom = false;
+    bool plain = false;      // the world ray holds no -0 / Inf / NaN component
+    bool sameSpace = false;  // inside a BLAS whose instance transform left the ray constants untouched
     float wox = 0, woy = 0, woz = 0, wdx = 0, wdy = 0, wdz = 1, tmin = 0, tCur = 0;
     RayPre cur;
     cur.ox = cur.oy = cur.oz = cur.ix = cur.iy = cur.iz = cur.oix = cur.oiy = cur.oiz = cur.sx = cur.sy = cur.sz = 0;
     cur.kx = 0, cur.ky = 1, cur.kz = 2;
-    const rt_wide_node *nodes = A.wide;
+#if RT_PERSIST_WIDE4
+    const rt_wide4_node *const topNodes = A.wide4;
+    const rt_wide4_node *nodes = topNodes;
+#else
+    const rt_wide_node *const topNodes = A.wide;
+    const rt_wide_node *nodes = topNodes;
+#endif
     const rt_packed_tri *tris = nullptr;
     uint32_t instFlags = 0, instOffset = 0;
     int cull = 0;
     float hu = 0, hv = 0;
     uint32_t hprim = RT_NO_HIT, hrec = 0;
+    // MODE 2 only: identity of the instance being traversed and of the committed hit
+    uint32_t instIndex = 0, instId = 0, hInst = 0, hGeom = 0, hId = 0, hSlot = 0;
     bool noMore = (A.count == 0 && n == 0);
 
     auto finish = [&]() {  // write the result of a finished ray
-        if (ANY) sink.vis[rayIdx] = (hprim != RT_NO_HIT) ? 0 : 1;
-        else {
+        if (MODE == 1) {
+            sink.vis[rayIdx] = (hprim != RT_NO_HIT) ? 0 : 1;
+        } else if (MODE == 0) {
             sink.hitA[rayIdx] = make_float4(tCur, hu, hv, __uint_as_float(hprim));
             sink.hitRec[rayIdx] = hrec;
+        } else {
+            uint4 *hp = reinterpret_cast<uint4 *>(sink.hits + rayIdx);
+            hp[0] = make_uint4(__float_as_uint(tCur), __float_as_uint(hu), __float_as_uint(hv), hprim);
+            hp[1] = make_uint4(hInst, hGeom, hId, hSlot);
         }
         alive = false;
     };
@@ -80,16 +143,21 @@ __global__ void __launch_bounds__(128) k_trace_persistent(const void *tlas, cons
                 if (rayIdx < n) {
                     const float4 *rp = reinterpret_cast<const float4 *>(rays + rayIdx);
                     const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
-                    if (b.w < 0.0f || A.count == 0) {
-                        sink.miss_inactive(rayIdx);
+                    wox = a.x, woy = a.y, woz = a.z, tmin = a.w, wdx = b.x, wdy = b.y, wdz = b.z, tCur = b.w;
+                    hprim = RT_NO_HIT, hu = hv = 0.0f, hrec = 0;
+                    if (GENERAL) hInst = hGeom = hId = hSlot = 0;
+                    alive = true;
+                    if (b.w < 0.0f || A.count == 0) {  // inactive queue slot / empty scene: a miss
+                        if (MODE == 0) hrec = 0xffffffffu;
+                        if (MODE == 0 && b.w < 0.0f) tCur = 0.0f;
+                        finish();
                     } else {
-                        wox = a.x, woy = a.y, woz = a.z, tmin = a.w, wdx = b.x, wdy = b.y, wdz = b.z, tCur = b.w;
-                        hprim = RT_NO_HIT, hu = hv = 0.0f, hrec = 0;
-                        cur = make_ray_pre(wox, woy, woz, wdx, wdy, wdz);
-                        nodes = A.wide;
-                        bottom = false, blasBase = -1, sp = 0;
+                        ray_pre_box(cur, wox, woy, woz, wdx, wdy, wdz);  // the TLAS level tests boxes only
+                        plain = plain_float(wox) && plain_float(woy) && plain_float(woz) && plain_float(wdx) && plain_float(wdy) &&
+                                plain_float(wdz);
+                        nodes = topNodes;
+                        bottom = false, sameSpace = false, blasBase = -1, sp = 0;
                         float tU;
-                        alive = true;
                         if (ray_box(tU, tCur, cur, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2]))
                             ref = A.root_ref;
                         else
@@ -116,13 +184,11 @@ __global__ void __launch_bounds__(128) k_trace_persistent(const void *tlas, cons
                     // TLAS leaf: TraverseFunction.hlsli:598-634
                     const uint4 *ip = reinterpret_cast<const uint4 *>(A.inst + slot);
                     const uint4 m3 = __ldg(ip + 3);
-                    if ((m3.x >> 24) & 0xFFu) {  // InstanceInclusionMask is 0xFF for every ray of the pipelines
-                        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(ip));
-                        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(ip + 1));
-                        const float4 r2 = __ldg(reinterpret_cast<const float4 *>(ip + 2));
+                    if ((m3.x >> 24) & instMask) {
                         const uint4 m4 = __ldg(ip + 4);
                         instFlags = m3.y >> 24;
                         instOffset = m3.y & 0x00ffffffu;
+                        if (GENERAL) instIndex = m3.z, instId = m3.x & 0x00ffffffu;
                         {
                             const bool useCulling = !(instFlags & RT_INSTANCE_FLAG_TRIANGLE_CULL_DISABLE);
                             const bool flip = (instFlags & RT_INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE) != 0;
@@ -130,35 +196,99 @@ __global__ void __launch_bounds__(128) k_trace_persistent(const void *tlas, cons
                             const uint32_t frontFlag = flip ? RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES : RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES;
                             cull = (useCulling && (rayFlags & frontFlag)) ? 2 : ((useCulling && (rayFlags & backFlag)) ? 1 : 0);
                         }
-                        const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-                        const f3 o2 = xform_point(m, mk3(wox, woy, woz));
-                        const f3 d2 = xform_vector(m, mk3(wdx, wdy, wdz));
-                        cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                        sameSpace = plain && (m3.y & RT_PACKED_INSTANCE_IDENTITY);
+                        if (sameSpace) {
+                            ray_pre_shear(cur, wdx, wdy, wdz);
+                        } else {
+                            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(ip));
+                            const float4 r1 = __ldg(reinterpret_cast<const float4 *>(ip + 1));
+                            const float4 r2 = __ldg(reinterpret_cast<const float4 *>(ip + 2));
+                            const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                            const f3 o2 = xform_point(m, mk3(wox, woy, woz));
+                            const f3 d2 = xform_vector(m, mk3(wdx, wdy, wdz));
+                            cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                        }
+#if RT_PERSIST_WIDE4
+                        nodes = reinterpret_cast<const rt_wide4_node *>(__ldg(reinterpret_cast<const unsigned long long *>(ip + 5)));
+#else
                         nodes = reinterpret_cast<const rt_wide_node *>(uintptr_t(uint64_t(m4.x) | (uint64_t(m4.y) << 32)));
+#endif
                         tris = reinterpret_cast<const rt_packed_tri *>(uintptr_t(uint64_t(m4.z) | (uint64_t(m4.w) << 32)));
                         bottom = true;
                         blasBase = sp;
-                        ref = m3.w;
+                        ref = m3.w;  // BLAS root (entered without a box test, as the reference does)
                     }
                 } else {
                     // BLAS leaf: TraverseFunction.hlsli:635-735
                     const float4 *tp = reinterpret_cast<const float4 *>(tris + slot);
                     const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-                    // every geometry of the pipelines is hit by these rays: their flags carry no FORCE_* / CULL_(NON_)OPAQUE bits
+                    bool culled = false;
+                    if (GENERAL) {  // IsOpaque() and the CULL_(NON_)OPAQUE ray flags (:119-134); the pipelines' rays carry none
+                        const uint32_t gflags = __float_as_uint(p2.w);
+                        bool opaque = (gflags & RT_GEOMETRY_FLAG_OPAQUE) != 0;
+                        if (instFlags & RT_INSTANCE_FLAG_FORCE_OPAQUE) opaque = true;
+                        else if (instFlags & RT_INSTANCE_FLAG_FORCE_NON_OPAQUE) opaque = false;
+                        if (rayFlags & RT_RAY_FLAG_FORCE_OPAQUE) opaque = true;
+                        else if (rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
+                        culled = (opaque && (rayFlags & RT_RAY_FLAG_CULL_OPAQUE)) || (!opaque && (rayFlags & RT_RAY_FLAG_CULL_NON_OPAQUE));
+                    }
                     float t0 = tCur, bu, bv;
-                    if (ray_triangle(t0, bu, bv, cull, cur, p0, p1, p2.x) && t0 < tCur && t0 > tmin) {
+                    if (!culled && ray_triangle(t0, bu, bv, cull, cur, p0, p1, p2.x) && t0 < tCur && t0 > tmin) {
                         tCur = t0, hu = bu, hv = bv;
                         hprim = __float_as_uint(p2.y);
                         hrec = rayContribution + instOffset;  // geometry multiplier is 0 in both shader libraries
-                        if (ANY) {
-                            finish();
-                        }
+                        if (GENERAL) hInst = instIndex, hId = instId, hGeom = __float_as_uint(p2.z), hSlot = slot;
+                        if (ANY) finish();
                     }
                 }
             }
         } else {
             // ---------------------------------------------------------------- internal phase
             if (alive && !atLeaf) {
+#if RT_PERSIST_WIDE4
+                // one 128-byte node = four child boxes (two BVH2 levels per dependent fetch)
+                const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
+#if RT_PERSIST_LDG256
+                float4 c0, h0, c1, h1, c2, h2, c3, h3;
+                ldg256(np, c0, h0), ldg256(np + 2, c1, h1), ldg256(np + 4, c2, h2), ldg256(np + 6, c3, h3);
+#else
+                const float4 c0 = __ldg(np), h0 = __ldg(np + 1), c1 = __ldg(np + 2), h1 = __ldg(np + 3);
+                const float4 c2 = __ldg(np + 4), h2 = __ldg(np + 5), c3 = __ldg(np + 6), h3 = __ldg(np + 7);
+#endif
+                float t0, t1, t2, t3;
+                const bool b0 = ray_box(t0, tCur, cur, c0.x, c0.y, c0.z, h0.x, h0.y, h0.z);
+                const bool b1 = ray_box(t1, tCur, cur, c1.x, c1.y, c1.z, h1.x, h1.y, h1.z);
+                const bool b2 = ray_box(t2, tCur, cur, c2.x, c2.y, c2.z, h2.x, h2.y, h2.z);
+                const bool b3 = ray_box(t3, tCur, cur, c3.x, c3.y, c3.z, h3.x, h3.y, h3.z);
+                uint32_t k0 = hit_key(b0, t0, 0), k1 = hit_key(b1, t1, 1), k2 = hit_key(b2, t2, 2), k3 = hit_key(b3, t3, 3);
+                key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
+                const uint32_t r0 = __float_as_uint(c0.w), r1 = __float_as_uint(c1.w), r2 = __float_as_uint(c2.w),
+                               r3 = __float_as_uint(c3.w);
+                if (k0 == 0xffffffffu) {
+                    ref = RT_SENTINEL;
+                } else {
+                    ref = ref_of(k0, r0, r1, r2, r3);
+                    if (k1 != 0xffffffffu) {  // push the other hits, farthest first
+                        if (sp + 3 > RT_STACK_SIZE) {
+                            atomicOr(status, 1u);
+                        } else {
+                            if (k3 != 0xffffffffu) {
+                                stack[sp] = ref_of(k3, r0, r1, r2, r3);
+                                if (MODE != 1) stackT[sp] = k3;
+                                sp++;
+                            }
+                            if (k2 != 0xffffffffu) {
+                                stack[sp] = ref_of(k2, r0, r1, r2, r3);
+                                if (MODE != 1) stackT[sp] = k2;
+                                sp++;
+                            }
+                            stack[sp] = ref_of(k1, r0, r1, r2, r3);
+                            if (MODE != 1) stackT[sp] = k1;
+                            sp++;
+                        }
+                    }
+                }
+#else
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
                 float lt, rt;
@@ -175,18 +305,31 @@ __global__ void __launch_bounds__(128) k_trace_persistent(const void *tlas, cons
                 } else {
                     ref = RT_SENTINEL;
                 }
+#endif
             }
         }
         // ------------------------------------------------------------------ pop
         if (alive && ref == RT_SENTINEL) {
-            if (bottom && sp == blasBase) {  // leaving the BLAS: back to the world-space ray
-                bottom = false;
-                cur = make_ray_pre(wox, woy, woz, wdx, wdy, wdz);
-                nodes = A.wide;
-                blasBase = -1;
+            for (;;) {
+                if (sp == 0) {
+                    finish();
+                    break;
+                }
+                if (bottom && sp == blasBase) {  // leaving the BLAS: back to the world-space ray (boxes only up there)
+                    bottom = false;
+                    if (!sameSpace) ray_pre_box(cur, wox, woy, woz, wdx, wdy, wdz);
+                    nodes = topNodes;
+                    blasBase = -1;
+                }
+                --sp;
+#if RT_PERSIST_WIDE4
+                // a node whose entry distance (rounded down when it was pushed) is not in front of the committed hit
+                // cannot hold a closer one
+                if (MODE != 1 && (stackT[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
+#endif
+                ref = stack[sp];
+                break;
             }
-            if (sp == 0) finish();
-            else ref = stack[--sp];
         }
     }
 }

@@ -13,7 +13,7 @@ import numpy as np
 from . import types as T
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "librt_core.so")
+LIB_PATH = os.environ.get("RT_CORE_LIB") or os.path.join(_DIR, "librt_core.so")  # RT_CORE_LIB: development builds with other tuning macros
 HEADER_PATH = os.path.join(_DIR, "..", "include", "rt_core.h")
 
 

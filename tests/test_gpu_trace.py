@@ -67,6 +67,19 @@ def test_incoherent_rays_and_work_counters(flags, ctx, orc):
     assert int(st_g[2]) == st_o.leaf_visits
     assert int(st_g[3]) == st_o.instance_visits
     assert int(st_g[4]) <= 64 and st_o.max_stack <= 64
+    # the production kernel (persistent warps over 4-wide nodes) visits nodes in its own order: the closest hit is
+    # the same triangle with the same bits; for any-hit rays only the visibility is order independent
+    hp = ctx.trace(gtlas, rays, flags)
+    if any_hit:
+        np.testing.assert_array_equal(hp["primitive_index"] == T.NO_HIT, ho["primitive_index"] == T.NO_HIT)
+    else:
+        frac, same = _agreement(hp, ho)
+        assert frac >= 0.9999
+        np.testing.assert_array_equal(hp["t"][same], ho["t"][same])
+        np.testing.assert_array_equal(hp["bary"][same], ho["bary"][same])
+        np.testing.assert_array_equal(hp["leaf_slot"][same], ho["leaf_slot"][same])
+        np.testing.assert_array_equal(hp["instance_id"][same], ho["instance_id"][same])
+        np.testing.assert_array_equal(hp["geometry_index"][same], ho["geometry_index"][same])
 
 
 def _ut_scene(ctx, orc, specs):
