@@ -106,8 +106,14 @@ __device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, un
 }
 
 // ------------------------------------------------------------------------------------------------ K1
+#ifndef RT_PRIMARY_WIDE4
+#define RT_PRIMARY_WIDE4 0  // coherent camera rays: BVH2 wins on L1-resident scenes (5.2 vs 4.2 Grays/s on C2), the 4-wide nodes only beyond ~1 M triangles (2.3 vs 2.1)
+#endif
+#ifndef RT_PRIMARY_MIN_BLOCKS
+#define RT_PRIMARY_MIN_BLOCKS 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status,
+__global__ void __launch_bounds__(kBlock, RT_PRIMARY_MIN_BLOCKS) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status,
                                                     unsigned long long *stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tilesX = (L.rw + 7) / 8;
@@ -121,8 +127,11 @@ __global__ void __launch_bounds__(kBlock) k_primary(const __grid_constant__ Laun
         primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
         TraceAccel A = resolve_tlas(tlas);
         TraceHit h;
-        trace_ray<false, STATS>(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, 0, h,
-                                &ctr, status);
+        if (STATS || !RT_PRIMARY_WIDE4)  // instrumented: BVH2 in the reference's visit order
+            trace_ray<false, STATS>(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, 0, h,
+                                    &ctr, status);
+        else
+            trace_ray4(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, h, status);
         const uint32_t p = ly * L.rw + lx;
         ws.hitA[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
         ws.hitRec[p] = h.record;

@@ -157,6 +157,177 @@ __device__ __forceinline__ TraceAccel resolve_tlas(const void *tlas_result) {
 
 #define RT_SENTINEL 0x7fffffffu  // never a valid internal index (indices are < 2^24)
 
+#ifndef RT_LDG256
+#define RT_LDG256 1  // fetch 4-wide nodes with four 256-bit loads instead of eight 128-bit ones
+#endif
+
+// Sorting key of a child hit: the entry distance (>= 0, so its bits order like the float) with the slot number in
+// the two lowest mantissa bits; a miss sorts last.
+__device__ __forceinline__ uint32_t hit_key(bool hit, float t, uint32_t slot) {
+    return hit ? ((__float_as_uint(t) & 0x7ffffffcu) | slot) : 0xffffffffu;
+}
+__device__ __forceinline__ void key_cas(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo, b = hi;
+}
+__device__ __forceinline__ uint32_t ref_of(uint32_t key, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    const uint32_t lo = (key & 1u) ? r1 : r0, hi = (key & 1u) ? r3 : r2;
+    return (key & 2u) ? hi : lo;
+}
+
+// One internal step over a 4-wide node: test the four child boxes (RayBoxTest arithmetic unchanged), order the
+// hits near-to-far with a 5-exchange network on integer keys, return the nearest and push the others farthest
+// first.  WITH_T: also record each pushed node's entry distance so that it can be dropped at pop time.
+template <bool WITH_T>
+__device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint32_t ref, const RayPre &cur, float tCur, uint32_t *stack,
+                                               uint32_t *stackT, int &sp, uint32_t *status) {
+    const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
+#if RT_LDG256
+    float4 c0, h0, c1, h1, c2, h2, c3, h3;
+    ldg256(np, c0, h0), ldg256(np + 2, c1, h1), ldg256(np + 4, c2, h2), ldg256(np + 6, c3, h3);
+#else
+    const float4 c0 = __ldg(np), h0 = __ldg(np + 1), c1 = __ldg(np + 2), h1 = __ldg(np + 3);
+    const float4 c2 = __ldg(np + 4), h2 = __ldg(np + 5), c3 = __ldg(np + 6), h3 = __ldg(np + 7);
+#endif
+    float t0, t1, t2, t3;
+    const bool b0 = ray_box(t0, tCur, cur, c0.x, c0.y, c0.z, h0.x, h0.y, h0.z);
+    const bool b1 = ray_box(t1, tCur, cur, c1.x, c1.y, c1.z, h1.x, h1.y, h1.z);
+    const bool b2 = ray_box(t2, tCur, cur, c2.x, c2.y, c2.z, h2.x, h2.y, h2.z);
+    const bool b3 = ray_box(t3, tCur, cur, c3.x, c3.y, c3.z, h3.x, h3.y, h3.z);
+    uint32_t k0 = hit_key(b0, t0, 0), k1 = hit_key(b1, t1, 1), k2 = hit_key(b2, t2, 2), k3 = hit_key(b3, t3, 3);
+    key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
+    const uint32_t r0 = __float_as_uint(c0.w), r1 = __float_as_uint(c1.w), r2 = __float_as_uint(c2.w), r3 = __float_as_uint(c3.w);
+    if (k0 == 0xffffffffu) return RT_SENTINEL;
+    if (k1 != 0xffffffffu) {  // push the other hits, farthest first
+        if (sp + 3 > RT_STACK_SIZE) {
+            atomicOr(status, 1u);
+        } else {
+            if (k3 != 0xffffffffu) {
+                stack[sp] = ref_of(k3, r0, r1, r2, r3);
+                if (WITH_T) stackT[sp] = k3;
+                sp++;
+            }
+            if (k2 != 0xffffffffu) {
+                stack[sp] = ref_of(k2, r0, r1, r2, r3);
+                if (WITH_T) stackT[sp] = k2;
+                sp++;
+            }
+            stack[sp] = ref_of(k1, r0, r1, r2, r3);
+            if (WITH_T) stackT[sp] = k1;
+            sp++;
+        }
+    }
+    return ref_of(k0, r0, r1, r2, r3);
+}
+
+// Closest-hit traversal of ONE ray over the 4-wide nodes, for coherent rays (one thread per pixel): the same
+// hits as trace_ray (same box / triangle arithmetic and acceptance rule) in a different visiting order.  No
+// any-hit / opaque-flag handling: the caller's rays carry only cull flags (RayGen: CULL_BACK_FACING_TRIANGLES).
+__device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
+                                           float tmax, uint32_t rayFlags, uint32_t mask, uint32_t rayContribution, TraceHit &hit,
+                                           uint32_t *status) {
+    hit.prim = RT_NO_HIT;
+    hit.t = tmax;
+    hit.u = hit.v = 0.0f;
+    hit.inst_index = hit.geom_index = hit.inst_id = hit.leaf_slot = hit.record = 0;
+    if (A.count == 0) return false;
+    uint32_t stack[RT_STACK_SIZE], stackT[RT_STACK_SIZE];
+    int sp = 0, blasBase = -1;
+    float tCur = tmax;
+    RayPre cur;
+    ray_pre_box(cur, ox, oy, oz, dx, dy, dz);
+    float tUnused;
+    if (!ray_box(tUnused, tCur, cur, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2])) return false;
+    const bool plain = [&] {
+        const float v[6] = {ox, oy, oz, dx, dy, dz};
+        bool p = true;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const uint32_t b = __float_as_uint(v[k]);
+            p = p && b != 0x80000000u && (b & 0x7f800000u) != 0x7f800000u;
+        }
+        return p;
+    }();
+    const rt_wide4_node *nodes = A.wide4;
+    const rt_packed_tri *tris = nullptr;
+    bool bottom = false, sameSpace = false;
+    uint32_t instIndex = 0, instOffset = 0, instId = 0;
+    int cull = 0;
+    uint32_t ref = A.root_ref;
+    while (true) {
+        if (ref & RT_NODE_LEAF_FLAG) {
+            const uint32_t slot = ref & 0x00ffffffu;
+            ref = RT_SENTINEL;
+            if (!bottom) {
+                const uint4 *ip = reinterpret_cast<const uint4 *>(A.inst + slot);
+                const uint4 m3 = __ldg(ip + 3);
+                if ((m3.x >> 24) & mask) {
+                    const uint4 m4 = __ldg(ip + 4);
+                    const uint32_t instFlags = m3.y >> 24;
+                    instIndex = m3.z, instOffset = m3.y & 0x00ffffffu, instId = m3.x & 0x00ffffffu;
+                    const bool useCulling = !(instFlags & RT_INSTANCE_FLAG_TRIANGLE_CULL_DISABLE);
+                    const bool flip = (instFlags & RT_INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE) != 0;
+                    const uint32_t backFlag = flip ? RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES : RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES;
+                    const uint32_t frontFlag = flip ? RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES : RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES;
+                    cull = (useCulling && (rayFlags & frontFlag)) ? 2 : ((useCulling && (rayFlags & backFlag)) ? 1 : 0);
+                    sameSpace = plain && (m3.y & RT_PACKED_INSTANCE_IDENTITY);
+                    if (sameSpace) {
+                        ray_pre_shear(cur, dx, dy, dz);
+                    } else {
+                        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(ip));
+                        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(ip + 1));
+                        const float4 r2 = __ldg(reinterpret_cast<const float4 *>(ip + 2));
+                        const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                        const f3 o2 = xform_point(m, mk3(ox, oy, oz));
+                        const f3 d2 = xform_vector(m, mk3(dx, dy, dz));
+                        cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                    }
+                    nodes = reinterpret_cast<const rt_wide4_node *>(__ldg(reinterpret_cast<const unsigned long long *>(ip + 5)));
+                    tris = reinterpret_cast<const rt_packed_tri *>(uintptr_t(uint64_t(m4.z) | (uint64_t(m4.w) << 32)));
+                    bottom = true;
+                    blasBase = sp;
+                    ref = m3.w;
+                }
+            } else {
+                const float4 *tp = reinterpret_cast<const float4 *>(tris + slot);
+                const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                float t0 = tCur, bu, bv;
+                if (ray_triangle(t0, bu, bv, cull, cur, p0, p1, p2.x) && t0 < tCur && t0 > tmin) {
+                    tCur = t0;
+                    hit.t = t0, hit.u = bu, hit.v = bv;
+                    hit.prim = __float_as_uint(p2.y);
+                    hit.geom_index = __float_as_uint(p2.z);
+                    hit.inst_index = instIndex, hit.inst_id = instId, hit.leaf_slot = slot;
+                    hit.record = rayContribution + instOffset;
+                }
+            }
+        } else {
+            ref = wide4_step<true>(nodes, ref, cur, tCur, stack, stackT, sp, status);
+        }
+        if (ref == RT_SENTINEL) {
+            bool done = false;
+            for (;;) {
+                if (sp == 0) {
+                    done = true;
+                    break;
+                }
+                if (bottom && sp == blasBase) {
+                    bottom = false;
+                    if (!sameSpace) ray_pre_box(cur, ox, oy, oz, dx, dy, dz);
+                    nodes = A.wide4;
+                    blasBase = -1;
+                }
+                --sp;
+                if ((stackT[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
+                ref = stack[sp];
+                break;
+            }
+            if (done) break;
+        }
+    }
+    return hit.prim != RT_NO_HIT;
+}
+
 // Fallback_TraceRay without shader call-outs.  ANY = RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH.
 // rayContribution / geomMultiplier feed the hit-group record index exactly as TraverseFunction.hlsli:684-687.
 template <bool ANY, bool STATS>

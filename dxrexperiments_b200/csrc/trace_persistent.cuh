@@ -45,26 +45,9 @@ struct TraceSink {  // where results go; only the members of the kernel's MODE a
 #ifndef RT_PERSIST_MIN_BLOCKS
 #define RT_PERSIST_MIN_BLOCKS 8
 #endif
-#ifndef RT_PERSIST_LDG256
-#define RT_PERSIST_LDG256 1  // fetch 4-wide nodes with four 256-bit loads instead of eight 128-bit ones
-#endif
 #ifndef RT_PERSIST_WIDE4
 #define RT_PERSIST_WIDE4 1  // 1: traverse the 4-wide nodes (rt_wide4_node); 0: the BVH2 wide nodes (A/B measurements)
 #endif
-
-// Sorting key of a child hit: the entry distance (>= 0, so its bits order like the float) with the slot number in
-// the two lowest mantissa bits; a miss sorts last.
-__device__ __forceinline__ uint32_t hit_key(bool hit, float t, uint32_t slot) {
-    return hit ? ((__float_as_uint(t) & 0x7ffffffcu) | slot) : 0xffffffffu;
-}
-__device__ __forceinline__ void key_cas(uint32_t &a, uint32_t &b) {
-    const uint32_t lo = min(a, b), hi = max(a, b);
-    a = lo, b = hi;
-}
-__device__ __forceinline__ uint32_t ref_of(uint32_t key, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-    const uint32_t lo = (key & 1u) ? r1 : r0, hi = (key & 1u) ? r3 : r2;
-    return (key & 2u) ? hi : lo;
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(128, RT_PERSIST_MIN_BLOCKS)
@@ -247,47 +230,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             if (alive && !atLeaf) {
 #if RT_PERSIST_WIDE4
                 // one 128-byte node = four child boxes (two BVH2 levels per dependent fetch)
-                const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
-#if RT_PERSIST_LDG256
-                float4 c0, h0, c1, h1, c2, h2, c3, h3;
-                ldg256(np, c0, h0), ldg256(np + 2, c1, h1), ldg256(np + 4, c2, h2), ldg256(np + 6, c3, h3);
-#else
-                const float4 c0 = __ldg(np), h0 = __ldg(np + 1), c1 = __ldg(np + 2), h1 = __ldg(np + 3);
-                const float4 c2 = __ldg(np + 4), h2 = __ldg(np + 5), c3 = __ldg(np + 6), h3 = __ldg(np + 7);
-#endif
-                float t0, t1, t2, t3;
-                const bool b0 = ray_box(t0, tCur, cur, c0.x, c0.y, c0.z, h0.x, h0.y, h0.z);
-                const bool b1 = ray_box(t1, tCur, cur, c1.x, c1.y, c1.z, h1.x, h1.y, h1.z);
-                const bool b2 = ray_box(t2, tCur, cur, c2.x, c2.y, c2.z, h2.x, h2.y, h2.z);
-                const bool b3 = ray_box(t3, tCur, cur, c3.x, c3.y, c3.z, h3.x, h3.y, h3.z);
-                uint32_t k0 = hit_key(b0, t0, 0), k1 = hit_key(b1, t1, 1), k2 = hit_key(b2, t2, 2), k3 = hit_key(b3, t3, 3);
-                key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
-                const uint32_t r0 = __float_as_uint(c0.w), r1 = __float_as_uint(c1.w), r2 = __float_as_uint(c2.w),
-                               r3 = __float_as_uint(c3.w);
-                if (k0 == 0xffffffffu) {
-                    ref = RT_SENTINEL;
-                } else {
-                    ref = ref_of(k0, r0, r1, r2, r3);
-                    if (k1 != 0xffffffffu) {  // push the other hits, farthest first
-                        if (sp + 3 > RT_STACK_SIZE) {
-                            atomicOr(status, 1u);
-                        } else {
-                            if (k3 != 0xffffffffu) {
-                                stack[sp] = ref_of(k3, r0, r1, r2, r3);
-                                if (MODE != 1) stackT[sp] = k3;
-                                sp++;
-                            }
-                            if (k2 != 0xffffffffu) {
-                                stack[sp] = ref_of(k2, r0, r1, r2, r3);
-                                if (MODE != 1) stackT[sp] = k2;
-                                sp++;
-                            }
-                            stack[sp] = ref_of(k1, r0, r1, r2, r3);
-                            if (MODE != 1) stackT[sp] = k1;
-                            sp++;
-                        }
-                    }
-                }
+                ref = wide4_step<MODE != 1>(nodes, ref, cur, tCur, stack, stackT, sp, status);
 #else
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
