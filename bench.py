@@ -7,7 +7,9 @@
 Workload (BASELINE.json configs[1], "C2"): the bunny-scale synthetic mesh (displaced icosphere, 81 922 triangles)
 at 1920x1080, 16 spp of the progressive pipeline.  One STEP = one 16-spp progressive frame = 16 DispatchRays.
 Metric: Mrays/s = all rays actually traced (primary + incoherent secondary + shadow, counted on the device) per
-second of device time, whole job over all ranks.
+second of device time, whole job over all ranks.  The same line carries `build` (LBVH build Mtri/s on a 10 M-triangle
+soup, the second half of BASELINE.json's metric).  `--config C3|C4|C5` measures the other BASELINE configs the same
+way (C5: realtime pipeline + denoise, reported as per-frame latency); they are extra lines, not the driver's.
 
 N > 1: the frame shards by SAMPLE INDEX: rank r renders samples r, r+N, ... with frameCount = the global
 sample index, every rank holds a replicated BVH, and one NCCL reduce sums the scaled accumulation buffers onto
@@ -41,22 +43,30 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--spp", type=int, default=None)
+    ap.add_argument("--build-tris", type=int, default=10_000_000, help="triangle soup size of the `build` measurement (0 = skip)")
     ap.add_argument("--subdiv", type=int, default=6, help="icosphere subdivisions of the bunny-scale mesh (6 -> 81 920 tris)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def workload_config(args, mesh):
+def load_workload(args):
+    wl = scenes.workload(args.config, args.subdiv)
+    wl.width, wl.height, wl.spp = args.width or wl.width, args.height or wl.height, args.spp or wl.spp
+    args.width, args.height, args.spp = wl.width, wl.height, wl.spp
+    return wl
+
+
+def workload_config(args, wl):
     return {
-        "workload": f"C2 bunny-scale synthetic mesh ({mesh.num_triangles} tris) {args.width}x{args.height} "
-                    f"{args.spp} spp progressive (Phong, 2 lights, 1 indirect-diffuse + 1 Phong-lobe bounce)",
-        "width": args.width, "height": args.height, "spp_per_step": args.spp, "triangles": mesh.num_triangles,
+        "workload": wl.description, "width": wl.width, "height": wl.height, "spp_per_step": wl.spp,
+        "triangles": wl.num_triangles, "instances": len(wl.transforms),
         "l2": "per-frame ray queues (~0.45 KB/pixel, ~0.9 GB per 1080p frame) exceed the 126 MB L2 and are rewritten "
-              "every frame; the ~12 MB BVH is meant to stay L2-resident",
+              "every frame; the traversal structure of C2/C3 stays L1/L2-resident by design",
     }
 
 
@@ -109,27 +119,46 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------- oracle scene (CPU arm)
+def oracle_scene(wl):
+    """The workload's scene in the CPU oracle (the reference's algorithm restated; test infrastructure)."""
+    import oracle
+    blases = [oracle.Blas.from_mesh(m) for m in wl.meshes]
+    tlas = oracle.Tlas([blases[k] for k in wl.instance_mesh], wl.transforms)
+    recs = oracle.Records([wl.meshes[k] for k in wl.instance_mesh], [wl.materials[k] for k in wl.instance_mesh])
+    return oracle, tlas, recs, blases
+
+
+def oracle_frame(orc, tlas, recs, env, wl, frame, acc, cores, counts):
+    if wl.realtime:
+        d, s = orc.render_realtime(tlas, recs, env, frame, wl.width, wl.height, threads=cores, counts=counts)
+        orc.denoise(d, s, denoiser_params(), threads=cores)
+    else:
+        orc.render_progressive(tlas, recs, env, frame, wl.width, wl.height, acc, threads=cores, counts=counts)
+
+
+def denoiser_params():
+    p = T.DenoiserParams()  # src/DenoiseCompositor.cpp:45-50
+    p.exposure, p.gamma, p.tonemap, p.gammaCorrect, p.maxKernelSize, p.debugVisualize = 1.0, 2.2, 1, 0, 12, 0
+    return p
+
+
 # ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's algorithm on the host CPU: the oracle port (there is no oracle/_ref — the reference is
-    Windows/D3D12-only), all host threads, each step = 1 spp of the same 1080p frame (a bounded sample)."""
+    Windows/D3D12-only), all host threads, each step = 1 spp of the same frame (a bounded sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle
-    mesh = scenes.bunny_scale(args.subdiv)
+    wl = load_workload(args)
     cores = os.cpu_count() or 1
-    setup = scenes.FrameSetup(camera=scenes.BUNNY_CAMERA)
     env = scenes.sky_cube(64)
-    blas = oracle.Blas.from_mesh(mesh)
-    tlas = oracle.Tlas([blas], [scenes.IDENTITY_3X4])
-    recs = oracle.Records([mesh], [scenes.make_material()])
-    jit = scenes.jitter_sequence(setup.seed, 1024, args.width, args.height)
-    acc = np.zeros((args.height, args.width, 4), np.float32)
+    orc, tlas, recs, _keep = oracle_scene(wl)
+    jit = scenes.jitter_sequence(wl.setup.seed, 1024, wl.width, wl.height)
+    acc = np.zeros((wl.height, wl.width, 4), np.float32)
 
     def step(i, counts):
-        oracle.render_progressive(tlas, recs, env, frame_for(setup, args, jit, i, 0), args.width, args.height, acc,
-                                  threads=cores, counts=counts)
+        oracle_frame(orc, tlas, recs, env, wl, frame_for(wl.setup, args, jit, i, 0), acc, cores, counts)
 
     for i in range(args.warmup):
         step(i, None)
@@ -139,16 +168,24 @@ def run_reference(args):
         step(args.warmup + i, counts)
     dt = time.perf_counter() - t0
     rays = counts.primary + counts.secondary + counts.shadow
-    value = rays / dt / 1e6
-    sample = f"{args.steps} x 1 spp of the {args.width}x{args.height} frame ({rays} rays), {cores} threads, row-parallel"
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh),
-           "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    mrays = rays / dt / 1e6
+    sample = f"{args.steps} x 1 spp of the {wl.width}x{wl.height} frame ({rays} rays), {cores} threads, row-parallel"
+    metric, value, hib = metric_of(wl, mrays, dt / args.steps * 1e3)
+    out = {"impl": "reference", "metric": metric, "value": value, "unit": metric, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": hib, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl),
+           "cpu_baseline": {"value": value, "unit": metric, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": metric, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
     return 0
+
+
+def metric_of(wl, mrays, ms_per_step):
+    """C2-C4: Mrays/s (higher is better).  C5: per-frame latency of realtime dispatch + denoise (lower is better)."""
+    if wl.realtime:
+        return "ms/frame (realtime 1 spp + denoise)", ms_per_step, False
+    return METRIC, mrays, True
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -179,15 +216,19 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     ctx = rt.Context(local_rank, stream=stream.cuda_stream)
 
-    W, H, SPP = args.width, args.height, args.spp
-    mesh = scenes.bunny_scale(args.subdiv)
-    setup = scenes.FrameSetup(camera=scenes.BUNNY_CAMERA)
+    wl = load_workload(args)
+    W, H, SPP = wl.width, wl.height, wl.spp
+    setup = wl.setup
     env = scenes.sky_cube(64)
-    mat = scenes.make_material()
     jit = scenes.jitter_sequence(setup.seed, 1024, W, H)
-
-    out_t = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
-    renderer = rt.Renderer(ctx, [mesh], [scenes.IDENTITY_3X4], [mat], env, rt.PROGRESSIVE, W, H, outputs=[TorchBuffer(out_t)])
+    n_out = 2 if wl.realtime else 1
+    outs = [torch.zeros(H * W * 4, dtype=torch.float32, device="cuda") for _ in range(n_out)]
+    out_t = outs[0]
+    renderer = rt.Renderer(ctx, wl.meshes, wl.transforms, wl.materials, env, rt.REALTIME if wl.realtime else rt.PROGRESSIVE, W, H,
+                           outputs=[TorchBuffer(t) for t in outs], instance_mesh=wl.instance_mesh)
+    dn = None
+    if wl.realtime:
+        dn = {"tmp": torch.empty_like(out_t), "out": torch.empty_like(out_t), "params": denoiser_params()}
 
     def barrier():
         if world > 1:
@@ -197,6 +238,9 @@ def run_ours(args):
         # rank r renders global samples r, r + world, ...; RNG is a pure function of (pixel, frameCount)
         for s in range(SPP):
             renderer.dispatch(frame_for(setup, args, jit, s * world + rank, s))
+            if dn:  # DenoiseCompositor::dispatch on the two AOVs of this frame
+                rt.check(rt.lib.rt_denoise(ctx.handle, outs[0].data_ptr(), outs[1].data_ptr(), dn["tmp"].data_ptr(), dn["out"].data_ptr(),
+                                           W, H, C.byref(dn["params"])))
         if world > 1:
             rt.check(rt.lib.rt_scale_buffer(ctx.handle, out_t.data_ptr(), out_t.numel(), 1.0 / world))
             dist.reduce(out_t, dst=0, op=dist.ReduceOp.SUM)
@@ -232,31 +276,36 @@ def run_ours(args):
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
     ms = float(t.item())
     rays = r.cpu().numpy()
-    value = rays.sum() / (ms * 1e-3) / 1e6
+    mrays = rays.sum() / (ms * 1e-3) / 1e6
+    metric, value, hib = metric_of(wl, mrays, ms / args.steps)
 
     # ---- e2e: the same step through the C ABI with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(args, ctx, rt, torch, dist, stream, mesh, setup, env, mat, jit, world, rank)
+        e2e = measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank)
 
-    # ---- roofline of the dominant kernel (rank 0 of a 1-GPU run: single-GPU kernel property)
+    # ---- roofline of the dominant kernel (rank 0: a single-GPU kernel property)
     roofline, stages = None, None
     if rank == 0:
         roofline, stages = measure_roofline(args, ctx, renderer, setup, jit, world, rank)
 
+    build = None
+    if rank == 0 and world == 1 and args.build_tris > 0:
+        build = measure_build(args, ctx, rt, torch, stream)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = measure_cpu_baseline(args, mesh, setup, env, jit)
+        cpu_baseline = measure_cpu_baseline(args, wl, env, jit)
 
     ctx.status()
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": workload_config(args, mesh),
+        out = {"metric": metric, "value": value, "unit": metric, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": hib, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl), "mrays_per_s": mrays,
                "rays_per_step": {"primary": rays[0] / args.steps, "secondary_incoherent": rays[1] / args.steps,
                                  "shadow": rays[2] / args.steps},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "stages": stages,
-               "cpu_baseline": cpu_baseline,
+               "build": build, "cpu_baseline": cpu_baseline,
                "parallelism": f"sample-index sharding x{world}, replicated BVH, 1 NCCL reduce/frame" if world > 1 else "single GPU"}
         print(json.dumps(out))
     if world > 1:
@@ -264,56 +313,78 @@ def run_ours(args):
     return 0
 
 
-def measure_e2e(args, ctx, rt, torch, dist, stream, mesh, setup, env, mat, jit, world, rank):
+def measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank):
     """Step through the reference-facing C ABI starting from HOST memory: pinned VB/IB/instance descs -> device,
-    BLAS + TLAS build, 16 dispatches, accumulated frame -> pinned host."""
-    W, H, SPP = args.width, args.height, args.spp
-    vb_h = torch.from_numpy(mesh.vertices.view(np.uint8).reshape(-1).copy()).pin_memory()
-    ib_h = torch.from_numpy(mesh.indices.view(np.uint8).reshape(-1).copy()).pin_memory()
-    vb_d, ib_d = torch.empty_like(vb_h, device="cuda"), torch.empty_like(ib_h, device="cuda")
-    img_h = torch.empty(H * W * 4, dtype=torch.float32).pin_memory()
-    out_t = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
-
-    desc = (T.GeometryDesc * 1)()
-    desc[0].vertex_buffer, desc[0].vertex_count, desc[0].vertex_stride_bytes = vb_d.data_ptr(), mesh.vertices.shape[0], 24
-    desc[0].index_buffer, desc[0].index_count, desc[0].index_format = ib_d.data_ptr(), mesh.indices.size, 32
-    desc[0].flags = T.GEOMETRY_FLAG_OPAQUE
-    binfo, tinfo = T.PrebuildInfo(), T.PrebuildInfo()
-    rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, 0, C.byref(binfo)))
-    rt.check(rt.lib.rt_tlas_prebuild(ctx.handle, 1, 0, C.byref(tinfo)))
-    bscr = torch.empty(binfo.scratch_bytes, dtype=torch.uint8, device="cuda")
-    bres = torch.empty(binfo.result_bytes, dtype=torch.uint8, device="cuda")
+    BLAS + TLAS builds, the step's dispatches (+ denoise for C5), accumulated frame -> pinned host."""
+    W, H, SPP = wl.width, wl.height, wl.spp
+    n_inst = len(wl.transforms)
+    host, dev, descs, binfo, bscr, bres = [], [], [], [], [], []
+    for m in wl.meshes:
+        vb_h = torch.from_numpy(m.vertices.view(np.uint8).reshape(-1).copy()).pin_memory()
+        ib_h = torch.from_numpy(m.indices.view(np.uint8).reshape(-1).copy()).pin_memory()
+        vb_d, ib_d = torch.empty_like(vb_h, device="cuda"), torch.empty_like(ib_h, device="cuda")
+        host.append((vb_h, ib_h))
+        dev.append((vb_d, ib_d))
+        d = (T.GeometryDesc * 1)()
+        d[0].vertex_buffer, d[0].vertex_count, d[0].vertex_stride_bytes = vb_d.data_ptr(), m.vertices.shape[0], 24
+        d[0].index_buffer, d[0].index_count, d[0].index_format = ib_d.data_ptr(), m.indices.size, 32
+        d[0].flags = T.GEOMETRY_FLAG_OPAQUE
+        info = T.PrebuildInfo()
+        rt.check(rt.lib.rt_blas_prebuild(ctx.handle, d, 1, 0, C.byref(info)))
+        descs.append(d)
+        bscr.append(torch.empty(info.scratch_bytes, dtype=torch.uint8, device="cuda"))
+        bres.append(torch.empty(info.result_bytes, dtype=torch.uint8, device="cuda"))
+    tinfo = T.PrebuildInfo()
+    rt.check(rt.lib.rt_tlas_prebuild(ctx.handle, n_inst, 0, C.byref(tinfo)))
     tscr = torch.empty(tinfo.scratch_bytes, dtype=torch.uint8, device="cuda")
     tres = torch.empty(tinfo.result_bytes, dtype=torch.uint8, device="cuda")
-    inst = (T.InstanceDesc * 1)()
-    inst[0].transform[:] = scenes.IDENTITY_3X4.tolist()
-    inst[0].instance_id_and_mask = 0xFF << 24
-    inst[0].hit_group_and_flags = 0
-    inst[0].blas = bres.data_ptr()
+    inst = (T.InstanceDesc * n_inst)()
+    for i, (k, xf) in enumerate(zip(wl.instance_mesh, wl.transforms)):
+        inst[i].transform[:] = np.asarray(xf, np.float32).reshape(12).tolist()
+        inst[i].instance_id_and_mask = (i & 0xFFFFFF) | (0xFF << 24)
+        inst[i].hit_group_and_flags = 2 * i  # InstanceContributionToHitGroupIndex = i * hitGroupCount (RtScene.cpp:29)
+        inst[i].blas = bres[k].data_ptr()
     inst_h = torch.from_numpy(np.frombuffer(bytes(inst), dtype=np.uint8).copy()).pin_memory()
     inst_d = torch.empty_like(inst_h, device="cuda")
     env_d = torch.from_numpy(np.ascontiguousarray(env, np.float32).reshape(-1)).cuda()
-    prog = rt.Program(ctx, rt.PROGRESSIVE)
-    for ray_type in range(2):
-        rt.check(rt.lib.rt_bindings_set_hit_record(prog.handle, ray_type, 0, vb_d.data_ptr(), ib_d.data_ptr(), C.byref(mat)))
+    prog = rt.Program(ctx, rt.REALTIME if wl.realtime else rt.PROGRESSIVE)
+    for i, k in enumerate(wl.instance_mesh):
+        for ray_type in range(2):
+            rt.check(rt.lib.rt_bindings_set_hit_record(prog.handle, ray_type, i, dev[k][0].data_ptr(), dev[k][1].data_ptr(),
+                                                       C.byref(wl.materials[k])))
     rt.check(rt.lib.rt_bindings_set_miss_record(prog.handle, 0, env_d.data_ptr(), env.shape[1]))
+    n_out = 2 if wl.realtime else 1
+    outs = [torch.zeros(H * W * 4, dtype=torch.float32, device="cuda") for _ in range(n_out)]
+    result_t = outs[0]
+    dn_tmp = dn_out = None
+    if wl.realtime:
+        dn_tmp, dn_out = torch.empty_like(outs[0]), torch.empty_like(outs[0])
+        result_t = dn_out
+    dparams = denoiser_params()
+    img_h = torch.empty(H * W * 4, dtype=torch.float32).pin_memory()
 
     def step(i):
-        vb_d.copy_(vb_h, non_blocking=True)
-        ib_d.copy_(ib_h, non_blocking=True)
+        for (vb_h, ib_h), (vb_d, ib_d) in zip(host, dev):
+            vb_d.copy_(vb_h, non_blocking=True)
+            ib_d.copy_(ib_h, non_blocking=True)
         inst_d.copy_(inst_h, non_blocking=True)
-        rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, 0, bscr.data_ptr(), bscr.numel(), bres.data_ptr(), bres.numel()))
-        rt.check(rt.lib.rt_tlas_build(ctx.handle, inst_d.data_ptr(), 1, 0, tscr.data_ptr(), tscr.numel(), tres.data_ptr(), tres.numel()))
+        for d, sc, rs in zip(descs, bscr, bres):
+            rt.check(rt.lib.rt_blas_build(ctx.handle, d, 1, 0, sc.data_ptr(), sc.numel(), rs.data_ptr(), rs.numel()))
+        rt.check(rt.lib.rt_tlas_build(ctx.handle, inst_d.data_ptr(), n_inst, 0, tscr.data_ptr(), tscr.numel(), tres.data_ptr(), tres.numel()))
         rt.check(rt.lib.rt_set_tlas(ctx.handle, tres.data_ptr()))
-        rt.check(rt.lib.rt_set_output(ctx.handle, 0, out_t.data_ptr(), 16 * W))
+        for slot, o in enumerate(outs):
+            rt.check(rt.lib.rt_set_output(ctx.handle, slot, o.data_ptr(), 16 * W))
         for s in range(SPP):
-            f = frame_for(setup, args, jit, s * world + rank, s)
+            f = frame_for(wl.setup, args, jit, s * world + rank, s)
             rt.check(rt.lib.rt_set_frame_constants(ctx.handle, C.byref(f)))
             rt.check(rt.lib.rt_dispatch_rays(ctx.handle, prog.handle, W, H, 3))
+            if wl.realtime:
+                rt.check(rt.lib.rt_denoise(ctx.handle, outs[0].data_ptr(), outs[1].data_ptr(), dn_tmp.data_ptr(), dn_out.data_ptr(), W, H,
+                                           C.byref(dparams)))
         if world > 1:
-            rt.check(rt.lib.rt_scale_buffer(ctx.handle, out_t.data_ptr(), out_t.numel(), 1.0 / world))
-            dist.reduce(out_t, dst=0, op=dist.ReduceOp.SUM)
-        img_h.copy_(out_t, non_blocking=True)
+            rt.check(rt.lib.rt_scale_buffer(ctx.handle, result_t.data_ptr(), result_t.numel(), 1.0 / world))
+            dist.reduce(result_t, dst=0, op=dist.ReduceOp.SUM)
+        img_h.copy_(result_t, non_blocking=True)
 
     for i in range(max(1, min(args.warmup, 2))):
         step(i)
@@ -337,10 +408,13 @@ def measure_e2e(args, ctx, rt, torch, dist, stream, mesh, setup, env, mat, jit, 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
     assert float(img_h.sum()) > 0.0
-    return {"value": float(r.item()) / (float(t.item()) * 1e-3) / 1e6, "unit": METRIC,
-            "h2d_bytes_per_step": int(vb_h.numel() + ib_h.numel() + inst_h.numel()), "d2h_bytes_per_step": int(img_h.numel() * 4),
-            "ms_per_step": float(t.item()) / args.steps,
-            "includes": "pinned H2D of VB/IB/instance descs, BLAS+TLAS build, 16 dispatches, D2H of the accumulated frame"}
+    ms = float(t.item())
+    metric, value, _ = metric_of(wl, float(r.item()) / (ms * 1e-3) / 1e6, ms / args.steps)
+    h2d = sum(int(a.numel() + b.numel()) for a, b in host) + int(inst_h.numel())
+    return {"value": value, "unit": metric, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(img_h.numel() * 4),
+            "ms_per_step": ms / args.steps,
+            "includes": "pinned H2D of VB/IB/instance descs, BLAS+TLAS build, the step's dispatches"
+                        + (" + denoise" if wl.realtime else "") + ", D2H of the frame"}
 
 
 def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
@@ -348,10 +422,10 @@ def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
     SPP = args.spp
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    # 1) instrumented pass (untimed): exact node visits / triangle tests of the very same rays
+    # 1) instrumented pass (untimed): node visits / triangle tests of the very same rays in the reference's visit order
     ctx.enable_trace_stats(True)
     ctx.trace_stats(reset=True)
     for s in range(SPP):
@@ -367,7 +441,8 @@ def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
             renderer.dispatch(frame_for(setup, args, jit, s * world + rank, s))
     tp, ts, tsh = ctx.stage_timing(reset=True)
     ctx.enable_stage_timing(False)
-    names = ["primary (k_primary)", "secondary_incoherent (k_trace_queue<closest>)", "shadow (k_trace_queue<any>, 2 launches/frame)"]
+    names = ["primary (k_primary)", "secondary_incoherent (k_trace_persistent<0>)", "shadow (k_trace_persistent<1>, 2 launches/frame)"]
+    keys = ["primary", "secondary", "shadow"]
     times = [tp, ts, tsh]
     launches_per_frame = [1, 1, 2]
     stages = {}
@@ -382,47 +457,88 @@ def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
                         "achieved_gbs": bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else None,
                         "mrays_per_s": s.rays / (SPP * lpf) / (ms_per_launch * 1e-3) / 1e6 if ms_per_launch > 0 else None,
                         "share_of_trace_time": t / max(sum(times), 1e-12)}
-    dom = max(stages, key=lambda k: stages[k]["share_of_trace_time"])
-    d = stages[dom]
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["achieved_gbs"] / peak if d["achieved_gbs"] else None, "traffic": load_ncu_traffic(),
+    dom_i = max(range(3), key=lambda i: times[i])
+    d = stages[names[dom_i]]
+    traffic = load_ncu_traffic(keys[dom_i]) if args.config == "C2" else None
+    roofline = {"bound": "hbm", "kernel": names[dom_i], "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["achieved_gbs"] / peak if d["achieved_gbs"] else None, "traffic": traffic,
                 "peak_source": peak_src,
-                "note": "achieved = algorithmic bytes/ray (48 + 64*n_int + 48*n_leaf, SURVEY 8d) x rays per launch / "
-                        "CUDA-event launch time; the BVH is L2-resident so achieved may legitimately exceed DRAM traffic"}
+                "note": "achieved = algorithmic bytes/ray (48 + 64*n_int + 48*n_leaf over the BVH2 visit counts of the same rays, "
+                        "SURVEY 8d) x rays per launch / CUDA-event launch time.  The traversal structure is L1/L2-resident, so "
+                        "DRAM traffic (`traffic`, ncu) is far below the algorithmic bytes and the kernel's real bound is the L1 "
+                        "data pipe (profiles/)"}
     return roofline, stages
 
 
-def load_ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if present."""
+def load_ncu_traffic(stage_key):
+    """dram bytes per launch of a trace stage from the committed ncu summary (profiles/traffic.json), if present."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p)).get("dram_bytes_per_launch", {}).get(stage_key)
         except Exception:
             return None
     return None
 
 
-def measure_cpu_baseline(args, mesh, setup, env, jit):
-    import oracle
+def measure_build(args, ctx, rt, torch, stream):
+    """LBVH build Mtri/s: device-resident VB/IB of a triangle soup -> traversable BVH (432 B/triangle)."""
+    n = args.build_tris
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    c = (torch.rand((n, 1, 3), device="cuda", generator=g) * 2 - 1) * 500.0   # centroids uniform in [-500, 500]^3
+    off = torch.rand((n, 3, 3), device="cuda", generator=g) - 0.5             # edge <= 1
+    vb = torch.zeros((3 * n, 6), dtype=torch.float32, device="cuda")          # {position, normal} stride 24
+    vb[:, :3] = (c + off).reshape(-1, 3)
+    ib = torch.arange(3 * n, dtype=torch.int32, device="cuda")
+    del c, off
+    desc = (T.GeometryDesc * 1)()
+    desc[0].vertex_buffer, desc[0].vertex_count, desc[0].vertex_stride_bytes = vb.data_ptr(), 3 * n, 24
+    desc[0].index_buffer, desc[0].index_count, desc[0].index_format = ib.data_ptr(), 3 * n, 32
+    desc[0].flags = T.GEOMETRY_FLAG_OPAQUE
+    info = T.PrebuildInfo()
+    rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, 0, C.byref(info)))
+    scr = torch.empty(info.scratch_bytes, dtype=torch.uint8, device="cuda")
+    res = torch.empty(info.result_bytes, dtype=torch.uint8, device="cuda")
+    times = []
+    l0 = ctx.launches()
+    for r in range(3 + max(3, args.steps)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, 0, scr.data_ptr(), scr.numel(), res.data_ptr(), res.numel()))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if r >= 3:
+            times.append(e0.elapsed_time(e1))
+    launches = (ctx.launches() - l0) // (3 + max(3, args.steps))
+    ms = float(np.median(times))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    gbs = n * 432.0 / (ms * 1e-3) / 1e9
+    return {"metric": "LBVH build Mtri/s", "value": n / ms / 1e3, "triangles": n, "ms": ms, "launches_per_build": int(launches),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes_per_triangle": 432},
+            "workload": f"{n}-triangle soup, uniform centroids in [-500,500]^3, edge <= 1, device-resident VB/IB -> traversable BVH "
+                        "(working set >> L2)", "result_mb": info.result_bytes / 2**20, "scratch_mb": info.scratch_bytes / 2**20}
+
+
+def measure_cpu_baseline(args, wl, env, jit):
     cores = os.cpu_count() or 1
-    blas = oracle.Blas.from_mesh(mesh)
-    tlas = oracle.Tlas([blas], [scenes.IDENTITY_3X4])
-    recs = oracle.Records([mesh], [scenes.make_material()])
-    acc = np.zeros((args.height, args.width, 4), np.float32)
+    orc, tlas, recs, _keep = oracle_scene(wl)
+    acc = np.zeros((wl.height, wl.width, 4), np.float32)
     counts = T.RayCounts()
     t0 = time.perf_counter()
     n = 0
     while True:
-        oracle.render_progressive(tlas, recs, env, frame_for(setup, args, jit, n, 0), args.width, args.height, acc,
-                                  threads=cores, counts=counts)
+        oracle_frame(orc, tlas, recs, env, wl, frame_for(wl.setup, args, jit, n, 0), acc, cores, counts)
         n += 1
         if time.perf_counter() - t0 > 10.0 or n >= 4:
             break
     dt = time.perf_counter() - t0
     rays = counts.primary + counts.secondary + counts.shadow
-    return {"value": rays / dt / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
-            "sample": f"{n} x 1 spp of the {args.width}x{args.height} frame ({rays} rays) in {dt:.1f} s, row-parallel over {cores} threads"}
+    metric, value, _ = metric_of(wl, rays / dt / 1e6, dt / n * 1e3)
+    return {"value": value, "unit": metric, "cores": cores, "kind": "port",
+            "sample": f"{n} x 1 spp of the {wl.width}x{wl.height} frame ({rays} rays) in {dt:.1f} s, row-parallel over {cores} threads"}
 
 
 def main():

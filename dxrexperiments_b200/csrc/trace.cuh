@@ -52,9 +52,22 @@ struct RayPre {  // GetRayData: TraverseFunction.hlsli:438-460
 __device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
 
 // The part of GetRayData the ray/box test needs: o, 1/d, o*(1/d).
+// ROBUST (production kernels): a direction component that is exactly 0 gets the finite "reciprocal" +-2^100 instead
+// of +-Inf.  With Inf the reference's slab arithmetic turns into NaN (Inf - Inf) and the slab then passes for EVERY
+// box, so an axis-aligned ray (cosine-hemisphere sample with u1 == 0: about one ray per 2^24) walks the whole tree —
+// tens of milliseconds on one lane while the GPU waits (tools/dbg_ray.py).  With 2^100 the same fused expression
+// evaluates the exact condition |c - o| <= h for that axis, which every box containing a hit point satisfies, so the
+// hits are unchanged and only boxes the ray cannot touch are skipped.  The instrumented kernels keep the literal
+// arithmetic, so that their visit counts stay those of the reference.
+template <bool ROBUST = false>
 __device__ __forceinline__ void ray_pre_box(RayPre &r, float ox, float oy, float oz, float dx, float dy, float dz) {
     r.ox = ox, r.oy = oy, r.oz = oz;
     r.ix = div_(1.0f, dx), r.iy = div_(1.0f, dy), r.iz = div_(1.0f, dz);
+    if (ROBUST) {
+        if (dx == 0.0f) r.ix = copysignf(0x1p100f, dx);
+        if (dy == 0.0f) r.iy = copysignf(0x1p100f, dy);
+        if (dz == 0.0f) r.iz = copysignf(0x1p100f, dz);
+    }
     r.oix = mul_(ox, r.ix), r.oiy = mul_(oy, r.iy), r.oiz = mul_(oz, r.iz);
 }
 
@@ -76,9 +89,10 @@ __device__ __forceinline__ void ray_pre_shear(RayPre &r, float dx, float dy, flo
     r.sz = pick(r.ix, r.iy, r.iz, kz);
 }
 
+template <bool ROBUST = false>
 __device__ __forceinline__ RayPre make_ray_pre(float ox, float oy, float oz, float dx, float dy, float dz) {
     RayPre r;
-    ray_pre_box(r, ox, oy, oz, dx, dy, dz);
+    ray_pre_box<ROBUST>(r, ox, oy, oz, dx, dy, dz);
     ray_pre_shear(r, dx, dy, dz);
     return r;
 }
@@ -194,9 +208,12 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
     const bool b1 = ray_box(t1, tCur, cur, c1.x, c1.y, c1.z, h1.x, h1.y, h1.z);
     const bool b2 = ray_box(t2, tCur, cur, c2.x, c2.y, c2.z, h2.x, h2.y, h2.z);
     const bool b3 = ray_box(t3, tCur, cur, c3.x, c3.y, c3.z, h3.x, h3.y, h3.z);
-    uint32_t k0 = hit_key(b0, t0, 0), k1 = hit_key(b1, t1, 1), k2 = hit_key(b2, t2, 2), k3 = hit_key(b3, t3, 3);
-    key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
     const uint32_t r0 = __float_as_uint(c0.w), r1 = __float_as_uint(c1.w), r2 = __float_as_uint(c2.w), r3 = __float_as_uint(c3.w);
+    // slots 2 and 3 may be empty; their half = -1 box fails the slab test of every ray except one whose slabs are all
+    // NaN (a zero direction passes every box, in the reference too), hence the explicit check
+    uint32_t k0 = hit_key(b0, t0, 0), k1 = hit_key(b1, t1, 1), k2 = hit_key(b2 && r2 != RT_WIDE4_EMPTY, t2, 2),
+             k3 = hit_key(b3 && r3 != RT_WIDE4_EMPTY, t3, 3);
+    key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
     if (k0 == 0xffffffffu) return RT_SENTINEL;
     if (k1 != 0xffffffffu) {  // push the other hits, farthest first
         if (sp + 3 > RT_STACK_SIZE) {
@@ -235,7 +252,7 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
     int sp = 0, blasBase = -1;
     float tCur = tmax;
     RayPre cur;
-    ray_pre_box(cur, ox, oy, oz, dx, dy, dz);
+    ray_pre_box<true>(cur, ox, oy, oz, dx, dy, dz);
     float tUnused;
     if (!ray_box(tUnused, tCur, cur, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2])) return false;
     const bool plain = [&] {
@@ -280,7 +297,7 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
                         const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
                         const f3 o2 = xform_point(m, mk3(ox, oy, oz));
                         const f3 d2 = xform_vector(m, mk3(dx, dy, dz));
-                        cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                        cur = make_ray_pre<true>(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
                     }
                     nodes = reinterpret_cast<const rt_wide4_node *>(__ldg(reinterpret_cast<const unsigned long long *>(ip + 5)));
                     tris = reinterpret_cast<const rt_packed_tri *>(uintptr_t(uint64_t(m4.z) | (uint64_t(m4.w) << 32)));
@@ -313,7 +330,7 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
                 }
                 if (bottom && sp == blasBase) {
                     bottom = false;
-                    if (!sameSpace) ray_pre_box(cur, ox, oy, oz, dx, dy, dz);
+                    if (!sameSpace) ray_pre_box<true>(cur, ox, oy, oz, dx, dy, dz);
                     nodes = A.wide4;
                     blasBase = -1;
                 }
@@ -344,7 +361,7 @@ __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float o
     int sp = 0;
     float tCur = tmax;
 
-    RayPre world = make_ray_pre(ox, oy, oz, dx, dy, dz);
+    RayPre world = make_ray_pre<!STATS>(ox, oy, oz, dx, dy, dz);
     RayPre cur = world;
     const rt_wide_node *nodes = A.wide;
     const rt_packed_tri *tris = nullptr;
@@ -386,7 +403,7 @@ __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float o
                     const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
                     f3 o2 = xform_point(m, mk3(ox, oy, oz));
                     f3 d2 = xform_vector(m, mk3(dx, dy, dz));
-                    cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                    cur = make_ray_pre<!STATS>(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
                     nodes = reinterpret_cast<const rt_wide_node *>(uintptr_t(uint64_t(m4.x) | (uint64_t(m4.y) << 32)));
                     tris = reinterpret_cast<const rt_packed_tri *>(uintptr_t(uint64_t(m4.z) | (uint64_t(m4.w) << 32)));
                     bottom = true;

@@ -45,6 +45,9 @@ struct TraceSink {  // where results go; only the members of the kernel's MODE a
 #ifndef RT_PERSIST_MIN_BLOCKS
 #define RT_PERSIST_MIN_BLOCKS 8
 #endif
+#ifndef RT_POP_CULL
+#define RT_POP_CULL 1
+#endif
 #ifndef RT_PERSIST_WIDE4
 #define RT_PERSIST_WIDE4 1  // 1: traverse the 4-wide nodes (rt_wide4_node); 0: the BVH2 wide nodes (A/B measurements)
 #endif
@@ -135,7 +138,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
                         if (MODE == 0 && b.w < 0.0f) tCur = 0.0f;
                         finish();
                     } else {
-                        ray_pre_box(cur, wox, woy, woz, wdx, wdy, wdz);  // the TLAS level tests boxes only
+                        ray_pre_box<true>(cur, wox, woy, woz, wdx, wdy, wdz);  // the TLAS level tests boxes only
                         plain = plain_float(wox) && plain_float(woy) && plain_float(woz) && plain_float(wdx) && plain_float(wdy) &&
                                 plain_float(wdz);
                         nodes = topNodes;
@@ -189,7 +192,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
                             const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
                             const f3 o2 = xform_point(m, mk3(wox, woy, woz));
                             const f3 d2 = xform_vector(m, mk3(wdx, wdy, wdz));
-                            cur = make_ray_pre(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                            cur = make_ray_pre<true>(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
                         }
 #if RT_PERSIST_WIDE4
                         nodes = reinterpret_cast<const rt_wide4_node *>(__ldg(reinterpret_cast<const unsigned long long *>(ip + 5)));
@@ -260,7 +263,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
                 }
                 if (bottom && sp == blasBase) {  // leaving the BLAS: back to the world-space ray (boxes only up there)
                     bottom = false;
-                    if (!sameSpace) ray_pre_box(cur, wox, woy, woz, wdx, wdy, wdz);
+                    if (!sameSpace) ray_pre_box<true>(cur, wox, woy, woz, wdx, wdy, wdz);
                     nodes = topNodes;
                     blasBase = -1;
                 }
@@ -268,7 +271,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
 #if RT_PERSIST_WIDE4
                 // a node whose entry distance (rounded down when it was pushed) is not in front of the committed hit
                 // cannot hold a closer one
-                if (MODE != 1 && (stackT[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
+                if (RT_POP_CULL && MODE != 1 && (stackT[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
 #endif
                 ref = stack[sp];
                 break;

@@ -369,16 +369,21 @@ class Renderer:
     """Convenience host for tests/bench: one scene (instances of meshes), one program, fp32 outputs on the device."""
 
     def __init__(self, ctx: Context, meshes, transforms, materials, env_texels, kind=PROGRESSIVE, width=256, height=256,
-                 outputs=None):
+                 outputs=None, instance_mesh=None):
         """outputs: optional list of caller-owned device buffers (anything with .ptr, e.g. a wrapped torch tensor)
-        of width*height RGBA fp32, one per output slot; allocated here when omitted."""
+        of width*height RGBA fp32, one per output slot; allocated here when omitted.
+        instance_mesh: optional list, one mesh index per transform (instancing: many instances of few BLASes);
+        by default instance i is mesh i."""
         self.ctx, self.width, self.height, self.kind = ctx, width, height, kind
         self.blases = [ctx.build_blas_from_mesh(m) for m in meshes]
-        self.tlas = ctx.build_tlas(self.blases, transforms)
+        if instance_mesh is None:
+            instance_mesh = list(range(len(meshes)))
+        assert len(instance_mesh) == len(transforms)
+        self.tlas = ctx.build_tlas([self.blases[k] for k in instance_mesh], transforms)
         self.program = Program(ctx, kind)
-        for i, (b, mat) in enumerate(zip(self.blases, materials)):
+        for i, k in enumerate(instance_mesh):
             for ray_type in range(2):
-                self.program.set_hit_record(ray_type, i, b.vb, b.ib, mat)
+                self.program.set_hit_record(ray_type, i, self.blases[k].vb, self.blases[k].ib, materials[k])
         self.program.set_env(env_texels)
         n_out = 2 if kind == REALTIME else 1
         self.out = list(outputs) if outputs is not None else [ctx.alloc(16 * width * height).zero() for _ in range(n_out)]

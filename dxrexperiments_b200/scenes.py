@@ -336,3 +336,55 @@ def make_frame(setup: FrameSetup, width: int, height: int, frame_count: int, acc
     f.pointLight.color[:] = setup.point_light_color
     f.options = options if options is not None else default_options()
     return f
+
+
+# ---------------------------------------------------------------------------------------------
+# The BASELINE.json workloads, shared by bench.py and the full-size tests.
+
+HALL_CAMERA = Camera(eye=(-29.0, 6.0, -29.0), at=(0.0, 4.0, 0.0))
+CLOUD_CAMERA = Camera(eye=(0.0, 40.0, 330.0), at=(0.0, 0.0, 0.0))
+
+
+@dataclass
+class Workload:
+    name: str
+    description: str
+    meshes: list
+    transforms: list
+    instance_mesh: list
+    materials: list
+    setup: FrameSetup
+    width: int
+    height: int
+    spp: int
+    realtime: bool = False
+
+    @property
+    def num_triangles(self) -> int:
+        return int(sum(self.meshes[k].num_triangles for k in self.instance_mesh))
+
+
+def workload(name: str, subdiv: int = 6) -> Workload:
+    """C2: bunny-scale mesh, 1080p, 16 spp progressive.  C3: sponza-scale column hall (~260 k tris), 4K, 64 spp.
+    C4: 512 instances (random rigid transforms, seed 10) of one 20 480-triangle BLAS = 10.5 M triangles, 1080p, 4 spp.
+    C5: the C2 scene through the realtime pipeline (1 spp + DenoiseCompositor), 1080p."""
+    if name in ("C2", "C5"):
+        m = bunny_scale(subdiv)
+        return Workload(name, f"{name} bunny-scale synthetic mesh ({m.num_triangles} tris) 1920x1080 " +
+                        ("16 spp progressive (Phong, 2 lights, 1 indirect-diffuse + 1 Phong-lobe bounce)" if name == "C2" else
+                         "realtime pipeline: 1 spp + shadow rays + Phong-lobe bounce + DenoiseCompositor"),
+                        [m], [IDENTITY_3X4], [0], [make_material()], FrameSetup(camera=BUNNY_CAMERA), 1920, 1080,
+                        16 if name == "C2" else 1, realtime=(name == "C5"))
+    if name == "C3":
+        m = column_hall(16, 1000)
+        setup = FrameSetup(camera=HALL_CAMERA, point_light_pos=(0.0, 8.0, 0.0, 1.0))
+        return Workload(name, f"C3 sponza-scale column hall ({m.num_triangles} tris) 3840x2160 64 spp progressive", [m],
+                        [IDENTITY_3X4], [0], [make_material()], setup, 3840, 2160, 64)
+    if name == "C4":
+        s = icosphere(5, 4.0)
+        xf = random_rigid_transforms(512, seed=10, extent=100.0)
+        setup = FrameSetup(camera=CLOUD_CAMERA, point_light_pos=(0.0, 0.0, 0.0, 1.0))
+        return Workload(name, f"C4 instanced scene: 512 instances x {s.num_triangles}-tri BLAS = {512 * s.num_triangles} tris "
+                        "(TLAS over BLAS), 1920x1080 4 spp progressive", [s], list(xf), [0] * 512, [make_material()], setup,
+                        1920, 1080, 4)
+    raise ValueError(name)

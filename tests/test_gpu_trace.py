@@ -173,3 +173,33 @@ def test_instanced_scene_hit_ids(ctx, orc):
     assert (ho["primitive_index"] != T.NO_HIT).mean() > 0.05
     np.testing.assert_array_equal(hg["t"][same], ho["t"][same])
     np.testing.assert_array_equal(hg["instance_id"][same], ho["instance_id"][same])
+
+
+def test_axis_aligned_rays_same_hits_without_walking_the_tree(ctx, orc):
+    """Direction components that are exactly 0 turn the reference's slab test into NaN, which passes EVERY box: the
+    reference (and the oracle, and the instrumented kernel) then walk the whole tree.  The production kernel evaluates
+    the exact slab condition for such an axis instead (trace.cuh: ray_pre_box<ROBUST>); the hits must not change."""
+    case = bunny_case(4)
+    otlas, gtlas = _build_both(case, ctx, orc)
+    rng = np.random.default_rng(5)
+    n = 3000
+    rays = np.zeros(n, T.RAY_DTYPE)
+    rays["origin"] = rng.uniform((-8, -0.5, -8), (8, 14, 8), size=(n, 3)).astype(np.float32)
+    axis = rng.integers(0, 3, size=n)
+    d = np.zeros((n, 3), np.float32)
+    d[np.arange(n), axis] = rng.choice([-1.0, 1.0], size=n)
+    two = rng.random(n) < 0.5   # half of the rays keep one more non-zero component (a single zero component)
+    d[two, (axis[two] + 1) % 3] = rng.uniform(-1, 1, size=int(two.sum())).astype(np.float32)
+    d[rng.random(n) < 0.2] *= np.float32(-0.0) + 1  # keep; negative zeros appear through the sign choice above
+    rays["direction"] = d
+    rays["tmin"], rays["tmax"] = 1e-4, 1e38
+    for flags in (0, T.RAY_FLAG_CULL_BACK_FACING_TRIANGLES):
+        st_o = T.TraceStats()
+        ho = otlas.trace(rays, flags, threads=8, stats=st_o)
+        hp = ctx.trace(gtlas, rays, flags)
+        frac, same = _agreement(hp, ho)
+        assert frac >= 0.9999, frac
+        np.testing.assert_array_equal(hp["t"][same], ho["t"][same])
+        np.testing.assert_array_equal(hp["bary"][same], ho["bary"][same])
+        assert (ho["primitive_index"] != T.NO_HIT).sum() > n // 10
+        assert st_o.internal_visits > 50 * n  # the literal arithmetic really does walk large parts of the tree
