@@ -1,0 +1,216 @@
+"""GPU parity at BASELINE.json's FULL sizes (C2-C5), through the C ABI.
+
+Where the oracle finishes in seconds the comparison is direct (1080p / 4K frames at 1-2 spp, 1 M-triangle builds bit
+for bit); beyond that the tests use size-independent properties: sortedness and permutation checks of the 10 M-triangle
+build, a tree walk that visits every leaf once, tiles == full frame, sample shards == single accumulation.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import rel_rmse
+from dxrexperiments_b200 import scenes, types as T
+
+pytestmark = pytest.mark.gpu
+
+REL_RMSE_TOL = 1e-3   # north-star criterion 3
+HIT_ID_MIN = 0.9999   # north-star criterion 2
+
+
+def _oracle_scene(orc, wl):
+    blases = [orc.Blas.from_mesh(m) for m in wl.meshes]
+    tlas = orc.Tlas([blases[k] for k in wl.instance_mesh], wl.transforms)
+    recs = orc.Records([wl.meshes[k] for k in wl.instance_mesh], [wl.materials[k] for k in wl.instance_mesh])
+    return tlas, recs, blases
+
+
+def _renderer(rt, ctx, wl, env, kind=None):
+    kind = kind if kind is not None else (rt.REALTIME if wl.realtime else rt.PROGRESSIVE)
+    return rt.Renderer(ctx, wl.meshes, wl.transforms, wl.materials, env, kind, wl.width, wl.height, instance_mesh=wl.instance_mesh)
+
+
+def _ids_agree(hg, ho):
+    same = ((hg["primitive_index"] == ho["primitive_index"]) & (hg["instance_index"] == ho["instance_index"])) | \
+           ((hg["primitive_index"] == T.NO_HIT) & (ho["primitive_index"] == T.NO_HIT))
+    return float(same.mean())
+
+
+def test_c2_1080p_frame_hit_ids_and_sample_shards(ctx, rt, orc):
+    wl = scenes.workload("C2")
+    W, H = wl.width, wl.height
+    env = scenes.sky_cube(64)
+    jit = scenes.jitter_sequence(wl.setup.seed, 8, W, H)
+    otlas, recs, _keep = _oracle_scene(orc, wl)
+    r = _renderer(rt, ctx, wl, env)
+    # criterion 1 at full size: the BLAS blob (Morton order, topology, boxes, triangles) is the oracle's, bit for bit
+    np.testing.assert_array_equal(r.blases[0].blob(), _keep[0].blob())
+    # criterion 2: all 2 073 600 primary rays of the frame
+    frame0 = scenes.make_frame(wl.setup, W, H, 0, 0, jitter=jit[0])
+    rays = orc.primary_rays(frame0, W, H, 30.0)
+    ho = otlas.trace(rays, T.RAY_FLAG_CULL_BACK_FACING_TRIANGLES, threads=16)
+    hg = ctx.trace(r.tlas, rays, T.RAY_FLAG_CULL_BACK_FACING_TRIANGLES)
+    assert _ids_agree(hg, ho) >= HIT_ID_MIN
+    hit = (hg["primitive_index"] == ho["primitive_index"]) & (ho["primitive_index"] != T.NO_HIT)
+    np.testing.assert_array_equal(hg["t"][hit], ho["t"][hit])
+    # criterion 3: 2 spp of the 1080p frame against the oracle
+    acc = np.zeros((H, W, 4), np.float32)
+    for s in range(2):
+        f = scenes.make_frame(wl.setup, W, H, s, s, jitter=jit[s])
+        orc.render_progressive(otlas, recs, env, f, W, H, acc, threads=16)
+        r.dispatch(f)
+    img = r.image(0)
+    assert rel_rmse(img[..., :3], acc[..., :3]) <= REL_RMSE_TOL
+    # sample-index sharding: two "ranks" render samples {0,2} and {1,3}; the scaled sum equals 4 spp on one
+    full = _renderer(rt, ctx, wl, env)
+    for s in range(4):
+        full.dispatch(scenes.make_frame(wl.setup, W, H, s, s, jitter=jit[s]))
+    shards = []
+    for rank in range(2):
+        rr = _renderer(rt, ctx, wl, env)
+        for local, s in enumerate(range(rank, 4, 2)):
+            rr.dispatch(scenes.make_frame(wl.setup, W, H, s, local, jitter=jit[s]))
+        shards.append(rr.image(0))
+    combined = 0.5 * shards[0] + 0.5 * shards[1]
+    assert rel_rmse(combined[..., :3], full.image(0)[..., :3]) <= 1e-6  # fp32 summation order only
+    ctx.status()
+
+
+def test_c3_4k_frame_and_tiles(ctx, rt, orc):
+    wl = scenes.workload("C3")
+    W, H = wl.width, wl.height
+    env = scenes.sky_cube(64)
+    jit = scenes.jitter_sequence(wl.setup.seed, 4, W, H)
+    otlas, recs, _keep = _oracle_scene(orc, wl)
+    r = _renderer(rt, ctx, wl, env)
+    f = scenes.make_frame(wl.setup, W, H, 0, 0, jitter=jit[0])
+    acc = np.zeros((H, W, 4), np.float32)
+    orc.render_progressive(otlas, recs, env, f, W, H, acc, threads=16)
+    r.dispatch(f)
+    full = r.image(0)
+    assert np.isfinite(full).all()
+    assert rel_rmse(full[..., :3], acc[..., :3]) <= REL_RMSE_TOL
+    # screen-tile sharding: four quadrant dispatches write exactly the full-frame pixels
+    t = _renderer(rt, ctx, wl, env)
+    for (x0, y0, x1, y1) in [(0, 0, W // 2, H // 2), (W // 2, 0, W, H // 2), (0, H // 2, W // 2, H), (W // 2, H // 2, W, H)]:
+        t.dispatch(f, region=(x0, y0, x1, y1))
+    np.testing.assert_array_equal(t.image(0), full)
+    ctx.status()
+
+
+def test_c4_instanced_scene_hits_and_frame(ctx, rt, orc):
+    wl = scenes.workload("C4")
+    W, H = wl.width, wl.height
+    env = scenes.sky_cube(64)
+    otlas, recs, _keep = _oracle_scene(orc, wl)
+    r = _renderer(rt, ctx, wl, env)
+    g, o = T.parse_tlas_blob(r.tlas.blob()), T.parse_tlas_blob(otlas.blob())  # 512-instance TLAS: bit-exact blob
+    np.testing.assert_array_equal(g["header"], o["header"])
+    np.testing.assert_array_equal(g["nodes"].view(np.uint8), o["nodes"].view(np.uint8))
+    for fld in ("w2o", "id_mask", "hg_flags", "o2w", "instance_index"):  # "blas" holds an address: differs by design
+        np.testing.assert_array_equal(g["meta"][fld], o["meta"][fld])
+    f = scenes.make_frame(wl.setup, W, H, 0, 0)
+    rays = orc.primary_rays(f, W, H, 30.0)[:: 7]
+    ho = otlas.trace(rays, T.RAY_FLAG_CULL_BACK_FACING_TRIANGLES, threads=16)
+    hg = ctx.trace(r.tlas, rays, T.RAY_FLAG_CULL_BACK_FACING_TRIANGLES)
+    assert _ids_agree(hg, ho) >= HIT_ID_MIN
+    assert (ho["primitive_index"] != T.NO_HIT).mean() > 0.1
+    # incoherent rays through the instance cloud, closest hit and any hit
+    rng = np.random.default_rng(3)
+    n = 200_000
+    inc = np.zeros(n, T.RAY_DTYPE)
+    inc["origin"] = rng.uniform(-120, 120, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    inc["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    inc["tmin"], inc["tmax"] = 1e-4, 1e38
+    ho = otlas.trace(inc, 0, threads=16)
+    hg = ctx.trace(r.tlas, inc, 0)
+    assert _ids_agree(hg, ho) >= HIT_ID_MIN
+    anyf = T.RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | T.RAY_FLAG_SKIP_CLOSEST_HIT_SHADER
+    vo = otlas.trace(inc, anyf, threads=16)["primitive_index"] == T.NO_HIT
+    vg = ctx.trace(r.tlas, inc, anyf)["primitive_index"] == T.NO_HIT
+    assert (vo == vg).mean() >= HIT_ID_MIN
+    # the configuration's 4 spp.  (At 1 spp this frame sits at 1.1e-3: ~70 of 2 M pixels flip a shadow term because
+    # CUDA's and glibc's sinf/cosf differ in the last ulp of a bounce direction — the same 70 pixels with the BVH2 and
+    # the 4-wide traversal, tools/dbg_c4.py — and one flipped light is a quarter of the pixel's value.)
+    acc = np.zeros((H, W, 4), np.float32)
+    jit = scenes.jitter_sequence(wl.setup.seed, wl.spp, W, H)
+    for s in range(wl.spp):
+        fs = scenes.make_frame(wl.setup, W, H, s, s, jitter=jit[s])
+        orc.render_progressive(otlas, recs, env, fs, W, H, acc, threads=16)
+        r.dispatch(fs)
+    assert rel_rmse(r.image(0)[..., :3], acc[..., :3]) <= REL_RMSE_TOL
+    ctx.status()
+
+
+def test_c4_build_1m_bit_exact_and_10m_properties(ctx, rt, orc):
+    # 1 M triangles: every stage and the whole blob against the oracle
+    soup = scenes.triangle_soup(1_000_000)
+    ob = orc.Blas.from_mesh(soup)
+    gb = ctx.build_blas_from_mesh(soup, keep_scratch=True)
+    ctx.sync()
+    np.testing.assert_array_equal(gb.stage("morton_codes"), ob.morton())
+    np.testing.assert_array_equal(gb.stage("sorted_indices"), ob.perm())
+    np.testing.assert_array_equal(gb.blob(), ob.blob())
+    del gb, ob
+    # 10 M triangles (the `build` workload of bench.py): size-independent properties
+    n = 10_000_000
+    soup = scenes.triangle_soup(n)
+    gb = ctx.build_blas_from_mesh(soup, keep_scratch=True)
+    ctx.sync()
+    ctx.status()
+    codes = gb.stage("sorted_codes")
+    perm = gb.stage("sorted_indices")
+    assert (np.diff(codes.astype(np.int64)) >= 0).all()                      # sorted
+    assert np.array_equal(np.bincount(perm, minlength=n), np.ones(n, np.int64))  # a permutation
+    assert np.array_equal(gb.stage("morton_codes")[perm], codes)              # of the right keys
+    ties = np.flatnonzero(np.diff(codes.astype(np.int64)) == 0)
+    assert (perm[ties] < perm[ties + 1]).all()                               # stable: ties keep load order
+    aabb = gb.stage("scene_aabb")
+    pos = soup.vertices["position"]
+    np.testing.assert_array_equal(aabb, np.concatenate([pos.min(0), pos.max(0)]))  # exact min/max
+    blob = gb.blob()
+    nodes = blob[16:16 + 32 * (2 * n - 1)].view(T.NODE_DTYPE)
+    leaf = (nodes["flags"] & 0x80000000) != 0
+    assert leaf.sum() == n and not leaf[: n - 1].any()
+    slots = nodes["flags"][n - 1:] & 0x00FFFFFF
+    assert np.array_equal(slots, np.arange(n, dtype=np.uint32))              # leaf i holds sorted slot i
+    # topology from the Karras pass (full 32-bit links; the reference blob keeps only 24 bits of the left index —
+    # FL/RayTracingHelper.hlsli:112-118 — which wraps beyond 8.38 M primitives; the traversal section
+    # that the kernels read carries full-width references)
+    hier = gb.stage("hierarchy")
+    left, right = hier["left"][: n - 1], hier["right"][: n - 1]
+    refs = np.bincount(np.concatenate([left, right]), minlength=2 * n - 1)
+    assert refs[0] == 0 and (refs[1:] == 1).all()                            # every node but the root has one parent
+    assert np.array_equal(hier["parent"][left], np.arange(n - 1)) and np.array_equal(hier["parent"][right], np.arange(n - 1))
+    blob_right = nodes["right"][: n - 1]
+    assert ((blob_right == left) | (blob_right == right)).all()              # the blob's right child is one of the two
+    assert ((nodes["flags"][: n - 1] & 0x00FFFFFF) == (np.where(blob_right == right, left, right) & 0x00FFFFFF)).all()
+    # parents enclose their children (boxes are re-rounded per level, so allow a little slack)
+    lo, hi = nodes["center"] - nodes["halfDim"], nodes["center"] + nodes["halfDim"]
+    for child in (left, right):
+        slack = 1e-3
+        assert (lo[: n - 1] <= lo[child] + slack).all() and (hi[: n - 1] >= hi[child] - slack).all()
+    root_lo, root_hi = lo[0], hi[0]
+    assert (root_lo <= pos.min(0) + 1e-3).all() and (root_hi >= pos.max(0) - 1e-3).all()
+
+
+def test_c5_realtime_1080p_and_denoise(ctx, rt, orc):
+    wl = scenes.workload("C5")
+    W, H = wl.width, wl.height
+    env = scenes.sky_cube(64)
+    otlas, recs, _keep = _oracle_scene(orc, wl)
+    r = _renderer(rt, ctx, wl, env)
+    f = scenes.make_frame(wl.setup, W, H, 0, 0, jitter=scenes.jitter_sequence(wl.setup.seed, 1, W, H)[0])
+    od, os_ = orc.render_realtime(otlas, recs, env, f, W, H, threads=16)
+    r.dispatch(f)
+    gd, gs = r.image(0), r.image(1)
+    assert rel_rmse(gd[..., :3], od[..., :3]) <= REL_RMSE_TOL
+    assert rel_rmse(gs[..., :3], os_[..., :3]) <= REL_RMSE_TOL
+    p = T.DenoiserParams()
+    p.exposure, p.gamma, p.tonemap, p.gammaCorrect, p.maxKernelSize, p.debugVisualize = 1.0, 2.2, 1, 0, 12, 0
+    oo = orc.denoise(od, os_, p, threads=16)
+    oo = oo[0] if isinstance(oo, tuple) else oo
+    go, _tmp = ctx.denoise(od, os_, p)  # the same inputs on both sides: the filter itself
+    assert np.abs(go - oo).max() <= 1e-5
+    ctx.status()
