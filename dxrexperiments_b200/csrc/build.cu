@@ -36,7 +36,10 @@ struct Aabb3 {
     float mn[3], mx[3];
 };
 
+// Warp shuffles, then one shared-memory exchange, then ONE set of six atomics per block (a per-warp version sent
+// 1.9 M atomics to the same six words for a 10 M-triangle build and made the load pass atomics-bound).
 __device__ __forceinline__ void block_reduce_aabb(float mn[3], float mx[3], uint32_t *enc /* 6 words */) {
+    __shared__ float s_red[32][6];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -44,11 +47,29 @@ __device__ __forceinline__ void block_reduce_aabb(float mn[3], float mx[3], uint
             mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
             mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
         }
-    if ((threadIdx.x & 31) == 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(&enc[k], enc_f32(mn[k]));
-            atomicMax(&enc[3 + k], enc_f32(mx[k]));
+        for (int k = 0; k < 3; ++k) s_red[warp][k] = mn[k], s_red[warp][3 + k] = mx[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = lane < nwarps ? s_red[lane][k] : (k < 3 ? FLT_MAX : -FLT_MAX);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t = __shfl_xor_sync(0xffffffffu, v[k], o);
+                v[k] = k < 3 ? fminf(v[k], t) : fmaxf(v[k], t);
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicMin(&enc[k], enc_f32(v[k]));
+                atomicMax(&enc[3 + k], enc_f32(v[3 + k]));
+            }
         }
     }
 }
@@ -72,38 +93,36 @@ struct LoadGeom {
     float xf[12];
 };
 
-__global__ void __launch_bounds__(kThreads) k_load_triangles(LoadGeom g, rt_primitive *prims, rt_primitive_meta *meta,
-                                                             uint32_t *aabb_enc) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+// The load-order scratch record is the 48-byte rt_packed_tri (9 floats + PrimitiveMetaData): three aligned 16-byte
+// stores here, three aligned 16-byte gathers in k_rearrange_tris (gathering the reference's unaligned 40 + 12 byte
+// records instead cost 2.6 GB of DRAM reads per 10 M triangles).
+__global__ void __launch_bounds__(kThreads) k_load_triangles(LoadGeom g, rt_packed_tri *recs, uint32_t *aabb_enc) {
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    if (t < g.num_tris) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < g.num_tris; t += gridDim.x * blockDim.x) {
         uint32_t idx[3];
         if (g.index_format == 32) {
             const uint32_t *ib = static_cast<const uint32_t *>(g.ib);
-            idx[0] = ib[3 * t], idx[1] = ib[3 * t + 1], idx[2] = ib[3 * t + 2];
+            idx[0] = ib[3 * size_t(t)], idx[1] = ib[3 * size_t(t) + 1], idx[2] = ib[3 * size_t(t) + 2];
         } else if (g.index_format == 16) {
             const uint16_t *ib = static_cast<const uint16_t *>(g.ib);
-            idx[0] = ib[3 * t], idx[1] = ib[3 * t + 1], idx[2] = ib[3 * t + 2];
+            idx[0] = ib[3 * size_t(t)], idx[1] = ib[3 * size_t(t) + 1], idx[2] = ib[3 * size_t(t) + 2];
         } else {
             idx[0] = 3 * t, idx[1] = 3 * t + 1, idx[2] = 3 * t + 2;
         }
-        uint32_t out = g.prim_offset + t;
-        uint32_t *dst = reinterpret_cast<uint32_t *>(prims + out);
-        dst[0] = 1;  // TRIANGLE_TYPE
+        float w[9];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float *p = reinterpret_cast<const float *>(g.vb + size_t(idx[k]) * g.stride);
             f3 v = mk3(p[0], p[1], p[2]);
             if (g.has_xf) v = xform_point(g.xf, v);
-            dst[1 + 3 * k] = __float_as_uint(v.x);
-            dst[2 + 3 * k] = __float_as_uint(v.y);
-            dst[3 + 3 * k] = __float_as_uint(v.z);
+            w[3 * k] = v.x, w[3 * k + 1] = v.y, w[3 * k + 2] = v.z;
             mn[0] = fminf(mn[0], v.x), mn[1] = fminf(mn[1], v.y), mn[2] = fminf(mn[2], v.z);
             mx[0] = fmaxf(mx[0], v.x), mx[1] = fmaxf(mx[1], v.y), mx[2] = fmaxf(mx[2], v.z);
         }
-        meta[out].geometryContributionToHitGroupIndex = g.geom_index;
-        meta[out].primitiveIndex = t;
-        meta[out].geometryFlags = g.flags;
+        float4 *dst = reinterpret_cast<float4 *>(recs + g.prim_offset + t);
+        dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+        dst[2] = make_float4(w[8], __uint_as_float(t), __uint_as_float(g.geom_index), __uint_as_float(g.flags));
     }
     block_reduce_aabb(mn, mx, aabb_enc);
 }
@@ -129,11 +148,13 @@ __device__ __forceinline__ uint32_t morton_from_centroid(f3 c, const float *aabb
     return expand10(qy) | (expand10(qx) << 1) | (expand10(qz) << 2);
 }
 
-__global__ void __launch_bounds__(kThreads) k_morton_prims(const rt_primitive *prims, uint32_t n, const float *aabb,
+__global__ void __launch_bounds__(kThreads) k_morton_prims(const rt_packed_tri *recs, uint32_t n, const float *aabb,
                                                            uint32_t *codes) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float *v = prims[i].v;
+    const float4 *q = reinterpret_cast<const float4 *>(recs + i);
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
     // (v0 + v1 + v2) / 3.0  (CalculateMortonCodesForPrimitives.hlsl:22-25)
     f3 c = mk3(((v[0] + v[3]) + v[6]) / 3.0f, ((v[1] + v[4]) + v[7]) / 3.0f, ((v[2] + v[5]) + v[8]) / 3.0f);
     codes[i] = morton_from_centroid(c, aabb);
@@ -165,36 +186,53 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *key
     hist[threadIdx.x * gridDim.x + blockIdx.x] = s[threadIdx.x];
 }
 
-// Exclusive scan of `len` words by one block: each thread scans a contiguous segment serially.
-__global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *data, uint32_t len) {
-    __shared__ uint32_t warp_sums[32];
-    const uint32_t seg = (len + 1023) / 1024;
-    const uint32_t b = threadIdx.x * seg, e = min(len, b + seg);
-    uint32_t sum = 0;
-    for (uint32_t i = b; i < e; ++i) sum += data[i];
-    uint32_t incl = sum;
+// Exclusive scan of the digit-major histogram hist[256][G] (flattened order) by one 1024-thread block: each warp
+// scans 8 rows with coalesced 32-wide steps, a 256-entry scan of the row totals follows, then the row bases are
+// added in a second coalesced sweep.  (A per-thread serial scan of contiguous segments took 134 us per pass.)
+__global__ void __launch_bounds__(1024) k_scan_hist(uint32_t *hist, uint32_t G) {
+    __shared__ uint32_t row_total[kRadix];
+    __shared__ uint32_t row_base[kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 32 warps x 8 rows
+    for (int r = 0; r < kRadix / 32; ++r) {
+        const int row = warp * (kRadix / 32) + r;
+        uint32_t *p = hist + size_t(row) * G;
+        uint32_t run = 0;
+        for (uint32_t c0 = 0; c0 < G; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const uint32_t v = c < G ? p[c] : 0u;
+            uint32_t incl = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += v;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t w = warp_sums[threadIdx.x], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (threadIdx.x >= o) wi += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (c < G) p[c] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        warp_sums[threadIdx.x] = wi - w;
+        if (lane == 0) row_total[row] = run;
     }
     __syncthreads();
-    uint32_t run = warp_sums[threadIdx.x >> 5] + (incl - sum);
-    for (uint32_t i = b; i < e; ++i) {
-        uint32_t v = data[i];
-        data[i] = run;
-        run += v;
+    if (warp == 0) {  // exclusive scan of the 256 row totals
+        uint32_t run = 0;
+        for (int c0 = 0; c0 < kRadix; c0 += 32) {
+            const uint32_t v = row_total[c0 + lane];
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            row_base[c0 + lane] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < kRadix / 32; ++r) {
+        const int row = warp * (kRadix / 32) + r;
+        const uint32_t b = row_base[row];
+        if (b == 0) continue;
+        uint32_t *p = hist + size_t(row) * G;
+        for (uint32_t c = lane; c < G; c += 32) p[c] += b;
     }
 }
 
@@ -319,25 +357,20 @@ __global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, u
 
 // ------------------------------------------------------------------------------------------ rearrange
 // FL/RearrangeTriangles.hlsl:18-36: out[dst] = in[perm[dst]]; also emits the packed 48-byte triangle.
-__global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_primitive *prims, const rt_primitive_meta *meta,
-                                                             const uint32_t *perm, uint32_t n, rt_primitive *out_prims,
-                                                             rt_primitive_meta *out_meta, rt_packed_tri *packed) {
+__global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_packed_tri *recs, const uint32_t *perm, uint32_t n,
+                                                             rt_primitive *out_prims, rt_primitive_meta *out_meta, rt_packed_tri *packed) {
     uint32_t dst = blockIdx.x * blockDim.x + threadIdx.x;
     if (dst >= n) return;
-    uint32_t src = perm[dst];
-    const uint32_t *s = reinterpret_cast<const uint32_t *>(prims + src);
-    uint32_t w[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) w[k] = s[k];
+    const uint32_t src = perm[dst];
+    const uint4 *q = reinterpret_cast<const uint4 *>(recs + src);
+    const uint4 q0 = __ldcs(q), q1 = __ldcs(q + 1), q2 = __ldcs(q + 2);  // each record is read exactly once
     uint32_t *d = reinterpret_cast<uint32_t *>(out_prims + dst);
-#pragma unroll
-    for (int k = 0; k < 10; ++k) d[k] = w[k];
-    rt_primitive_meta m = meta[src];
-    out_meta[dst] = m;
+    d[0] = 1;  // TRIANGLE_TYPE
+    d[1] = q0.x, d[2] = q0.y, d[3] = q0.z, d[4] = q0.w, d[5] = q1.x, d[6] = q1.y, d[7] = q1.z, d[8] = q1.w, d[9] = q2.x;
+    uint32_t *m = reinterpret_cast<uint32_t *>(out_meta + dst);
+    m[0] = q2.z, m[1] = q2.y, m[2] = q2.w;  // {geometryContributionToHitGroupIndex, primitiveIndex, geometryFlags}
     uint4 *p = reinterpret_cast<uint4 *>(packed + dst);
-    p[0] = make_uint4(w[1], w[2], w[3], w[4]);
-    p[1] = make_uint4(w[5], w[6], w[7], w[8]);
-    p[2] = make_uint4(w[9], m.primitiveIndex, m.geometryContributionToHitGroupIndex, m.geometryFlags);
+    p[0] = q0, p[1] = q1, p[2] = q2;
 }
 
 // ------------------------------------------------------------------------------------------ bottom-up fit
@@ -665,8 +698,8 @@ Layout make_layout(uint32_t n, bool top) {
     L.hier = take(12 * (2 * nn - 1));
     L.counters = take(4 * nn);
     L.hist = take(4ull * kRadix * 148 * 8);
-    L.elems = take((top ? 32 : 40) * nn);
-    L.meta = take((top ? 116 : 12) * nn);
+    L.elems = take((top ? 32 : 48) * nn);  // BLAS: rt_packed_tri records in load order; TLAS: instance boxes
+    L.meta = take((top ? 116 : 0) * nn);
     L.total = o;
     return L;
 }
@@ -707,7 +740,7 @@ int sort_pairs(rt_context *ctx, uint8_t *scratch, const Layout &L, uint32_t n) {
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = pass * kRadixBits;
         k_radix_hist<<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, n, shift, sp.tiles_per_block, hist);
-        k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(hist, kRadix * sp.blocks);
+        k_scan_hist<<<1, 1024, 0, ctx->stream>>>(hist, sp.blocks);
         if (pass == 0)
             k_radix_scatter<true><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, kout, vout);
         else
@@ -735,7 +768,7 @@ int rt_build_scratch_layout(uint32_t n, int top_level, rt_scratch_layout *out) {
     out->sorted_indices = L.valsC;
     out->hierarchy = L.hier;
     out->primitives = L.elems;
-    out->metadata = L.meta;
+    out->metadata = top_level ? L.meta : L.elems;
     out->total = L.total;
     return RT_OK;
 }
@@ -775,7 +808,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint8_t *scratch,
     if (top)
         k_morton_boxes<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_aabb_node *>(scratch + L.elems), n, aabb, codes);
     else
-        k_morton_prims<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_primitive *>(scratch + L.elems), n, aabb, codes);
+        k_morton_prims<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), n, aabb, codes);
     ctx->launches += 2;
     int rc = sort_pairs(ctx, scratch, L, n);
     if (rc) return rc;
@@ -799,8 +832,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint8_t *scratch,
                                                reinterpret_cast<rt_aabb_node *>(scratch + L.elems), perm, wide, ext);
     } else {
         rt_primitive *sp = reinterpret_cast<rt_primitive *>(result + R.off.offsetToVertices);
-        k_rearrange_tris<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_primitive *>(scratch + L.elems),
-                                                    reinterpret_cast<rt_primitive_meta *>(scratch + L.meta), perm, n, sp,
+        k_rearrange_tris<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), perm, n, sp,
                                                     reinterpret_cast<rt_primitive_meta *>(result + R.off.offsetToPrimitiveMetaData),
                                                     reinterpret_cast<rt_packed_tri *>(result + R.leaf));
         k_fit<false><<<grid, kThreads, 0, st>>>(n, hier, reinterpret_cast<uint32_t *>(scratch + L.counters), nodes, sp, nullptr,
@@ -874,8 +906,8 @@ int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geo
             RT_CUDA(cudaStreamSynchronize(st));
         }
         if (lg.num_tris) {
-            k_load_triangles<<<rt_div_up(lg.num_tris, kThreads), kThreads, 0, st>>>(
-                lg, reinterpret_cast<rt_primitive *>(scratch + L.elems), reinterpret_cast<rt_primitive_meta *>(scratch + L.meta), aabb_enc);
+            k_load_triangles<<<std::min(rt_div_up(lg.num_tris, kThreads), ctx->num_sms * 16), kThreads, 0, st>>>(
+                lg, reinterpret_cast<rt_packed_tri *>(scratch + L.elems), aabb_enc);
             ctx->launches++;
         }
         offset += lg.num_tris;

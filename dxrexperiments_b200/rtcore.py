@@ -326,9 +326,19 @@ class Accel:
         assert self.scratch is not None, "build with keep_scratch=True"
         L = self.scratch_layout()
         n = self.n
+        if name in ("primitives", "metadata"):
+            # load-order scratch records are 48-byte packed triangles {v[9], primitiveIndex, geometryIndex, flags}
+            rec = self.scratch.download(T.PACKED_TRI_DTYPE, n, offset=L.primitives)
+            if name == "primitives":
+                out = np.zeros(n, T.PRIM_DTYPE)
+                out["type"] = 1
+                out["v"] = rec["v"]
+                return out
+            out = np.zeros(n, T.META_DTYPE)
+            out["geom"], out["prim"], out["flags"] = rec["geom"], rec["prim"], rec["flags"]
+            return out
         spec = {"scene_aabb": (np.float32, 6), "morton_codes": (np.uint32, n), "sorted_codes": (np.uint32, n),
-                "sorted_indices": (np.uint32, n), "hierarchy": (T.HIER_DTYPE, max(2 * n - 1, 0)),
-                "primitives": (T.PRIM_DTYPE, n), "metadata": (T.META_DTYPE, n)}[name]
+                "sorted_indices": (np.uint32, n), "hierarchy": (T.HIER_DTYPE, max(2 * n - 1, 0))}[name]
         return self.scratch.download(spec[0], spec[1], offset=getattr(L, name))
 
 

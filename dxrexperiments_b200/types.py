@@ -93,6 +93,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("bary", "<f4", 2), ("primitive_index", "<u4
 NODE_DTYPE = np.dtype([("center", "<f4", 3), ("flags", "<u4"), ("halfDim", "<f4", 3), ("right", "<u4")])
 PRIM_DTYPE = np.dtype([("type", "<u4"), ("v", "<f4", 9)])
 META_DTYPE = np.dtype([("geom", "<u4"), ("prim", "<u4"), ("flags", "<u4")])
+PACKED_TRI_DTYPE = np.dtype([("v", "<f4", 9), ("prim", "<u4"), ("geom", "<u4"), ("flags", "<u4")])  # csrc/common.cuh rt_packed_tri
 HIER_DTYPE = np.dtype([("parent", "<u4"), ("left", "<u4"), ("right", "<u4")])
 BVH_METADATA_DTYPE = np.dtype([("w2o", "<f4", 12), ("id_mask", "<u4"), ("hg_flags", "<u4"), ("blas", "<u8"),
                                ("o2w", "<f4", 12), ("instance_index", "<u4")])

@@ -59,8 +59,9 @@ typedef struct rt_scratch_layout {
     uint64_t sorted_codes;   /* n x u32                                               (FL/BitonicSort.cpp)           */
     uint64_t sorted_indices; /* n x u32: sorted slot -> load-order primitive          (FL/BitonicSort.cpp)           */
     uint64_t hierarchy;      /* (2n-1) x rt_hierarchy_node                            (FL/BuildBVHSplits.hlsli)      */
-    uint64_t primitives;     /* n x rt_primitive, load order (BLAS only)              (FL/BottomLevelLoadTriangles.hlsli) */
-    uint64_t metadata;       /* n x rt_primitive_meta, load order (BLAS only)                                         */
+    uint64_t primitives;     /* BLAS: n x 48-byte load-order records {float v[9]; u32 primitiveIndex, geometryIndex,
+                                geometryFlags} = Primitive + PrimitiveMetaData of FL/BottomLevelLoadTriangles.hlsli      */
+    uint64_t metadata;       /* same offset as `primitives` (the metadata lives in the same records)                  */
     uint64_t total;
 } rt_scratch_layout;
 
