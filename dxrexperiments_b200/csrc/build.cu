@@ -405,11 +405,14 @@ __device__ __forceinline__ Box load_node_box(const rt_aabb_node *nodes, uint32_t
 // left"; on equal counts the reference is arrival-order dependent, pinned here as "keep Karras order".
 // TOP = false: leaf box from the sorted triangle (GetBoxDataFromTriangle, RayTracingHelper.hlsli:273-285).
 // TOP = true : leaf box = load-order instance box permuted by `perm`.
-template <bool TOP>
+// UPDATE = true (PERFORM_UPDATE, ComputeAABBs.hlsli:38-67): the topology is the one already in `nodes` — children
+// from each node's {flags, right} words, parents from the cached parent array — and only the boxes are re-fitted.
+// The subtree sizes are those of the original build, so the child order never changes (ties: pinned "no swap").
+template <bool TOP, bool UPDATE>
 __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy_node *hier, uint32_t *counters,
                                                   rt_aabb_node *nodes, const rt_primitive *sorted_prims,
                                                   const rt_aabb_node *inst_boxes, const uint32_t *perm,
-                                                  rt_wide_node *wide, rt_ext_header *ext) {
+                                                  rt_wide_node *wide, rt_ext_header *ext, const uint32_t *parents) {
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n) return;
     const uint32_t nInternal = n - 1;
@@ -438,18 +441,23 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
     }
     uint32_t count = 1;
     while (true) {
-        const uint32_t parent = hier[node].parent;
+        const uint32_t parent = UPDATE ? parents[node] : hier[node].parent;
         __threadfence();
         const uint32_t other = atomicAdd(&counters[parent], count);
         if (other == 0) return;  // first to arrive: the sibling will fit the parent
         __threadfence();
-        uint32_t l = hier[parent].left, r = hier[parent].right;
+        uint32_t l, r;
+        if (UPDATE) {
+            l = nodes[parent].flags & 0x00ffffffu, r = nodes[parent].right;
+        } else {
+            l = hier[parent].left, r = hier[parent].right;
+        }
         const bool isLeft = (l == node);
         const uint32_t lc = isLeft ? count : other, rc = isLeft ? other : count;
         const uint32_t sibling = isLeft ? r : l;
         Box sb = load_node_box(nodes, sibling);
         Box bl = isLeft ? box : sb, br = isLeft ? sb : box;
-        if (rc < lc) {  // smaller subtree on the left; ties keep the Karras order
+        if (!UPDATE && rc < lc) {  // smaller subtree on the left; ties keep the Karras order
             uint32_t t = l; l = r; r = t;
             Box tb = bl; bl = br; br = tb;
         }
@@ -531,13 +539,28 @@ __global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide
     }
 }
 
+// ALLOW_UPDATE: what FL/RearrangeTriangles.hlsl:25-28 (load order -> sorted slot) and FL/ComputeAABBs.hlsli:160-164
+// (parent of every node) leave behind for a later PERFORM_UPDATE.  The root's entry is 0.
+__global__ void __launch_bounds__(kThreads) k_save_update_cache(const uint32_t *perm, const rt_hierarchy_node *hier, uint32_t n,
+                                                                uint32_t *sort_cache, uint32_t *parents) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sort_cache[perm[i]] = i;
+    if (i < 2 * n - 1) parents[i] = i == 0 ? 0u : hier[i].parent;
+}
+// PERFORM_UPDATE: sorted slot -> load-order element, so that the rearrange kernels of the full build are reused.
+__global__ void __launch_bounds__(kThreads) k_invert_cache(const uint32_t *sort_cache, uint32_t n, uint32_t *perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[sort_cache[i]] = i;
+}
+
 __global__ void k_write_headers(uint8_t *result, rt_bvh_offsets off, rt_ext_header ext, uint64_t ext_offset) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *reinterpret_cast<rt_bvh_offsets *>(result) = off;
         rt_ext_header *e = reinterpret_cast<rt_ext_header *>(result + ext_offset);
         e->magic = ext.magic, e->count = ext.count, e->root_ref = ext.root_ref, e->top_level = ext.top_level;
         e->off_wide = ext.off_wide, e->off_leaf = ext.off_leaf, e->off_wide4 = ext.off_wide4;
-        e->_pad0 = e->_pad1 = 0;
+        e->off_sort_cache = ext.off_sort_cache, e->off_parents = ext.off_parents, e->build_flags = ext.build_flags;
+        e->_pad0 = e->_pad1 = e->_pad3 = 0;
         if (ext.count == 0) {
             // empty TLAS: node 0 is a zero box with zero flags (FL/TopLevelPrepareForComputeAABBs.hlsl:40-48)
             float4 *p = reinterpret_cast<float4 *>(result + 16);
@@ -706,9 +729,9 @@ Layout make_layout(uint32_t n, bool top) {
 
 struct ResultLayout {
     rt_bvh_offsets off;
-    uint64_t ext, wide, leaf, wide4, total;
+    uint64_t ext, wide, leaf, wide4, sort_cache, parents, total;
 };
-ResultLayout make_result_layout(uint32_t n, bool top) {
+ResultLayout make_result_layout(uint32_t n, bool top, bool allow_update = false) {
     ResultLayout R{};
     const uint32_t nodes = n == 0 ? 1 : 2 * n - 1;
     R.off.offsetToBoxes = 16;
@@ -725,6 +748,13 @@ ResultLayout make_result_layout(uint32_t n, bool top) {
     R.leaf = R.wide + 64ull * std::max(1u, n > 0 ? n - 1 : 0u);
     R.wide4 = align_up(R.leaf + (top ? 96ull : 48ull) * std::max(n, 1u), 128);
     R.total = R.wide4 + 128ull * std::max(1u, n > 0 ? n - 1 : 0u);
+    if (allow_update && n > 0) {
+        // The reference appends exactly these 4n + 4(2n-1) bytes to ResultDataMaxSizeInBytes (FL/GpuBVH2Builder.cpp:444-448,
+        // asserted by UT:1054-1087); here they follow the traversal section (they are private to the builder).
+        R.sort_cache = R.total;
+        R.parents = R.sort_cache + 4ull * n;
+        R.total = R.parents + 4ull * (2ull * n - 1);
+    }
     return R;
 }
 
@@ -779,64 +809,105 @@ static uint32_t count_prims(const rt_geometry_desc *geoms, uint32_t n_geoms) {
     return uint32_t(n);
 }
 
-int rt_blas_prebuild(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t /*flags*/, rt_prebuild_info *info) {
+static inline bool allows_update(uint32_t f) { return (f & RT_BUILD_FLAG_ALLOW_UPDATE) != 0; }
+static inline bool performs_update(uint32_t f) { return (f & RT_BUILD_FLAG_PERFORM_UPDATE) != 0; }
+
+int rt_blas_prebuild(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t flags, rt_prebuild_info *info) {
     RT_REQUIRE(ctx && info && (geoms || n_geoms == 0), "null argument");
     uint32_t n = count_prims(geoms, n_geoms);
     RT_REQUIRE(n < (1u << 24), "more than 2^24-1 primitives (node indices are 24 bit: RayTracingHelper.hlsli:112-118)");
-    info->result_bytes = make_result_layout(n, false).total;
-    info->scratch_bytes = make_layout(n, false).total;
-    info->update_scratch_bytes = 0;
+    info->result_bytes = make_result_layout(n, false, allows_update(flags)).total;
+    info->scratch_bytes = make_layout(n, false).total;  // the same with and without ALLOW_UPDATE (UT:1085)
+    info->update_scratch_bytes = allows_update(flags) ? info->scratch_bytes : 0;
     return RT_OK;
 }
 
-int rt_tlas_prebuild(rt_context *ctx, uint32_t n, uint32_t /*flags*/, rt_prebuild_info *info) {
+int rt_tlas_prebuild(rt_context *ctx, uint32_t n, uint32_t flags, rt_prebuild_info *info) {
     RT_REQUIRE(ctx && info, "null argument");
     RT_REQUIRE(n < (1u << 24), "more than 2^24-1 instances");
-    info->result_bytes = make_result_layout(n, true).total;
+    info->result_bytes = make_result_layout(n, true, allows_update(flags)).total;
     info->scratch_bytes = make_layout(n, true).total;
-    info->update_scratch_bytes = 0;
+    info->update_scratch_bytes = allows_update(flags) ? info->scratch_bytes : 0;
     return RT_OK;
 }
 
-static int build_common(rt_context *ctx, uint32_t n, bool top, uint8_t *scratch, uint8_t *result, const Layout &L,
+int rt_update_cache_layout(uint32_t n, int top_level, uint64_t *sort_cache_offset, uint64_t *parents_offset) {
+    RT_REQUIRE(sort_cache_offset && parents_offset, "null argument");
+    ResultLayout R = make_result_layout(n, top_level != 0, true);
+    *sort_cache_offset = R.sort_cache;
+    *parents_offset = R.parents;
+    return RT_OK;
+}
+
+// PERFORM_UPDATE is only defined on a buffer that an ALLOW_UPDATE build of the same element count produced
+// (the reference does not check and reads garbage; here it is E_INVALIDARG).  One 128-byte read back.
+static int check_updatable(rt_context *ctx, const uint8_t *result, const ResultLayout &R, uint32_t n, bool top) {
+    rt_ext_header e{};
+    RT_CUDA(cudaMemcpyAsync(&e, result + R.ext, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_REQUIRE(e.magic == RT_EXT_MAGIC && e.count == n && e.top_level == (top ? 1u : 0u) && allows_update(e.build_flags) &&
+                   e.off_sort_cache == R.sort_cache && e.off_parents == R.parents,
+               "PERFORM_UPDATE: the result buffer does not hold an ALLOW_UPDATE build of the same element count");
+    return RT_OK;
+}
+
+static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, uint8_t *scratch, uint8_t *result, const Layout &L,
                         const ResultLayout &R) {
     cudaStream_t st = ctx->stream;
-    float *aabb = reinterpret_cast<float *>(scratch + L.aabb);
-    uint32_t *codes = reinterpret_cast<uint32_t *>(scratch + L.codes);
+    const bool update = performs_update(flags);
     const int grid = rt_div_up(n, kThreads);
-    k_decode_aabb<<<1, 32, 0, st>>>(reinterpret_cast<uint32_t *>(scratch + L.aabb_enc), aabb);
-    if (top)
-        k_morton_boxes<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_aabb_node *>(scratch + L.elems), n, aabb, codes);
-    else
-        k_morton_prims<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), n, aabb, codes);
-    ctx->launches += 2;
-    int rc = sort_pairs(ctx, scratch, L, n);
-    if (rc) return rc;
-    const uint32_t *sorted_codes = reinterpret_cast<uint32_t *>(scratch + L.keysC);
-    const uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + L.valsC);
+    uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + L.valsC);
     rt_hierarchy_node *hier = reinterpret_cast<rt_hierarchy_node *>(scratch + L.hier);
-    RT_CUDA(cudaMemsetAsync(hier, 0, 12ull * (2ull * n - 1), st));
-    RT_CUDA(cudaMemsetAsync(scratch + L.counters, 0, 4ull * n, st));
-    if (n > 1) {
-        k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier);
+    uint32_t *sort_cache = reinterpret_cast<uint32_t *>(result + R.sort_cache);
+    uint32_t *parents = reinterpret_cast<uint32_t *>(result + R.parents);
+    if (update) {
+        k_invert_cache<<<grid, kThreads, 0, st>>>(sort_cache, n, perm);
         ctx->launches++;
+    } else {
+        float *aabb = reinterpret_cast<float *>(scratch + L.aabb);
+        uint32_t *codes = reinterpret_cast<uint32_t *>(scratch + L.codes);
+        k_decode_aabb<<<1, 32, 0, st>>>(reinterpret_cast<uint32_t *>(scratch + L.aabb_enc), aabb);
+        if (top)
+            k_morton_boxes<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_aabb_node *>(scratch + L.elems), n, aabb, codes);
+        else
+            k_morton_prims<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), n, aabb, codes);
+        ctx->launches += 2;
+        int rc = sort_pairs(ctx, scratch, L, n);
+        if (rc) return rc;
+        const uint32_t *sorted_codes = reinterpret_cast<uint32_t *>(scratch + L.keysC);
+        RT_CUDA(cudaMemsetAsync(hier, 0, 12ull * (2ull * n - 1), st));
+        if (n > 1) {
+            k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier);
+            ctx->launches++;
+        }
+        if (allows_update(flags)) {
+            k_save_update_cache<<<rt_div_up(2ull * n - 1, kThreads), kThreads, 0, st>>>(perm, hier, n, sort_cache, parents);
+            ctx->launches++;
+        }
     }
+    RT_CUDA(cudaMemsetAsync(scratch + L.counters, 0, 4ull * n, st));
     rt_aabb_node *nodes = reinterpret_cast<rt_aabb_node *>(result + 16);
     rt_wide_node *wide = reinterpret_cast<rt_wide_node *>(result + R.wide);
     rt_ext_header *ext = reinterpret_cast<rt_ext_header *>(result + R.ext);
+    uint32_t *counters = reinterpret_cast<uint32_t *>(scratch + L.counters);
     if (top) {
+        const rt_aabb_node *boxes = reinterpret_cast<rt_aabb_node *>(scratch + L.elems);
         k_rearrange_instances<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), perm, n,
                                                          reinterpret_cast<rt_bvh_metadata *>(result + R.off.offsetToVertices),
                                                          reinterpret_cast<rt_packed_instance *>(result + R.leaf));
-        k_fit<true><<<grid, kThreads, 0, st>>>(n, hier, reinterpret_cast<uint32_t *>(scratch + L.counters), nodes, nullptr,
-                                               reinterpret_cast<rt_aabb_node *>(scratch + L.elems), perm, wide, ext);
+        if (update)
+            k_fit<true, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, nullptr, boxes, perm, wide, ext, parents);
+        else
+            k_fit<true, false><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, nullptr, boxes, perm, wide, ext, parents);
     } else {
         rt_primitive *sp = reinterpret_cast<rt_primitive *>(result + R.off.offsetToVertices);
         k_rearrange_tris<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), perm, n, sp,
                                                     reinterpret_cast<rt_primitive_meta *>(result + R.off.offsetToPrimitiveMetaData),
                                                     reinterpret_cast<rt_packed_tri *>(result + R.leaf));
-        k_fit<false><<<grid, kThreads, 0, st>>>(n, hier, reinterpret_cast<uint32_t *>(scratch + L.counters), nodes, sp, nullptr,
-                                                perm, wide, ext);
+        if (update)
+            k_fit<false, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
+        else
+            k_fit<false, false><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
     }
     ctx->launches += 2;
     if (n > 1) {
@@ -847,7 +918,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint8_t *scratch,
     return RT_OK;
 }
 
-static int write_headers(rt_context *ctx, uint32_t n, bool top, uint8_t *result, const ResultLayout &R) {
+static int write_headers(rt_context *ctx, uint32_t n, bool top, uint32_t flags, uint8_t *result, const ResultLayout &R) {
     rt_ext_header e{};
     e.magic = RT_EXT_MAGIC;
     e.count = n;
@@ -856,21 +927,25 @@ static int write_headers(rt_context *ctx, uint32_t n, bool top, uint8_t *result,
     e.off_wide = R.wide;
     e.off_leaf = R.leaf;
     e.off_wide4 = R.wide4;
+    e.off_sort_cache = R.sort_cache;
+    e.off_parents = R.parents;
+    e.build_flags = flags & ~uint32_t(RT_BUILD_FLAG_PERFORM_UPDATE);
     k_write_headers<<<1, 32, 0, ctx->stream>>>(result, R.off, e, R.ext);
     ctx->launches++;
     RT_LAUNCH_CHECK();
     return RT_OK;
 }
 
-int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t /*build_flags*/, void *scratch_,
+int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags, void *scratch_,
                   uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
     RT_REQUIRE(ctx && scratch_ && result_, "null argument");  // E_INVALIDARG: FL/GpuBVH2Builder.cpp:145-148
     RT_REQUIRE((uintptr_t(result_) & 63) == 0 && (uintptr_t(scratch_) & 63) == 0, "buffers must be 64-byte aligned");
+    RT_REQUIRE(!performs_update(build_flags) || allows_update(build_flags), "PERFORM_UPDATE without ALLOW_UPDATE");
     uint32_t n = count_prims(geoms, n_geoms);
     RT_REQUIRE(n > 0, "bottom-level build with zero primitives");
     RT_REQUIRE(n < (1u << 24), "more than 2^24-1 primitives");
     Layout L = make_layout(n, false);
-    ResultLayout R = make_result_layout(n, false);
+    ResultLayout R = make_result_layout(n, false, allows_update(build_flags));
     if (scratch_bytes < L.total || result_bytes < R.total) {
         rt_set_error("buffer too small: scratch %llu < %llu or result %llu < %llu", (unsigned long long)scratch_bytes,
                      (unsigned long long)L.total, (unsigned long long)result_bytes, (unsigned long long)R.total);
@@ -879,7 +954,7 @@ int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geo
     RT_CUDA(cudaSetDevice(ctx->device));
     uint8_t *scratch = static_cast<uint8_t *>(scratch_), *result = static_cast<uint8_t *>(result_);
     cudaStream_t st = ctx->stream;
-    int rc = write_headers(ctx, n, false, result, R);
+    int rc = performs_update(build_flags) ? check_updatable(ctx, result, R, n, false) : write_headers(ctx, n, false, build_flags, result, R);
     if (rc) return rc;
     uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
     k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
@@ -913,17 +988,18 @@ int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geo
         offset += lg.num_tris;
     }
     RT_LAUNCH_CHECK();
-    return build_common(ctx, n, false, scratch, result, L, R);
+    return build_common(ctx, n, false, build_flags, scratch, result, L, R);
 }
 
-int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, uint32_t /*build_flags*/, void *scratch_,
+int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, uint32_t build_flags, void *scratch_,
                   uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
     RT_REQUIRE(ctx && result_, "null argument");
     RT_REQUIRE(n == 0 || (descs && scratch_), "null argument");
     RT_REQUIRE((uintptr_t(result_) & 63) == 0 && (uintptr_t(scratch_) & 63) == 0, "buffers must be 64-byte aligned");
     RT_REQUIRE(n < (1u << 24), "more than 2^24-1 instances");
+    RT_REQUIRE(!performs_update(build_flags) || allows_update(build_flags), "PERFORM_UPDATE without ALLOW_UPDATE");
     Layout L = make_layout(n, true);
-    ResultLayout R = make_result_layout(n, true);
+    ResultLayout R = make_result_layout(n, true, allows_update(build_flags));
     if ((n > 0 && scratch_bytes < L.total) || result_bytes < R.total) {
         rt_set_error("buffer too small: scratch %llu < %llu or result %llu < %llu", (unsigned long long)scratch_bytes,
                      (unsigned long long)L.total, (unsigned long long)result_bytes, (unsigned long long)R.total);
@@ -932,7 +1008,7 @@ int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, ui
     RT_CUDA(cudaSetDevice(ctx->device));
     uint8_t *scratch = static_cast<uint8_t *>(scratch_), *result = static_cast<uint8_t *>(result_);
     cudaStream_t st = ctx->stream;
-    int rc = write_headers(ctx, n, true, result, R);
+    int rc = performs_update(build_flags) ? check_updatable(ctx, result, R, n, true) : write_headers(ctx, n, true, build_flags, result, R);
     if (rc || n == 0) return rc;
     uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
     k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
@@ -940,7 +1016,7 @@ int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, ui
                                                                  reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), aabb_enc);
     ctx->launches += 2;
     RT_LAUNCH_CHECK();
-    return build_common(ctx, n, true, scratch, result, L, R);
+    return build_common(ctx, n, true, build_flags, scratch, result, L, R);
 }
 
 }  // extern "C"

@@ -108,7 +108,12 @@ struct rt_ext_header {  // 128 bytes, located at align64(reference blob size)
     float root_half[3];
     uint32_t _pad1;
     uint64_t off_wide4;     // ... to the 4-wide nodes (rt_wide4_node), one per BVH2 internal node, same indexing
-    uint64_t _pad2[7];
+    // ALLOW_UPDATE builds only (0 otherwise): the two arrays FL/GpuBVH2Builder.cpp:82-92 appends for PERFORM_UPDATE
+    uint64_t off_sort_cache;  // count x u32: load-order element -> sorted slot (RearrangeTriangles.hlsl:25-28)
+    uint64_t off_parents;     // (2*count-1) x u32: parent of every node (ComputeAABBs.hlsli:160-164)
+    uint32_t build_flags;     // RT_BUILD_FLAG_* of the build that produced this buffer
+    uint32_t _pad3;
+    uint64_t _pad2[4];
 };
 static_assert(sizeof(rt_ext_header) == 128, "ext header");
 
