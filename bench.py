@@ -459,7 +459,7 @@ def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
                         "share_of_trace_time": t / max(sum(times), 1e-12)}
     dom_i = max(range(3), key=lambda i: times[i])
     d = stages[names[dom_i]]
-    traffic = load_ncu_traffic(keys[dom_i]) if args.config == "C2" else None
+    traffic = load_ncu_traffic(names[dom_i]) if args.config == "C2" else None
     roofline = {"bound": "hbm", "kernel": names[dom_i], "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["achieved_gbs"] / peak if d["achieved_gbs"] else None, "traffic": traffic,
                 "peak_source": peak_src,

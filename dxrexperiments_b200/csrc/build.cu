@@ -560,7 +560,9 @@ __global__ void k_write_headers(uint8_t *result, rt_bvh_offsets off, rt_ext_head
         e->magic = ext.magic, e->count = ext.count, e->root_ref = ext.root_ref, e->top_level = ext.top_level;
         e->off_wide = ext.off_wide, e->off_leaf = ext.off_leaf, e->off_wide4 = ext.off_wide4;
         e->off_sort_cache = ext.off_sort_cache, e->off_parents = ext.off_parents, e->build_flags = ext.build_flags;
+        e->total_bytes = ext.total_bytes, e->compacted_bytes = ext.compacted_bytes;
         e->_pad0 = e->_pad1 = e->_pad3 = 0;
+        e->_pad2[0] = e->_pad2[1] = 0;
         if (ext.count == 0) {
             // empty TLAS: node 0 is a zero box with zero flags (FL/TopLevelPrepareForComputeAABBs.hlsl:40-48)
             float4 *p = reinterpret_cast<float4 *>(result + 16);
@@ -930,6 +932,8 @@ static int write_headers(rt_context *ctx, uint32_t n, bool top, uint32_t flags, 
     e.off_sort_cache = R.sort_cache;
     e.off_parents = R.parents;
     e.build_flags = flags & ~uint32_t(RT_BUILD_FLAG_PERFORM_UPDATE);
+    e.total_bytes = R.total;
+    e.compacted_bytes = R.sort_cache ? R.sort_cache : R.total;
     k_write_headers<<<1, 32, 0, ctx->stream>>>(result, R.off, e, R.ext);
     ctx->launches++;
     RT_LAUNCH_CHECK();

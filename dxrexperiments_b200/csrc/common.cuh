@@ -113,7 +113,9 @@ struct rt_ext_header {  // 128 bytes, located at align64(reference blob size)
     uint64_t off_parents;     // (2*count-1) x u32: parent of every node (ComputeAABBs.hlsli:160-164)
     uint32_t build_flags;     // RT_BUILD_FLAG_* of the build that produced this buffer
     uint32_t _pad3;
-    uint64_t _pad2[4];
+    uint64_t total_bytes;      // bytes of the result buffer in use (what rt_*_prebuild reported as result_bytes)
+    uint64_t compacted_bytes;  // bytes a COMPACT copy needs: total_bytes minus the two update caches
+    uint64_t _pad2[2];
 };
 static_assert(sizeof(rt_ext_header) == 128, "ext header");
 

@@ -62,6 +62,10 @@ def _load():
         "rt_tlas_prebuild": (i32, [vp, u32, u32, vp]),
         "rt_tlas_build": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
         "rt_build_scratch_layout": (i32, [u32, i32, vp]),
+        "rt_update_cache_layout": (i32, [u32, i32, C.POINTER(u64), C.POINTER(u64)]),
+        "rt_as_copy": (i32, [vp, vp, u64, vp, i32]),
+        "rt_as_emit_postbuild_info": (i32, [vp, vp, u32, vp]),
+        "rt_as_get_info": (i32, [vp, vp, vp]),
         "rt_blob_bytes": (u64, [u32, i32]),
         "rt_program_create": (i32, [vp, i32, u32, u32, pp]),
         "rt_program_destroy": (i32, [vp]),
@@ -179,16 +183,7 @@ class Context:
     def build_blas(self, geoms, build_flags: int = 0, keep_scratch: bool = False):
         """geoms: list of dicts {vertices: Buffer|ptr, vertex_count, stride, indices: Buffer|ptr|None, index_count,
         index_format, transform: Buffer|ptr|None, flags}."""
-        descs = (T.GeometryDesc * len(geoms))()
-        for d, g in zip(descs, geoms):
-            d.vertex_buffer = _ptr(g["vertices"])
-            d.vertex_count = g["vertex_count"]
-            d.vertex_stride_bytes = g.get("stride", 24)
-            d.index_buffer = _ptr(g.get("indices"))
-            d.index_count = g.get("index_count", 0)
-            d.index_format = g.get("index_format", 32 if g.get("indices") is not None else 0)
-            d.transform3x4 = _ptr(g.get("transform"))
-            d.flags = g.get("flags", T.GEOMETRY_FLAG_OPAQUE)
+        descs = _geometry_descs(geoms)
         info = T.PrebuildInfo()
         check(lib.rt_blas_prebuild(self.handle, descs, len(geoms), build_flags, C.byref(info)))
         scratch = self.alloc(info.scratch_bytes)
@@ -197,44 +192,70 @@ class Context:
                                 result.nbytes))
         n = sum((g.get("index_count", 0) if g.get("index_format", 32 if g.get("indices") is not None else 0) else
                  g["vertex_count"]) // 3 for g in geoms)
-        acc = Accel(self, result, n, top=False, scratch=scratch if keep_scratch else None, keep=list(geoms))
+        acc = Accel(self, result, n, top=False, scratch=scratch if keep_scratch else None, keep=list(geoms),
+                    build_flags=build_flags)
         if not keep_scratch:
             self.sync()
             scratch.free()
         return acc
 
-    def build_blas_from_mesh(self, mesh, flags=T.GEOMETRY_FLAG_OPAQUE, keep_scratch=False):
+    def build_blas_from_mesh(self, mesh, flags=T.GEOMETRY_FLAG_OPAQUE, keep_scratch=False, build_flags: int = 0):
         vb = self.upload(mesh.vertices)
         ib = self.upload(mesh.indices)
         acc = self.build_blas([dict(vertices=vb, vertex_count=mesh.vertices.shape[0], stride=24, indices=ib,
                                     index_count=mesh.indices.size, index_format=32, flags=flags)],
-                              keep_scratch=keep_scratch)
+                              build_flags=build_flags, keep_scratch=keep_scratch)
         acc.vb, acc.ib = vb, ib
         return acc
+
+    def update_blas(self, acc, geoms):
+        """PERFORM_UPDATE of an ALLOW_UPDATE bottom-level build with new geometry data (same counts and order)."""
+        descs = _geometry_descs(geoms)
+        flags = acc.build_flags | T.BUILD_FLAG_PERFORM_UPDATE
+        info = T.PrebuildInfo()
+        check(lib.rt_blas_prebuild(self.handle, descs, len(geoms), acc.build_flags, C.byref(info)))
+        scratch = self.alloc(info.update_scratch_bytes or info.scratch_bytes)
+        check(lib.rt_blas_build(self.handle, descs, len(geoms), flags, scratch.ptr, scratch.nbytes, acc.result.ptr,
+                                acc.result.nbytes))
+        self.sync()
+        scratch.free()
+        acc._keep = list(geoms)
+        return acc
+
+    def update_tlas(self, acc, transforms, ids=None, masks=None, hit_groups=None, flags=None):
+        """PERFORM_UPDATE of an ALLOW_UPDATE top-level build: same instances in the same order, new descs."""
+        blases = acc._keep[1]
+        dev_descs = self.upload(_instance_descs_bytes(blases, transforms, ids, masks, hit_groups, flags))
+        info = T.PrebuildInfo()
+        check(lib.rt_tlas_prebuild(self.handle, acc.n, acc.build_flags, C.byref(info)))
+        scratch = self.alloc(info.update_scratch_bytes or info.scratch_bytes)
+        check(lib.rt_tlas_build(self.handle, dev_descs.ptr, acc.n, acc.build_flags | T.BUILD_FLAG_PERFORM_UPDATE, scratch.ptr,
+                                scratch.nbytes, acc.result.ptr, acc.result.nbytes))
+        self.sync()
+        scratch.free()
+        acc._keep = [dev_descs, blases]
+        return acc
+
+    def compacted_sizes(self, accels):
+        """EmitRaytracingAccelerationStructurePostbuildInfo: compacted byte size of each structure."""
+        n = len(accels)
+        out = self.alloc(max(8 * n, 8))
+        arr = (C.c_void_p * max(n, 1))(*[a.result.ptr for a in accels])
+        check(lib.rt_as_emit_postbuild_info(self.handle, out.ptr, n, arr))
+        return out.download(np.uint64, n)
 
     def build_tlas(self, blases, transforms, ids=None, masks=None, hit_groups=None, flags=None, build_flags: int = 0,
                    keep_scratch: bool = False):
         n = len(blases)
-        descs = (T.InstanceDesc * max(n, 1))()
-        for i in range(n):
-            tr = np.asarray(transforms[i], np.float32).reshape(12)
-            descs[i].transform[:] = tr.tolist()
-            iid = i if ids is None else ids[i]
-            mask = 0xFF if masks is None else masks[i]
-            hg = 2 * i if hit_groups is None else hit_groups[i]
-            fl = 0 if flags is None else flags[i]
-            descs[i].instance_id_and_mask = (iid & 0xFFFFFF) | ((mask & 0xFF) << 24)
-            descs[i].hit_group_and_flags = (hg & 0xFFFFFF) | ((fl & 0xFF) << 24)
-            descs[i].blas = blases[i].result.ptr
-        host = np.frombuffer(bytes(descs), dtype=np.uint8)[: 64 * n] if n else np.zeros(0, np.uint8)
-        dev_descs = self.upload(host) if n else None
+        dev_descs = self.upload(_instance_descs_bytes(blases, transforms, ids, masks, hit_groups, flags)) if n else None
         info = T.PrebuildInfo()
         check(lib.rt_tlas_prebuild(self.handle, n, build_flags, C.byref(info)))
         scratch = self.alloc(info.scratch_bytes)
         result = self.alloc(info.result_bytes)
         check(lib.rt_tlas_build(self.handle, dev_descs.ptr if n else None, n, build_flags, scratch.ptr, scratch.nbytes,
                                 result.ptr, result.nbytes))
-        acc = Accel(self, result, n, top=True, scratch=scratch if keep_scratch else None, keep=[dev_descs, list(blases)])
+        acc = Accel(self, result, n, top=True, scratch=scratch if keep_scratch else None, keep=[dev_descs, list(blases)],
+                    build_flags=build_flags)
         if not keep_scratch:
             self.sync()
             scratch.free()
@@ -298,6 +319,36 @@ class Context:
         return p.value, s.value, sh.value
 
 
+def _geometry_descs(geoms):
+    descs = (T.GeometryDesc * len(geoms))()
+    for d, g in zip(descs, geoms):
+        d.vertex_buffer = _ptr(g["vertices"])
+        d.vertex_count = g["vertex_count"]
+        d.vertex_stride_bytes = g.get("stride", 24)
+        d.index_buffer = _ptr(g.get("indices"))
+        d.index_count = g.get("index_count", 0)
+        d.index_format = g.get("index_format", 32 if g.get("indices") is not None else 0)
+        d.transform3x4 = _ptr(g.get("transform"))
+        d.flags = g.get("flags", T.GEOMETRY_FLAG_OPAQUE)
+    return descs
+
+
+def _instance_descs_bytes(blases, transforms, ids=None, masks=None, hit_groups=None, flags=None) -> np.ndarray:
+    n = len(blases)
+    descs = (T.InstanceDesc * max(n, 1))()
+    for i in range(n):
+        tr = np.asarray(transforms[i], np.float32).reshape(12)
+        descs[i].transform[:] = tr.tolist()
+        iid = i if ids is None else ids[i]
+        mask = 0xFF if masks is None else masks[i]
+        hg = 2 * i if hit_groups is None else hit_groups[i]
+        fl = 0 if flags is None else flags[i]
+        descs[i].instance_id_and_mask = (iid & 0xFFFFFF) | ((mask & 0xFF) << 24)
+        descs[i].hit_group_and_flags = (hg & 0xFFFFFF) | ((fl & 0xFF) << 24)
+        descs[i].blas = blases[i].result.ptr
+    return np.frombuffer(bytes(descs), dtype=np.uint8)[: 64 * n].copy() if n else np.zeros(0, np.uint8)
+
+
 def _ptr(x):
     if x is None:
         return None
@@ -309,8 +360,34 @@ def _ptr(x):
 class Accel:
     """A built acceleration structure: the result buffer plus (optionally) the scratch of its build."""
 
-    def __init__(self, ctx, result: Buffer, n: int, top: bool, scratch=None, keep=None):
+    def __init__(self, ctx, result: Buffer, n: int, top: bool, scratch=None, keep=None, build_flags: int = 0):
         self.ctx, self.result, self.n, self.top, self.scratch, self._keep = ctx, result, n, top, scratch, keep
+        self.build_flags = build_flags
+
+    def info(self) -> T.AsInfo:
+        i = T.AsInfo()
+        check(lib.rt_as_get_info(self.ctx.handle, self.result.ptr, C.byref(i)))
+        return i
+
+    def clone(self, compact: bool = False, nbytes: int = None):
+        """CopyRaytracingAccelerationStructure into a new buffer (CLONE, or COMPACT which drops the update caches)."""
+        i = self.info()
+        need = int(i.compacted_bytes if compact else i.total_bytes)
+        dst = self.ctx.alloc(need if nbytes is None else nbytes)
+        check(lib.rt_as_copy(self.ctx.handle, dst.ptr, dst.nbytes, self.result.ptr, T.COPY_MODE_COMPACT if compact else T.COPY_MODE_CLONE))
+        flags = self.build_flags & ~T.BUILD_FLAG_ALLOW_UPDATE if compact else self.build_flags
+        out = Accel(self.ctx, dst, self.n, self.top, keep=self._keep, build_flags=flags)
+        for a in ("vb", "ib"):
+            if hasattr(self, a):
+                setattr(out, a, getattr(self, a))
+        return out
+
+    def update_caches(self):
+        """(sort cache, parents) of an ALLOW_UPDATE build: load-order element -> sorted slot; parent of every node."""
+        so, po = C.c_uint64(), C.c_uint64()
+        check(lib.rt_update_cache_layout(self.n, 1 if self.top else 0, C.byref(so), C.byref(po)))
+        return (self.result.download(np.uint32, self.n, offset=so.value),
+                self.result.download(np.uint32, max(2 * self.n - 1, 0), offset=po.value))
 
     def blob(self) -> np.ndarray:
         nbytes = int(lib.rt_blob_bytes(self.n, 1 if self.top else 0))

@@ -79,6 +79,11 @@ class PrebuildInfo(C.Structure):
     _fields_ = [("result_bytes", C.c_uint64), ("scratch_bytes", C.c_uint64), ("update_scratch_bytes", C.c_uint64)]
 
 
+class AsInfo(C.Structure):  # rt_as_info
+    _fields_ = [("count", C.c_uint32), ("top_level", C.c_uint32), ("build_flags", C.c_uint32), ("_pad", C.c_uint32),
+                ("blob_bytes", C.c_uint64), ("total_bytes", C.c_uint64), ("compacted_bytes", C.c_uint64)]
+
+
 assert C.sizeof(PerFrameConstants) == 188
 assert C.sizeof(MaterialParams) == 64
 assert C.sizeof(DenoiserParams) == 24
@@ -110,6 +115,14 @@ RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH = 0x04
 RAY_FLAG_SKIP_CLOSEST_HIT_SHADER = 0x08
 RAY_FLAG_CULL_BACK_FACING_TRIANGLES = 0x10
 RAY_FLAG_CULL_FRONT_FACING_TRIANGLES = 0x20
+BUILD_FLAG_NONE = 0
+BUILD_FLAG_ALLOW_UPDATE = 0x1
+BUILD_FLAG_ALLOW_COMPACTION = 0x2
+BUILD_FLAG_PREFER_FAST_TRACE = 0x4
+BUILD_FLAG_PREFER_FAST_BUILD = 0x8
+BUILD_FLAG_MINIMIZE_MEMORY = 0x10
+BUILD_FLAG_PERFORM_UPDATE = 0x20
+COPY_MODE_CLONE, COPY_MODE_COMPACT = 0, 1
 INSTANCE_FLAG_NONE = 0
 INSTANCE_FLAG_TRIANGLE_CULL_DISABLE = 0x1
 INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE = 0x2

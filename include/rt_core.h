@@ -106,6 +106,42 @@ int rt_tlas_prebuild(rt_context *ctx, uint32_t n_instances, uint32_t build_flags
 /* instance_descs: DEVICE array of n rt_instance_desc (ELEMENTS_LAYOUT_ARRAY). */
 int rt_tlas_build(rt_context *ctx, const rt_instance_desc *instance_descs, uint32_t n_instances, uint32_t build_flags,
                   void *scratch, uint64_t scratch_bytes, void *result, uint64_t result_bytes);
+/* Acceleration-structure updates (D3D12_RAYTRACING_ACCELERATION_STRUCTURE_BUILD_FLAG_ALLOW_UPDATE / PERFORM_UPDATE,
+ * FL/GpuBVH2Builder.cpp:152-204, FL/ComputeAABBs.hlsli:38-67,160-164, unit tests UT:1054-1475).
+ *   - build_flags | RT_BUILD_FLAG_ALLOW_UPDATE: rt_*_prebuild reports 4n + 4(2n-1) more result bytes and the same
+ *     scratch bytes (UT:1085-1086); the build also stores the sort cache (load-order element -> sorted slot) and the
+ *     parent of every node.
+ *   - build_flags | ALLOW_UPDATE | PERFORM_UPDATE on the SAME result buffer with the same element count and order:
+ *     the elements are re-loaded into their cached slots and the boxes re-fitted on the stored topology (no Morton
+ *     codes, no sort, no hierarchy pass).  RT_ERR_INVALID_ARG if the buffer does not hold such a build (the
+ *     reference does not check).  PERFORM_UPDATE without ALLOW_UPDATE is RT_ERR_INVALID_ARG.
+ * rt_update_cache_layout: byte offsets of the two caches inside an ALLOW_UPDATE result buffer (the reference puts
+ * them at BVHOffsets.totalSize; here they follow the traversal section). */
+int rt_update_cache_layout(uint32_t n_elements, int top_level, uint64_t *sort_cache_offset, uint64_t *parents_offset);
+
+/* ID3D12RaytracingFallbackCommandList::CopyRaytracingAccelerationStructure (FL/GpuBVH2Builder.cpp:330-347,
+ * FL/GpuBvh2Copy.hlsl:17-27).  mode: RT_COPY_MODE_CLONE or RT_COPY_MODE_COMPACT (D3D12's values 0 and 1); any other
+ * mode is RT_ERR_INVALID_ARG as in the reference.  CLONE copies everything, COMPACT drops the update caches (the copy
+ * cannot be updated).  A bottom-level buffer is position independent (offsets only): its bytes can also be moved with
+ * rt_download / rt_upload to another device or to disk.  A top-level buffer stores the addresses of its BLASes and
+ * stays valid only while they do.  Reads the 144 header bytes back (synchronises) to validate dst_bytes. */
+typedef enum rt_copy_mode { RT_COPY_MODE_CLONE = 0, RT_COPY_MODE_COMPACT = 1 } rt_copy_mode;
+int rt_as_copy(rt_context *ctx, void *dst, uint64_t dst_bytes, const void *src, int mode);
+/* EmitRaytracingAccelerationStructurePostbuildInfo, COMPACTED_SIZE (FL/GpuBVH2Builder.cpp:459-470,
+ * FL/GetBVHCompactedSize.hlsl:22-63): dst_sizes[i] (DEVICE, u64) = bytes rt_as_copy(COMPACT) of sources[i] needs;
+ * `sources` is a HOST array of n device addresses.  Stream ordered, no host synchronisation. */
+int rt_as_emit_postbuild_info(rt_context *ctx, uint64_t *dst_sizes, uint32_t n, const void *const *sources);
+typedef struct rt_as_info {
+    uint32_t count;      /* triangles or instances */
+    uint32_t top_level;  /* 1 for a TLAS */
+    uint32_t build_flags;
+    uint32_t _pad;
+    uint64_t blob_bytes;      /* BVHOffsets.totalSize: the reference-format blob at the head of the buffer */
+    uint64_t total_bytes;     /* bytes in use = result_bytes of the matching prebuild */
+    uint64_t compacted_bytes; /* bytes a COMPACT copy needs */
+} rt_as_info;
+/* Host-side query of a finished acceleration structure (synchronises). */
+int rt_as_get_info(rt_context *ctx, const void *as, rt_as_info *info);
 int rt_build_scratch_layout(uint32_t n_elements, int top_level, rt_scratch_layout *layout);
 /* Size in bytes of the reference-format blob at the head of a result buffer holding n elements. */
 uint64_t rt_blob_bytes(uint32_t n_elements, int top_level);

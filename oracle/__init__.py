@@ -54,6 +54,13 @@ def lib():
             f.restype = vp
         L.orc_blas_blob.argtypes = [vp, C.POINTER(u64)]
         L.orc_blas_blob.restype = vp
+        L.orc_blas_update.argtypes = [vp, vp, u32]
+        L.orc_blas_update.restype = i32
+        for name in ("orc_blas_sort_cache", "orc_blas_parents", "orc_tlas_sort_cache", "orc_tlas_parents"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = vp
+        L.orc_tlas_update.argtypes = [vp, vp, u32]
+        L.orc_tlas_update.restype = i32
         L.orc_tlas_build.argtypes = [vp, u32, u32]
         L.orc_tlas_build.restype = vp
         L.orc_tlas_free.argtypes = [vp]
@@ -141,6 +148,24 @@ class Blas:
     def __init__(self, geoms, build_flags: int = 0):
         """geoms: list of dicts {vertices (V,k) float32 array or structured, stride, indices (uint16/uint32 or None),
         transform (12,) or None, flags}."""
+        descs = self._descs(geoms)
+        self.handle = lib().orc_blas_build(descs, len(geoms), build_flags)
+        self.n = int(lib().orc_blas_num_prims(self.handle))
+
+    def update(self, geoms):
+        """PERFORM_UPDATE with new vertex data (same triangle count and order), in place."""
+        descs = self._descs(geoms)
+        rc = lib().orc_blas_update(self.handle, descs, len(geoms))
+        if rc != 0:
+            raise ValueError("update: primitive count differs from the original build")
+
+    def sort_cache(self):
+        return _view(lib().orc_blas_sort_cache(self.handle), self.n, np.uint32)
+
+    def parents(self):
+        return _view(lib().orc_blas_parents(self.handle), max(2 * self.n - 1, 0), np.uint32)
+
+    def _descs(self, geoms):
         self._keep = []
         descs = (T.GeometryDesc * len(geoms))()
         for d, g in zip(descs, geoms):
@@ -162,8 +187,7 @@ class Blas:
                 self._keep.append(tr)
                 d.transform3x4 = tr.ctypes.data
             d.flags = int(g.get("flags", T.GEOMETRY_FLAG_OPAQUE))
-        self.handle = lib().orc_blas_build(descs, len(geoms), build_flags)
-        self.n = int(lib().orc_blas_num_prims(self.handle))
+        return descs
 
     @classmethod
     def from_mesh(cls, mesh, flags=T.GEOMETRY_FLAG_OPAQUE):
@@ -227,6 +251,18 @@ class Tlas:
         if getattr(self, "handle", None):
             lib().orc_tlas_free(self.handle)
             self.handle = None
+
+    def update(self, transforms, ids=None, masks=None, hit_groups=None, flags=None):
+        """PERFORM_UPDATE: same instances in the same order, new transforms / ids / masks / flags."""
+        descs = make_instance_descs([b.handle for b in self.blases], transforms, ids, masks, hit_groups, flags)
+        if lib().orc_tlas_update(self.handle, descs, self.n) != 0:
+            raise ValueError("update: instance count differs from the original build")
+
+    def sort_cache(self):
+        return _view(lib().orc_tlas_sort_cache(self.handle), self.n, np.uint32)
+
+    def parents(self):
+        return _view(lib().orc_tlas_parents(self.handle), max(2 * self.n - 1, 0), np.uint32)
 
     def blob(self):
         nbytes = C.c_uint64(0)

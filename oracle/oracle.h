@@ -65,8 +65,17 @@ const uint32_t *orc_blas_perm(const orc_blas *b);          /* sorted slot -> inp
 const rt_hierarchy_node *orc_blas_hierarchy(const orc_blas *b);
 const uint8_t *orc_blas_blob(const orc_blas *b, uint64_t *bytes);
 
+/* PERFORM_UPDATE (FL/GpuBVH2Builder.cpp:152-204, FL/ComputeAABBs.hlsli:38-67): re-load the triangles (same count, same
+ * order) into the cached sorted slots and re-fit the boxes on the stored topology, in place.  -1 if the count differs. */
+int orc_blas_update(orc_blas *b, const rt_geometry_desc *geoms, uint32_t n_geoms);
+const uint32_t *orc_blas_sort_cache(const orc_blas *b); /* n: load order -> sorted slot  (FL/RearrangeTriangles.hlsl:25-28) */
+const uint32_t *orc_blas_parents(const orc_blas *b);    /* 2n-1: parent of every node    (FL/ComputeAABBs.hlsli:160-164) */
+
 /* TLAS over instances; inst[i].blas must hold an orc_blas* cast to uint64_t. */
 orc_tlas *orc_tlas_build(const rt_instance_desc *inst, uint32_t n, uint32_t build_flags);
+int orc_tlas_update(orc_tlas *t, const rt_instance_desc *inst, uint32_t n);
+const uint32_t *orc_tlas_sort_cache(const orc_tlas *t);
+const uint32_t *orc_tlas_parents(const orc_tlas *t);
 void orc_tlas_free(orc_tlas *t);
 const uint8_t *orc_tlas_blob(const orc_tlas *t, uint64_t *bytes);
 const uint32_t *orc_tlas_sorted_morton(const orc_tlas *t);

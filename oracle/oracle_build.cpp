@@ -182,6 +182,73 @@ static void fit_boxes(uint32_t n, const rt_hierarchy_node *hier, rt_aabb_node *n
     }
 }
 
+// PERFORM_UPDATE (FL/ComputeAABBs.hlsli:38-67): the topology is read back from the nodes already in the result buffer
+// (children = {flags & 0xffffff, right}), only the boxes are re-fitted.  The subtree sizes are those of the original
+// build and the children are already ordered, so the "smaller on the left" rule (:142-148) changes nothing except on
+// ties, which are arrival-order dependent in the reference and pinned to "no swap" here exactly as in the full build.
+template <class LeafBox>
+static void refit_boxes(uint32_t n, rt_aabb_node *nodes, LeafBox leaf_box) {
+    if (n == 0) return;
+    const uint32_t nInternal = n - 1;
+    std::vector<uint32_t> order, st;
+    order.reserve(2 * size_t(n) - 1);
+    st.push_back(0);
+    while (!st.empty()) {
+        uint32_t v = st.back();
+        st.pop_back();
+        order.push_back(v);
+        if (v < nInternal) {
+            st.push_back(nodes[v].flags & 0x00ffffffu);
+            st.push_back(nodes[v].right);
+        }
+    }
+    for (size_t i = order.size(); i-- > 0;) {
+        const uint32_t v = order[i];
+        Box b;
+        if (v >= nInternal) {
+            b = leaf_box(v - nInternal);
+        } else {
+            const uint32_t l = nodes[v].flags & 0x00ffffffu, r = nodes[v].right;
+            Box bl{mk(nodes[l].center[0], nodes[l].center[1], nodes[l].center[2]),
+                   mk(nodes[l].halfDim[0], nodes[l].halfDim[1], nodes[l].halfDim[2])};
+            Box br{mk(nodes[r].center[0], nodes[r].center[1], nodes[r].center[2]),
+                   mk(nodes[r].halfDim[0], nodes[r].halfDim[1], nodes[r].halfDim[2])};
+            Aabb a;
+            a.mn = vmin(bl.center - bl.half, br.center - br.half);
+            a.mx = vmax(bl.center + bl.half, br.center + br.half);
+            b = aabb_to_box(a);
+        }
+        nodes[v].center[0] = b.center.x, nodes[v].center[1] = b.center.y, nodes[v].center[2] = b.center.z;
+        nodes[v].halfDim[0] = b.half.x, nodes[v].halfDim[1] = b.half.y, nodes[v].halfDim[2] = b.half.z;
+    }
+}
+
+// What an ALLOW_UPDATE build leaves behind the blob (FL/GpuBVH2Builder.cpp:444-451): sort cache = load order ->
+// sorted slot (FL/RearrangeTriangles.hlsl:25-28), parents = parent of every node (FL/ComputeAABBs.hlsli:160-164;
+// the root's entry is never written there, pinned to 0).
+static void make_update_cache(uint32_t n, const uint32_t *perm, const rt_aabb_node *nodes, std::vector<uint32_t> &sort_cache,
+                              std::vector<uint32_t> &parents) {
+    sort_cache.assign(n, 0);
+    parents.assign(n ? 2 * size_t(n) - 1 : 0, 0);
+    for (uint32_t i = 0; i < n; ++i) sort_cache[perm[i]] = i;
+    for (uint32_t v = 0; v + 1 < n; ++v) {
+        parents[nodes[v].flags & 0x00ffffffu] = v;
+        parents[nodes[v].right] = v;
+    }
+}
+
+static Box triangle_leaf_box(const rt_primitive &p) {
+    // GetBoxDataFromTriangle: FL/RayTracingHelper.hlsli:273-285
+    const float *v = p.v;
+    f3 v0 = mk(v[0], v[1], v[2]), v1 = mk(v[3], v[4], v[5]), v2 = mk(v[6], v[7], v[8]);
+    Aabb a;
+    a.mn = vmin(vmin(v0, v1), v2);
+    a.mx = vmax(vmax(v0, v1), v2);
+    const float pad = 0.001f;  // AABB_Min_Padding
+    a.mn = vmin(a.mn, a.mx - mk(pad, pad, pad));
+    return aabb_to_box(a);
+}
+
 // FL/RayTracingHelper.hlsli:309-338.  Terms multiplied by the literal 0.0f in the reference
 // vanish and the "* 1.0f" factors are exact, so only the surviving products are written,
 // in the reference's order.
@@ -299,19 +366,34 @@ orc_blas *orc_blas_build(const rt_geometry_desc *geoms, uint32_t n_geoms, uint32
         sp[i] = b->prims[b->perm[i]];
         sm[i] = b->meta[b->perm[i]];
     }
-    fit_boxes(n, b->hier.data(), nodes, [&](uint32_t slot) {
-        // GetBoxDataFromTriangle: FL/RayTracingHelper.hlsli:273-285
-        const float *v = sp[slot].v;
-        f3 v0 = mk(v[0], v[1], v[2]), v1 = mk(v[3], v[4], v[5]), v2 = mk(v[6], v[7], v[8]);
-        Aabb a;
-        a.mn = vmin(vmin(v0, v1), v2);
-        a.mx = vmax(vmax(v0, v1), v2);
-        const float pad = 0.001f;  // AABB_Min_Padding
-        a.mn = vmin(a.mn, a.mx - mk(pad, pad, pad));
-        return aabb_to_box(a);
-    });
+    fit_boxes(n, b->hier.data(), nodes, [&](uint32_t slot) { return triangle_leaf_box(sp[slot]); });
+    make_update_cache(n, b->perm.data(), nodes, b->sort_cache, b->parents);
     return b;
 }
+
+// PERFORM_UPDATE on a bottom-level structure (FL/GpuBVH2Builder.cpp:152-204): the load pass writes every triangle and
+// its metadata straight to its cached sorted slot (FL/BottomLevelLoadTriangles.hlsli:107-112 via the sort cache), the
+// hierarchy passes are skipped, ComputeAABBs re-fits on the stored topology.
+int orc_blas_update(orc_blas *b, const rt_geometry_desc *geoms, uint32_t n_geoms) {
+    std::vector<rt_primitive> prims;
+    std::vector<rt_primitive_meta> meta;
+    load_triangles(geoms, n_geoms, prims, meta);
+    if (prims.size() != b->n) return -1;
+    b->prims = prims;
+    b->meta = meta;
+    const rt_bvh_offsets *off = reinterpret_cast<const rt_bvh_offsets *>(b->blob.data());
+    rt_aabb_node *nodes = reinterpret_cast<rt_aabb_node *>(b->blob.data() + 16);
+    rt_primitive *sp = reinterpret_cast<rt_primitive *>(b->blob.data() + off->offsetToVertices);
+    rt_primitive_meta *sm = reinterpret_cast<rt_primitive_meta *>(b->blob.data() + off->offsetToPrimitiveMetaData);
+    for (uint32_t i = 0; i < b->n; ++i) {
+        sp[b->sort_cache[i]] = prims[i];
+        sm[b->sort_cache[i]] = meta[i];
+    }
+    refit_boxes(b->n, nodes, [&](uint32_t slot) { return triangle_leaf_box(sp[slot]); });
+    return 0;
+}
+const uint32_t *orc_blas_sort_cache(const orc_blas *b) { return b->sort_cache.data(); }
+const uint32_t *orc_blas_parents(const orc_blas *b) { return b->parents.data(); }
 
 void orc_blas_free(orc_blas *b) { delete b; }
 uint32_t orc_blas_num_prims(const orc_blas *b) { return b->n; }
@@ -324,6 +406,20 @@ const rt_hierarchy_node *orc_blas_hierarchy(const orc_blas *b) { return b->hier.
 const uint8_t *orc_blas_blob(const orc_blas *b, uint64_t *bytes) {
     if (bytes) *bytes = b->blob.size();
     return b->blob.data();
+}
+
+// FL/TopLevelLoadAABBs.hlsli:58-100: world box of the BLAS root box + BVHMetadata of every instance, load order.
+static void load_instances(const rt_instance_desc *inst, uint32_t n, std::vector<orc::Box> &leaf, std::vector<rt_bvh_metadata> &md) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const orc_blas *b = reinterpret_cast<const orc_blas *>(uintptr_t(inst[i].blas));
+        const rt_aabb_node &root = b->nodes()[0];
+        Aabb box = box_to_aabb(Box{mk(root.center[0], root.center[1], root.center[2]), mk(root.halfDim[0], root.halfDim[1], root.halfDim[2])});
+        leaf[i] = aabb_to_box(transform_aabb(box, inst[i].transform));
+        md[i].instanceDesc = inst[i];
+        invert_affine(inst[i].transform, md[i].instanceDesc.transform);  // ObjectToWorld -> WorldToObject
+        std::memcpy(md[i].objectToWorld, inst[i].transform, 48);
+        md[i].instanceIndex = i;
+    }
 }
 
 // TLAS: FL/TopLevelLoadAABBs.hlsli:58-100 -> CalculateSceneAABBFromBVHs.hlsl -> CalculateMortonCodesForAABBs.hlsl
@@ -344,16 +440,7 @@ orc_tlas *orc_tlas_build(const rt_instance_desc *inst, uint32_t n, uint32_t /*bu
 
     std::vector<Box> leaf(n);
     std::vector<rt_bvh_metadata> md(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        const orc_blas *b = reinterpret_cast<const orc_blas *>(uintptr_t(inst[i].blas));
-        const rt_aabb_node &root = b->nodes()[0];
-        Aabb box = box_to_aabb(Box{mk(root.center[0], root.center[1], root.center[2]), mk(root.halfDim[0], root.halfDim[1], root.halfDim[2])});
-        leaf[i] = aabb_to_box(transform_aabb(box, inst[i].transform));
-        md[i].instanceDesc = inst[i];
-        invert_affine(inst[i].transform, md[i].instanceDesc.transform);  // ObjectToWorld -> WorldToObject
-        std::memcpy(md[i].objectToWorld, inst[i].transform, 48);
-        md[i].instanceIndex = i;
-    }
+    load_instances(inst, n, leaf, md);
     // scene AABB from leaf boxes (re-derived from center/halfDim): CalculateSceneAABBFromBVHs.hlsl:16-40
     f3 mn = mk(FLT_MAX, FLT_MAX, FLT_MAX), mx = mk(-FLT_MAX, -FLT_MAX, -FLT_MAX);
     for (uint32_t i = 0; i < n; ++i) {
@@ -374,8 +461,27 @@ orc_tlas *orc_tlas_build(const rt_instance_desc *inst, uint32_t n, uint32_t /*bu
     rt_bvh_metadata *smd = reinterpret_cast<rt_bvh_metadata *>(t->blob.data() + off.offsetToVertices);
     for (uint32_t i = 0; i < n; ++i) smd[i] = md[t->perm[i]];
     fit_boxes(n, t->hier.data(), nodes, [&](uint32_t slot) { return leaf[t->perm[slot]]; });
+    make_update_cache(n, t->perm.data(), nodes, t->sort_cache, t->parents);
     return t;
 }
+
+// PERFORM_UPDATE on a top-level structure: instances are re-loaded to their cached sorted slots (the instance count
+// and order of the descs must be those of the original build), then the boxes are re-fitted.
+int orc_tlas_update(orc_tlas *t, const rt_instance_desc *inst, uint32_t n) {
+    if (n != t->n) return -1;
+    if (n == 0) return 0;
+    std::vector<Box> leaf(n);
+    std::vector<rt_bvh_metadata> md(n);
+    load_instances(inst, n, leaf, md);
+    const rt_bvh_offsets *off = reinterpret_cast<const rt_bvh_offsets *>(t->blob.data());
+    rt_aabb_node *nodes = reinterpret_cast<rt_aabb_node *>(t->blob.data() + 16);
+    rt_bvh_metadata *smd = reinterpret_cast<rt_bvh_metadata *>(t->blob.data() + off->offsetToVertices);
+    for (uint32_t i = 0; i < n; ++i) smd[t->sort_cache[i]] = md[i];
+    refit_boxes(n, nodes, [&](uint32_t slot) { return leaf[t->perm[slot]]; });
+    return 0;
+}
+const uint32_t *orc_tlas_sort_cache(const orc_tlas *t) { return t->sort_cache.data(); }
+const uint32_t *orc_tlas_parents(const orc_tlas *t) { return t->parents.data(); }
 
 void orc_tlas_free(orc_tlas *t) { delete t; }
 const uint8_t *orc_tlas_blob(const orc_tlas *t, uint64_t *bytes) {

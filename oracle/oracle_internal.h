@@ -80,6 +80,7 @@ struct orc_blas {
     std::vector<uint32_t> morton, sorted_morton, perm;
     std::vector<rt_hierarchy_node> hier;
     std::vector<uint8_t> blob;
+    std::vector<uint32_t> sort_cache, parents;  // what ALLOW_UPDATE appends (FL/GpuBVH2Builder.cpp:444-451)
     // convenience views into blob
     const rt_aabb_node *nodes() const { return reinterpret_cast<const rt_aabb_node *>(blob.data() + 16); }
     const rt_primitive *sorted_prims() const {
@@ -95,6 +96,7 @@ struct orc_tlas {
     std::vector<uint32_t> morton, sorted_morton, perm;
     std::vector<rt_hierarchy_node> hier;
     std::vector<uint8_t> blob;
+    std::vector<uint32_t> sort_cache, parents;
     const rt_aabb_node *nodes() const { return reinterpret_cast<const rt_aabb_node *>(blob.data() + 16); }
     const rt_bvh_metadata *metadata() const {
         return reinterpret_cast<const rt_bvh_metadata *>(blob.data() + reinterpret_cast<const rt_bvh_offsets *>(blob.data())->offsetToVertices);

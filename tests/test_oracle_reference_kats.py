@@ -249,3 +249,108 @@ def test_traversal_equals_brute_force_closest_hit(orc):
     np.testing.assert_array_equal(hits["t"][hit], best_t[hit])
     same = hits["primitive_index"][hit] == best_p[hit]
     assert same.mean() > 0.995  # the rest are exact ties on shared edges (first found wins in both, in different orders)
+
+
+# ------------------------------------------------------------------------------------------------ ALLOW_UPDATE / PERFORM_UPDATE
+def scrambled_vertices(tris):
+    """RefitAABBsOnUpdate (UT:1277-1292): v' = ((v + vertexIndex) * (vertexIndex even ? -8 : 8)) * (triangle even ? -12 : 12)."""
+    flat = tris.reshape(-1).astype(np.float32).copy()
+    out = np.empty_like(flat)
+    for i in range(flat.size):
+        vi = i // 3
+        ti = vi // 3
+        out[i] = np.float32(np.float32(np.float32(flat[i] + np.float32(vi)) * np.float32(-8 if vi % 2 == 0 else 8)) *
+                            np.float32(-12 if ti % 2 == 0 else 12))
+    return out.reshape(tris.shape)
+
+
+def test_store_sort_result_for_update(orc):
+    """StoreSortResultForUpdate (UT:1089-1125): prims[sortCache[i]] is input triangle i."""
+    tris = reference_vertices(6)  # ReferenceVerticies1 has 6 triangles
+    blas = orc.Blas([dict(vertices=tris.reshape(-1, 3), stride=12, indices=None)], build_flags=T.BUILD_FLAG_ALLOW_UPDATE | T.BUILD_FLAG_PREFER_FAST_BUILD)
+    prims = T.parse_blas_blob(blas.blob())["prims"]
+    cache = blas.sort_cache()
+    assert sorted(cache.tolist()) == list(range(6))
+    for i in range(6):
+        np.testing.assert_array_equal(prims["v"][cache[i]].reshape(3, 3), tris[i])
+    np.testing.assert_array_equal(blas.perm()[cache], np.arange(6))
+
+
+@pytest.mark.parametrize("n", [2, 6, 300])
+def test_store_parent_indices_for_update(n, orc):
+    """StoreParentIndicesForUpdate (UT:1127-1165): both children of every internal node name it as their parent."""
+    tris = reference_vertices(n) if n <= 6 else ut_triangles(n, seed=11)
+    blas = orc.Blas([dict(vertices=tris.reshape(-1, 3), stride=12, indices=None)], build_flags=T.BUILD_FLAG_ALLOW_UPDATE)
+    nodes = T.parse_blas_blob(blas.blob())["nodes"]
+    parents = blas.parents()
+    assert parents.size == 2 * n - 1
+    for p in range(2 * n - 1):
+        if not (nodes["flags"][p] & T.LEAF_FLAG):
+            assert parents[int(nodes["flags"][p] & 0xFFFFFF)] == p
+            assert parents[int(nodes["right"][p])] == p
+
+
+def test_refit_aabbs_on_update(orc):
+    """RefitAABBsOnUpdate (UT:1167-1292): build, PERFORM_UPDATE with scrambled vertices, then the reference validator
+    must accept the result for the UPDATED triangles; the topology (child links) must be the one of the first build."""
+    tris = reference_vertices(6)
+    moved = scrambled_vertices(tris)
+    blas = orc.Blas([dict(vertices=tris.reshape(-1, 3), stride=12, indices=None)], build_flags=T.BUILD_FLAG_ALLOW_UPDATE | T.BUILD_FLAG_PREFER_FAST_BUILD)
+    before = T.parse_blas_blob(blas.blob())
+    blas.update([dict(vertices=moved.reshape(-1, 3), stride=12, indices=None)])
+    after = T.parse_blas_blob(blas.blob())
+    assert validate_bvh(blas.blob(), list(moved)) == 6
+    np.testing.assert_array_equal(before["nodes"]["flags"], after["nodes"]["flags"])
+    np.testing.assert_array_equal(before["nodes"]["right"], after["nodes"]["right"])
+    assert not np.array_equal(before["nodes"]["center"], after["nodes"]["center"])
+    with pytest.raises(ValueError):
+        blas.update([dict(vertices=moved.reshape(-1, 3)[:9], stride=12, indices=None)])
+
+
+def test_update_with_unchanged_input_is_the_identity_and_matches_a_rebuild_when_order_is_kept(orc):
+    """Two properties of the refit that need no reference run: (i) updating with the original vertices reproduces the
+    original blob bit for bit; (ii) a rigid translation keeps the Morton order, so update == fresh build of the moved mesh."""
+    from dxrexperiments_b200 import scenes
+    mesh = scenes.icosphere(3)
+    g = [dict(vertices=mesh.vertices, stride=24, indices=mesh.indices)]
+    blas = orc.Blas(g, build_flags=T.BUILD_FLAG_ALLOW_UPDATE)
+    blob0 = blas.blob()
+    blas.update(g)
+    np.testing.assert_array_equal(blas.blob(), blob0)
+    # power-of-two scale about the origin: every coordinate, centroid and box scales exactly, the Morton codes are equal
+    moved = mesh.vertices.copy()
+    moved["position"] *= np.float32(4.0)
+    g2 = [dict(vertices=moved, stride=24, indices=mesh.indices)]
+    fresh = orc.Blas(g2, build_flags=T.BUILD_FLAG_ALLOW_UPDATE)
+    np.testing.assert_array_equal(fresh.perm(), blas.perm())
+    blas.update(g2)
+    a, b = T.parse_blas_blob(blas.blob()), T.parse_blas_blob(fresh.blob())
+    np.testing.assert_array_equal(a["prims"].view(np.uint8), b["prims"].view(np.uint8))
+    np.testing.assert_array_equal(a["nodes"]["flags"], b["nodes"]["flags"])
+    # leaf boxes carry the absolute 0.001 padding, so only un-padded internal extents scale exactly; all must contain
+    np.testing.assert_allclose(a["nodes"]["center"], b["nodes"]["center"], rtol=0, atol=0)
+    np.testing.assert_allclose(a["nodes"]["halfDim"], b["nodes"]["halfDim"], rtol=0, atol=0)
+
+
+def test_tlas_update_refits_instances(orc):
+    """TopLevel ..._WithUpdate (UT:913-935): rebuild with PERFORM_UPDATE and new transforms; metadata follows the cached
+    order, every instance's world box is inside the root box, and traversal sees the moved instances."""
+    from dxrexperiments_b200 import scenes
+    from helpers import random_rays
+    mesh = scenes.icosphere(1)
+    ob = orc.Blas.from_mesh(mesh)
+    n = 40
+    xf0 = scenes.random_rigid_transforms(n, seed=3)
+    xf1 = scenes.random_rigid_transforms(n, seed=4)
+    t = orc.Tlas([ob] * n, xf0, build_flags=T.BUILD_FLAG_ALLOW_UPDATE)
+    perm = t.perm()
+    np.testing.assert_array_equal(perm[t.sort_cache()], np.arange(n))
+    t.update(xf1)
+    b = T.parse_tlas_blob(t.blob())
+    np.testing.assert_array_equal(b["meta"]["instance_index"], perm)            # order of the ORIGINAL build
+    np.testing.assert_array_equal(b["meta"]["o2w"], np.asarray(xf1, np.float32).reshape(n, 12)[perm])
+    fresh = orc.Tlas([ob] * n, xf1)
+    rays = random_rays(4000, 5, -60, 60)
+    h_upd, h_new = t.trace(rays), fresh.trace(rays)
+    for f in ("t", "primitive_index", "instance_index"):
+        np.testing.assert_array_equal(h_upd[f], h_new[f])                        # same scene => same closest hits
