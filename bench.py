@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5", "C1M"])
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spp", type=int, default=None)
@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--subdiv", type=int, default=6, help="icosphere subdivisions of the bunny-scale mesh (6 -> 81 920 tris)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-denoise", action="store_true", help="skip the DenoiseCompositor kernel measurement")
     return ap.parse_args()
 
 
@@ -293,6 +294,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.build_tris > 0:
         build = measure_build(args, ctx, rt, torch, stream)
 
+    denoise = None
+    if rank == 0 and world == 1 and not args.no_denoise:
+        denoise = measure_denoise(args, ctx, rt, torch, stream)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = measure_cpu_baseline(args, wl, env, jit)
@@ -305,7 +310,7 @@ def run_ours(args):
                "rays_per_step": {"primary": rays[0] / args.steps, "secondary_incoherent": rays[1] / args.steps,
                                  "shadow": rays[2] / args.steps},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "stages": stages,
-               "build": build, "cpu_baseline": cpu_baseline,
+               "build": build, "denoise": denoise, "cpu_baseline": cpu_baseline,
                "parallelism": f"sample-index sharding x{world}, replicated BVH, 1 NCCL reduce/frame" if world > 1 else "single GPU"}
         print(json.dumps(out))
     if world > 1:
@@ -520,6 +525,37 @@ def measure_build(args, ctx, rt, torch, stream):
                          "algorithmic_bytes_per_triangle": 432},
             "workload": f"{n}-triangle soup, uniform centroids in [-500,500]^3, edge <= 1, device-resident VB/IB -> traversable BVH "
                         "(working set >> L2)", "result_mb": info.result_bytes / 2**20, "scratch_mb": info.scratch_bytes / 2**20}
+
+
+def measure_denoise(args, ctx, rt, torch, stream):
+    """DenoiseCompositor::dispatch alone at 1920x1080, maxKernelSize 12 (SURVEY 8d: 96 B/pixel algorithmic = 2 passes x
+    (2 float4 reads + 1 float4 write)).  Between timed launches a 256 MB buffer is rewritten so the 132 MB of images do
+    not stay in the 126 MB L2."""
+    W, H = 1920, 1080
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    direct = torch.rand((H * W * 4,), device="cuda", generator=g)
+    spec = torch.rand((H * W * 4,), device="cuda", generator=g)
+    tmp, out = torch.empty_like(direct), torch.empty_like(direct)
+    flush = torch.empty(64 * 2**20, dtype=torch.float32, device="cuda")
+    prm = denoiser_params()
+    times = []
+    for r in range(3 + 10):
+        flush.fill_(float(r))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rt.check(rt.lib.rt_denoise(ctx.handle, direct.data_ptr(), spec.data_ptr(), tmp.data_ptr(), out.data_ptr(), W, H, C.byref(prm)))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if r >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    gbs = W * H * 96.0 / (ms * 1e-3) / 1e9
+    return {"metric": "DenoiseCompositor ms/frame (1920x1080, maxKernelSize 12, 2 launches)", "ms": ms, "mpixels_per_s": W * H / ms / 1e3,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes_per_pixel": 96}, "l2": "256 MB flush between launches"}
 
 
 def measure_cpu_baseline(args, wl, env, jit):

@@ -15,6 +15,14 @@
 //   K6 shadow1   : any-hit traversal of the depth-1 shadow rays
 //   K7 resolve   : recombines exactly the expression tree of shade()/shadeAOV() and accumulates
 //
+// Queue layout: every ray queue is PLANAR by ray kind — ray k of hit slot s lives at k * plane + s (plane = pixels of
+// the dispatch for the depth-0 queues, twice that for the depth-1 shadow queue), not at s * kinds + k.  A warp of a
+// trace kernel therefore holds rays of ONE kind from neighbouring pixels: all directional-light shadow rays are
+// parallel, all point-light rays converge on one point, Phong-lobe rays cluster around the mirror directions, and
+// only the cosine-hemisphere plane is truly incoherent.  Interleaved queues put two unrelated directions in adjacent
+// lanes and halved the SIMT efficiency of the shadow kernels (profiles/r1_ncu_trace_w4.md: 13.8-18.2 of 32 lanes).
+// Rays are "sorted by kind" by construction, with no sorting pass.
+//
 // Random numbers are a pure function of (pixel, frameCount) and are re-derived at each depth exactly as the
 // shaders re-initialise their seed, so no RNG state travels through the queues.
 #include <cstdio>
@@ -37,6 +45,7 @@ struct Launch {
 };
 
 struct WS {
+    uint32_t plane;     // P: plane stride of the depth-0 queues (the depth-1 shadow queue uses 2P)
     float4 *hitA;       // [P]  primary hit: t, u, v, primitive
     uint32_t *hitRec;   // [P]  hit-group record index
     uint32_t *counters; // [0] hit slots, [1] depth-1 shadow pairs
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
                     nol[i] = saturatef(dot3(N, dir));
                     pdf[i] = 1.0f / (2.0f * RT_M_PI);
                 }
-                store_ray(&ws.shadowQ0[4 * size_t(slot) + i], pos, RT_RAY_EPSILON, dir, 10.0f);
+                store_ray(&ws.shadowQ0[size_t(i) * ws.plane + slot], pos, RT_RAY_EPSILON, dir, 10.0f);
             }
             nShadow = 4;
             ws.S0[slot] = make_float4(nol[0], nol[1], nol[2], nol[3]);
@@ -246,10 +255,9 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
                 if (next_rand(seed) < 0.5f) usePoint = false, flags |= SLOT_DEBUG2_DIR;
                 else useDir = false, flags |= SLOT_DEBUG2_POINT;
             }
-            const size_t sq = size_t(L.shadowsPerHit) * slot;
-            store_ray(&ws.shadowQ0[sq + 0], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
-            store_ray(&ws.shadowQ0[sq + 1], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
-            for (uint32_t k = 2; k < L.shadowsPerHit; ++k) store_ray(&ws.shadowQ0[sq + k], pos, 0.0f, le.dirL, -1.0f);
+            store_ray(&ws.shadowQ0[slot], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
+            store_ray(&ws.shadowQ0[size_t(ws.plane) + slot], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
+            for (uint32_t k = 2; k < L.shadowsPerHit; ++k) store_ray(&ws.shadowQ0[size_t(k) * ws.plane + slot], pos, 0.0f, le.dirL, -1.0f);
             nShadow = (useDir ? 1 : 0) + (usePoint ? 1 : 0);
             // indirect diffuse: S/ProgressiveRaytracing.hlsl:57-78,107-110
             float uniformNoL = 0.0f;
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
                 }
                 flags |= SLOT_HAS_DIFFUSE;
             }
-            store_ray(&ws.secQ[2 * size_t(slot) + 0], pos, RT_RAY_EPSILON, dDir, hasDiffuse ? RT_RAY_MAX_T : -1.0f);
+            store_ray(&ws.secQ[slot], pos, RT_RAY_EPSILON, dDir, hasDiffuse ? RT_RAY_MAX_T : -1.0f);
             // indirect specular: S/ProgressiveRaytracing.hlsl:114-131
             f3 fres = mk3(0, 0, 0), sDir = mk3(0, 0, 1);
             float pdf = 1.0f, brdf = 0.0f;
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
                 fres = fresnel_schlick(d, N, mk3(R.mat.specular[0], R.mat.specular[1], R.mat.specular[2]));
                 flags |= SLOT_HAS_SPEC;
             }
-            store_ray(&ws.secQ[2 * size_t(slot) + 1], pos, RT_RAY_EPSILON, sDir, hasSpec ? RT_RAY_MAX_T : -1.0f);
+            store_ray(&ws.secQ[size_t(ws.plane) + slot], pos, RT_RAY_EPSILON, sDir, hasSpec ? RT_RAY_MAX_T : -1.0f);
             nSecondary = (hasDiffuse ? 1 : 0) + (hasSpec ? 1 : 0);
             ws.S0[slot] = make_float4(le.dirPre.x, le.dirPre.y, le.dirPre.z, le.falloff);
             ws.S1[slot] = make_float4(le.pointPre.x, le.pointPre.y, le.pointPre.z, pdf);
@@ -293,13 +301,14 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
 // ------------------------------------------------------------------------------------------------ K3 / K4 / K6
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult,
-                                                        float4 *hitA, uint32_t *hitRec, uint8_t *vis, uint32_t *status,
+                                                        uint32_t plane, float4 *hitA, uint32_t *hitRec, uint8_t *vis, uint32_t *status,
                                                         unsigned long long *stats) {
-    const uint32_t n = count[0] * mult;
+    const uint32_t cnt = count[0], n = cnt * mult;
     TraceAccel A = resolve_tlas(tlas);
     TraceCtr ctr{0, 0, 0, 0};
     uint32_t traced = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
+        const uint32_t kind = li / cnt, i = kind * plane + (li - kind * cnt);  // planar queue: kind-major
         const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
         const float4 a = rp[0], b = rp[1];
         TraceHit h;
@@ -332,16 +341,19 @@ __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const 
 __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
                                                             uint32_t n_recs, const float *env, uint32_t envSize,
                                                             unsigned long long *rayCounts) {
-    const uint32_t n = ws.counters[0] * 2;
+    const uint32_t cnt = ws.counters[0], n = cnt * 2;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t r = base + threadIdx.x;
+        const uint32_t lr = base + threadIdx.x;
+        // planar queue: plane 0 = indirect-diffuse rays, plane 1 = Phong-lobe rays; r is the physical index
+        const uint32_t kindPlane = lr >= cnt ? 1u : 0u, hitSlot = lr - kindPlane * cnt;
+        const uint32_t r = lr < n ? kindPlane * ws.plane + hitSlot : 0xffffffffu;
         bool wantShadow = false;
         f3 pos = mk3(0, 0, 0);
         LightEval le;
         uint32_t kind = 0, rec = 0;
         f3 specTerm = mk3(0, 0, 0);
         bool useDir = true, usePoint = true;
-        if (r < n) {
+        if (lr < n) {
             const float4 *rp = reinterpret_cast<const float4 *>(ws.secQ + r);
             const float4 a = rp[0], b = rp[1];
             if (b.w >= 0.0f) {
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constan
                     const rt_hit_record_dev &R = recs[rec];
                     const f3 N = normalize3(interpolate_normal(R, __float_as_uint(hA.w), hA.y, hA.z));
                     pos = o + hA.x * d;
-                    const uint32_t pix = ws.slotInfo[r >> 1].x;
+                    const uint32_t pix = ws.slotInfo[hitSlot].x;
                     const uint32_t x = L.x0 + pix % L.rw, y = L.y0 + pix / L.rw;
                     uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
                     le = eval_lights(L.f, pos, N);
@@ -384,8 +396,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constan
         }
         const uint32_t sh = warp_alloc(wantShadow, &ws.counters[1]);
         if (wantShadow) {
-            store_ray(&ws.shadowQ1[2 * size_t(sh) + 0], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
-            store_ray(&ws.shadowQ1[2 * size_t(sh) + 1], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
+            store_ray(&ws.shadowQ1[sh], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
+            store_ray(&ws.shadowQ1[2 * size_t(ws.plane) + sh], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
             ws.secShadow[r] = sh;
             ws.T0[r] = make_float4(le.dirPre.x, le.dirPre.y, le.dirPre.z, __uint_as_float(kind));
             ws.T1[r] = make_float4(le.pointPre.x, le.pointPre.y, le.pointPre.z, le.falloff);
@@ -403,7 +415,7 @@ __device__ __forceinline__ f3 secondary_radiance(const Launch &L, const WS &ws, 
     if ((kind & 15u) == 1) return mk3(t0.x, t0.y, t0.z);
     const float4 t1 = ws.T1[r], t2 = ws.T2[r];
     const uint32_t sh = ws.secShadow[r];
-    const float v0 = float(ws.vis1[2 * size_t(sh) + 0]), v1 = float(ws.vis1[2 * size_t(sh) + 1]);
+    const float v0 = float(ws.vis1[sh]), v1 = float(ws.vis1[2 * size_t(ws.plane) + sh]);
     const rt_material_params &m = recs[__float_as_uint(t2.w)].mat;
     f3 direct = mk3(0, 0, 0);
     const f3 dirC = mk3(t0.x, t0.y, t0.z) * v0;
@@ -432,19 +444,19 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Laun
         f3 color;
         if (flags & SLOT_AO) {
             const float4 nol = ws.S0[s], pdf = ws.S1[s];
-            const uint8_t *v = ws.vis0 + 4 * size_t(s);
+            const uint8_t *v = ws.vis0 + s;
+            const size_t pl = ws.plane;
             float vis = 0.0f;
             vis += float(v[0]) * nol.x / pdf.x;
-            vis += float(v[1]) * nol.y / pdf.y;
-            vis += float(v[2]) * nol.z / pdf.z;
-            vis += float(v[3]) * nol.w / pdf.w;
+            vis += float(v[pl]) * nol.y / pdf.y;
+            vis += float(v[2 * pl]) * nol.z / pdf.z;
+            vis += float(v[3 * pl]) * nol.w / pdf.w;
             const float ao = vis / 4.0f;
             write_pixel(L, out0, pitch0, x, y, mk3(ao, ao, ao), true);
             continue;
         }
         const float4 s0 = ws.S0[s], s1 = ws.S1[s], s2 = ws.S2[s];
-        const size_t sq = size_t(L.shadowsPerHit) * s;
-        const float v0 = float(ws.vis0[sq + 0]), v1 = float(ws.vis0[sq + 1]);
+        const float v0 = float(ws.vis0[s]), v1 = float(ws.vis0[size_t(ws.plane) + s]);
         f3 direct = mk3(0, 0, 0);
         const f3 dirC = mk3(s0.x, s0.y, s0.z) * v0;
         const f3 pointC = mk3(s1.x, s1.y, s1.z) * v1 * s0.w;
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Laun
         }
         f3 indirect = mk3(0, 0, 0);
         if (flags & SLOT_HAS_DIFFUSE) {
-            const f3 rad = secondary_radiance(L, ws, recs, 2 * s + 0);
+            const f3 rad = secondary_radiance(L, ws, recs, s);
             f3 c = mk3(0, 0, 0);
             if (flags & SLOT_UNIFORM) {
                 const float pdfU = 1.0f / (2.0f * RT_M_PI);
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Laun
         f3 spec = mk3(0, 0, 0);
         const f3 fres = mk3(s2.x, s2.y, s2.z);
         if (flags & SLOT_HAS_SPEC) {
-            const f3 refl = secondary_radiance(L, ws, recs, 2 * s + 1);
+            const f3 refl = secondary_radiance(L, ws, recs, ws.plane + s);
             spec = spec + refl * s2.w / s1.w;
         }
         const f3 albedo = mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
@@ -553,6 +565,7 @@ int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws) {
         ctx->ws.bytes = o;
     }
     uint8_t *b = static_cast<uint8_t *>(ctx->ws.base);
+    ws.plane = uint32_t(P);
     ws.hitA = (float4 *)(b + oHitA), ws.hitRec = (uint32_t *)(b + oHitRec), ws.counters = (uint32_t *)(b + oCnt);
     ws.slotInfo = (uint4 *)(b + oSlot), ws.S0 = (float4 *)(b + oS0), ws.S1 = (float4 *)(b + oS1), ws.S2 = (float4 *)(b + oS2);
     ws.S3 = (float *)(b + oS3), ws.shadowQ0 = (rt_ray *)(b + oSQ0), ws.vis0 = b + oV0, ws.secQ = (rt_ray *)(b + oSec);
@@ -634,16 +647,16 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     k_shade_primary<<<rt_div_up(P, kBlock), kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
                                                              ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
-    if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
-    else k_trace_persistent<0><<<pgrid<0>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, TraceSink{ws.secHitA, ws.secRec, nullptr, nullptr}, ctx->status, ws.counters + 4, 0, 0xFF);
+    if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.plane, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
+    else k_trace_persistent<0><<<pgrid<0>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.plane, TraceSink{ws.secHitA, ws.secRec, nullptr, nullptr}, ctx->status, ws.counters + 4, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
-    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
-    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, TraceSink{nullptr, nullptr, ws.vis0, nullptr}, ctx->status, ws.counters + 5, 0, 0xFF);
+    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
+    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, TraceSink{nullptr, nullptr, ws.vis0, nullptr}, ctx->status, ws.counters + 5, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
     k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
-    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
-    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
+    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
+    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;
@@ -684,7 +697,7 @@ static int trace_common(rt_context *ctx, const void *tlas, const rt_ray *rays, u
         for (uint64_t done = 0; done < n;) {
             const uint32_t chunk = uint32_t(std::min<uint64_t>(n - done, 1u << 30));
             RT_CUDA(cudaMemsetAsync(counter, 0, 4, ctx->stream));
-            k_trace_persistent<2><<<pgrid<2>(ctx), 128, 0, ctx->stream>>>(tlas, rays + done, nullptr, chunk, TraceSink{nullptr, nullptr, nullptr, hits + done},
+            k_trace_persistent<2><<<pgrid<2>(ctx), 128, 0, ctx->stream>>>(tlas, rays + done, nullptr, chunk, 0, TraceSink{nullptr, nullptr, nullptr, hits + done},
                                                                          ctx->status, counter, flags, mask);
             ctx->launches++;
             done += chunk;

@@ -54,10 +54,13 @@ struct TraceSink {  // where results go; only the members of the kernel's MODE a
 
 template <int MODE>
 __global__ void __launch_bounds__(128, RT_PERSIST_MIN_BLOCKS)
-k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult, TraceSink sink, uint32_t *status,
-                   uint32_t *nextRay, uint32_t userFlags, uint32_t userMask) {
+k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult, uint32_t plane, TraceSink sink,
+                   uint32_t *status, uint32_t *nextRay, uint32_t userFlags, uint32_t userMask) {
     constexpr bool GENERAL = MODE == 2;
-    const uint32_t n = count ? count[0] * mult : mult;  // standalone launches pass the ray count in `mult`
+    // Pipeline queues are planar (pipeline.cu): `mult` kinds of `count[0]` rays each, kind k starting at k * plane.
+    // Rays are drawn kind-major, so a warp holds one kind.  Standalone launches pass the ray count in `mult`.
+    const uint32_t cnt = count ? count[0] : 0u;
+    const uint32_t n = count ? cnt * mult : mult;
     const TraceAccel A = resolve_tlas(tlas);
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -125,8 +128,13 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             base = __shfl_sync(FULL, base, leader);
             noMore = base + uint32_t(idle) >= n;
             if (!alive) {
-                rayIdx = base + __popc(dead & ltMask);
-                if (rayIdx < n) {
+                const uint32_t drawn = base + __popc(dead & ltMask);
+                if (drawn < n) {
+                    rayIdx = drawn;
+                    if (!GENERAL) {
+                        const uint32_t kind = drawn / cnt;
+                        rayIdx = kind * plane + (drawn - kind * cnt);
+                    }
                     const float4 *rp = reinterpret_cast<const float4 *>(rays + rayIdx);
                     const float4 a = __ldcs(rp), b = __ldcs(rp + 1);
                     wox = a.x, woy = a.y, woz = a.z, tmin = a.w, wdx = b.x, wdy = b.y, wdz = b.z, tCur = b.w;

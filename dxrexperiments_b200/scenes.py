@@ -375,6 +375,11 @@ def workload(name: str, subdiv: int = 6) -> Workload:
                          "realtime pipeline: 1 spp + shadow rays + Phong-lobe bounce + DenoiseCompositor"),
                         [m], [IDENTITY_3X4], [0], [make_material()], FrameSetup(camera=BUNNY_CAMERA), 1920, 1080,
                         16 if name == "C2" else 1, realtime=(name == "C5"))
+    if name == "C1M":  # the north-star target scene: >= 1 Grays/s of incoherent secondary rays on ~1 M triangles at 1080p
+        m = bunny_scale(8)
+        return Workload(name, f"C1M 1M-triangle-scale synthetic mesh ({m.num_triangles} tris, flat BLAS, traversal section "
+                        "~200 MB > L2) 1920x1080 4 spp progressive", [m], [IDENTITY_3X4], [0], [make_material()],
+                        FrameSetup(camera=BUNNY_CAMERA), 1920, 1080, 4)
     if name == "C3":
         m = column_hall(16, 1000)
         setup = FrameSetup(camera=HALL_CAMERA, point_light_pos=(0.0, 8.0, 0.0, 1.0))

@@ -50,7 +50,9 @@ static void filter_pixel(const Img &input, const Img &joint, int x, int y, int d
         float dist = ((fabsf(sj[0] - cj[0]) + fabsf(sj[1] - cj[1])) + fabsf(sj[2] - cj[2])) * 10.0f;
         float cw = 1.0f - fminf(fmaxf(dist, 0.0f), 1.0f);
         float bw = g * cw;
-        for (int c = 0; c < 3; ++c) color[c] += s[c] * bw;
+        // `color += s * w`: whether the multiply-add is fused is implementation-defined in HLSL (DXIL FMad / driver
+        // contraction; the shader is not `precise`).  Pinned as ONE fused multiply-add, like the ray/box test.
+        for (int c = 0; c < 3; ++c) color[c] = fmaf(s[c], bw, color[c]);
         weight += bw;
     }
     for (int c = 0; c < 3; ++c) out[c] = color[c] / weight;
