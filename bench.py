@@ -505,24 +505,37 @@ def measure_build(args, ctx, rt, torch, stream):
     rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, 0, C.byref(info)))
     scr = torch.empty(info.scratch_bytes, dtype=torch.uint8, device="cuda")
     res = torch.empty(info.result_bytes, dtype=torch.uint8, device="cuda")
-    times = []
-    l0 = ctx.launches()
-    for r in range(3 + max(3, args.steps)):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, 0, scr.data_ptr(), scr.numel(), res.data_ptr(), res.numel()))
-        e1.record(stream)
-        torch.cuda.synchronize()
-        if r >= 3:
-            times.append(e0.elapsed_time(e1))
-    launches = (ctx.launches() - l0) // (3 + max(3, args.steps))
-    ms = float(np.median(times))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+
+    def timed(flags):
+        times = []
+        l0 = ctx.launches()
+        reps = 3 + max(3, args.steps)
+        for r in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, flags, scr.data_ptr(), scr.numel(), res.data_ptr(), res.numel()))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if r >= 3:
+                times.append(e0.elapsed_time(e1))
+        return float(np.median(times)), int((ctx.launches() - l0) // reps)
+
+    # Headline: the LBVH of the north star (Morton codes, radix sort, Karras hierarchy, bottom-up fit) = PREFER_FAST_BUILD,
+    # which skips the Fallback Layer's treelet optimisation (FL/TreeletReorder.cpp:66-69).  `with_treelet_pass` = default
+    # flags, what the reference application builds (one optimisation pass), `fast_trace` = three passes.
+    ms, launches = timed(T.BUILD_FLAG_PREFER_FAST_BUILD)
+    ms_default, launches_default = timed(0)
+    ms_trace, _ = timed(T.BUILD_FLAG_PREFER_FAST_TRACE)
     gbs = n * 432.0 / (ms * 1e-3) / 1e9
-    return {"metric": "LBVH build Mtri/s", "value": n / ms / 1e3, "triangles": n, "ms": ms, "launches_per_build": int(launches),
+    return {"metric": "LBVH build Mtri/s", "value": n / ms / 1e3, "triangles": n, "ms": ms, "launches_per_build": launches,
+            "build_flags": "PREFER_FAST_BUILD (plain LBVH)",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes_per_triangle": 432},
+            "with_treelet_pass": {"value": n / ms_default / 1e3, "ms": ms_default, "launches_per_build": launches_default,
+                                  "build_flags": "NONE (1 treelet pass, the reference application's build)"},
+            "fast_trace": {"value": n / ms_trace / 1e3, "ms": ms_trace, "build_flags": "PREFER_FAST_TRACE (3 treelet passes)"},
             "workload": f"{n}-triangle soup, uniform centroids in [-500,500]^3, edge <= 1, device-resident VB/IB -> traversable BVH "
                         "(working set >> L2)", "result_mb": info.result_bytes / 2**20, "scratch_mb": info.scratch_bytes / 2**20}
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "treelet.cuh"
 
 namespace {
 
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
     }
     uint32_t count = 1;
     while (true) {
-        const uint32_t parent = UPDATE ? parents[node] : hier[node].parent;
+        const uint32_t parent = UPDATE ? parents[node] : (hier[node].parent & ~treelet::kCollapseBit);
         __threadfence();
         const uint32_t other = atomicAdd(&counters[parent], count);
         if (other == 0) return;  // first to arrive: the sibling will fit the parent
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(kThreads) k_save_update_cache(const uint32_t *
                                                                 uint32_t *sort_cache, uint32_t *parents) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sort_cache[perm[i]] = i;
-    if (i < 2 * n - 1) parents[i] = i == 0 ? 0u : hier[i].parent;
+    if (i < 2 * n - 1) parents[i] = i == 0 ? 0u : (hier[i].parent & ~treelet::kCollapseBit);
 }
 // PERFORM_UPDATE: sorted slot -> load-order element, so that the rearrange kernels of the full build are reused.
 __global__ void __launch_bounds__(kThreads) k_invert_cache(const uint32_t *sort_cache, uint32_t n, uint32_t *perm) {
@@ -702,7 +703,7 @@ SortPlan plan_sort(uint32_t n, int num_sms) {
 }
 
 struct Layout {
-    uint64_t aabb_enc, aabb, codes, keysB, valsB, keysC, valsC, hier, counters, hist, elems, meta, total;
+    uint64_t aabb_enc, aabb, codes, keysB, valsB, keysC, valsC, hier, counters, hist, elems, meta, tl_aabb, tl_base, total;
 };
 Layout make_layout(uint32_t n, bool top) {
     Layout L{};
@@ -725,6 +726,9 @@ Layout make_layout(uint32_t n, bool top) {
     L.hist = take(4ull * kRadix * 148 * 8);
     L.elems = take((top ? 32 : 48) * nn);  // BLAS: rt_packed_tri records in load order; TLAS: instance boxes
     L.meta = take((top ? 116 : 0) * nn);
+    // treelet pass (bottom level only): one 24-byte box per node, the base-treelet list (FL/GpuBVH2Builder.cpp:376-408)
+    L.tl_aabb = take(top ? 0 : 24 * (2 * nn - 1));
+    L.tl_base = take(top ? 0 : 4 * (nn / treelet::kFull + 2));
     L.total = o;
     return L;
 }
@@ -813,6 +817,10 @@ static uint32_t count_prims(const rt_geometry_desc *geoms, uint32_t n_geoms) {
 
 static inline bool allows_update(uint32_t f) { return (f & RT_BUILD_FLAG_ALLOW_UPDATE) != 0; }
 static inline bool performs_update(uint32_t f) { return (f & RT_BUILD_FLAG_PERFORM_UPDATE) != 0; }
+// FL/TreeletReorder.cpp:66-80
+static inline uint32_t treelet_passes(uint32_t f) {
+    return (f & RT_BUILD_FLAG_PREFER_FAST_BUILD) ? 0u : ((f & RT_BUILD_FLAG_PREFER_FAST_TRACE) ? 3u : 1u);
+}
 
 int rt_blas_prebuild(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t flags, rt_prebuild_info *info) {
     RT_REQUIRE(ctx && info && (geoms || n_geoms == 0), "null argument");
@@ -882,36 +890,55 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
             k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier);
             ctx->launches++;
         }
+    }
+    rt_aabb_node *nodes = reinterpret_cast<rt_aabb_node *>(result + 16);
+    rt_wide_node *wide = reinterpret_cast<rt_wide_node *>(result + R.wide);
+    rt_ext_header *ext = reinterpret_cast<rt_ext_header *>(result + R.ext);
+    uint32_t *counters = reinterpret_cast<uint32_t *>(scratch + L.counters);
+    const rt_aabb_node *boxes = reinterpret_cast<rt_aabb_node *>(scratch + L.elems);
+    rt_primitive *sp = reinterpret_cast<rt_primitive *>(result + R.off.offsetToVertices);
+    rt_packed_tri *packed = reinterpret_cast<rt_packed_tri *>(result + R.leaf);
+    if (top)
+        k_rearrange_instances<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), perm, n,
+                                                         reinterpret_cast<rt_bvh_metadata *>(result + R.off.offsetToVertices),
+                                                         reinterpret_cast<rt_packed_instance *>(result + R.leaf));
+    else
+        k_rearrange_tris<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), perm, n, sp,
+                                                    reinterpret_cast<rt_primitive_meta *>(result + R.off.offsetToPrimitiveMetaData), packed);
+    ctx->launches++;
+    if (!update) {
+        if (!top) {
+            // FL/TreeletReorder.cpp:38-109: 0 / 1 / 3 optimisation passes, MinTrianglesPerTreelet 7, 14, 28
+            uint32_t min_tris = treelet::kFull;
+            float *tl_aabb = reinterpret_cast<float *>(scratch + L.tl_aabb);
+            uint32_t *tl_base = reinterpret_cast<uint32_t *>(scratch + L.tl_base);
+            for (uint32_t pass = 0; pass < treelet_passes(flags) && min_tris <= n; ++pass, min_tris *= 2) {
+                RT_CUDA(cudaMemsetAsync(counters, 0, 4ull * n, st));  // ClearBuffers.hlsl
+                RT_CUDA(cudaMemsetAsync(tl_base, 0, 4, st));
+                treelet::k_find_treelets<<<grid, kThreads, 0, st>>>(n, hier, packed, counters, tl_aabb, tl_base, min_tris);
+                treelet::k_treelet_reorder<<<rt_div_up(n / min_tris, treelet::kWarps), 32 * treelet::kWarps, 0, st>>>(n, hier, counters,
+                                                                                                                    tl_aabb, tl_base);
+                ctx->launches += 2;
+            }
+        }
         if (allows_update(flags)) {
             k_save_update_cache<<<rt_div_up(2ull * n - 1, kThreads), kThreads, 0, st>>>(perm, hier, n, sort_cache, parents);
             ctx->launches++;
         }
     }
-    RT_CUDA(cudaMemsetAsync(scratch + L.counters, 0, 4ull * n, st));
-    rt_aabb_node *nodes = reinterpret_cast<rt_aabb_node *>(result + 16);
-    rt_wide_node *wide = reinterpret_cast<rt_wide_node *>(result + R.wide);
-    rt_ext_header *ext = reinterpret_cast<rt_ext_header *>(result + R.ext);
-    uint32_t *counters = reinterpret_cast<uint32_t *>(scratch + L.counters);
+    RT_CUDA(cudaMemsetAsync(counters, 0, 4ull * n, st));
     if (top) {
-        const rt_aabb_node *boxes = reinterpret_cast<rt_aabb_node *>(scratch + L.elems);
-        k_rearrange_instances<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), perm, n,
-                                                         reinterpret_cast<rt_bvh_metadata *>(result + R.off.offsetToVertices),
-                                                         reinterpret_cast<rt_packed_instance *>(result + R.leaf));
         if (update)
             k_fit<true, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, nullptr, boxes, perm, wide, ext, parents);
         else
             k_fit<true, false><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, nullptr, boxes, perm, wide, ext, parents);
     } else {
-        rt_primitive *sp = reinterpret_cast<rt_primitive *>(result + R.off.offsetToVertices);
-        k_rearrange_tris<<<grid, kThreads, 0, st>>>(reinterpret_cast<rt_packed_tri *>(scratch + L.elems), perm, n, sp,
-                                                    reinterpret_cast<rt_primitive_meta *>(result + R.off.offsetToPrimitiveMetaData),
-                                                    reinterpret_cast<rt_packed_tri *>(result + R.leaf));
         if (update)
             k_fit<false, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
         else
             k_fit<false, false><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
     }
-    ctx->launches += 2;
+    ctx->launches++;
     if (n > 1) {
         k_collapse4<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(wide, n - 1, reinterpret_cast<rt_wide4_node *>(result + R.wide4));
         ctx->launches++;

@@ -39,6 +39,7 @@ def lib():
         L.orc_morton_code_from_centroid.restype = u32
         L.orc_sort_pairs.argtypes = [vp, u32, vp, vp]
         L.orc_build_hierarchy.argtypes = [vp, u32, vp]
+        L.orc_treelet_optimise.argtypes = [u32, vp, vp, u32]
         L.orc_init_rand.argtypes = [u32, u32]
         L.orc_init_rand.restype = u32
         L.orc_next_rand.argtypes = [C.POINTER(u32)]
@@ -132,6 +133,15 @@ def build_hierarchy(sorted_codes: np.ndarray) -> np.ndarray:
     return h
 
 
+def treelet_optimise(hier: np.ndarray, sorted_prims: np.ndarray, build_flags: int = 0) -> np.ndarray:
+    """FL/TreeletReorder.cpp:38-109 on a copy of `hier` (2n-1 {parent,left,right}) over n sorted rt_primitive records."""
+    h = np.ascontiguousarray(hier, dtype=T.HIER_DTYPE).copy()
+    prims = np.ascontiguousarray(sorted_prims, dtype=T.PRIM_DTYPE)
+    assert h.shape[0] == 2 * prims.shape[0] - 1
+    lib().orc_treelet_optimise(prims.shape[0], _ptr(h), _ptr(prims), build_flags)
+    return h
+
+
 def init_rand(v0: int, v1: int) -> int:
     return int(lib().orc_init_rand(v0 & 0xFFFFFFFF, v1 & 0xFFFFFFFF))
 
@@ -190,8 +200,8 @@ class Blas:
         return descs
 
     @classmethod
-    def from_mesh(cls, mesh, flags=T.GEOMETRY_FLAG_OPAQUE):
-        return cls([dict(vertices=mesh.vertices, stride=24, indices=mesh.indices, flags=flags)])
+    def from_mesh(cls, mesh, flags=T.GEOMETRY_FLAG_OPAQUE, build_flags: int = 0):
+        return cls([dict(vertices=mesh.vertices, stride=24, indices=mesh.indices, flags=flags)], build_flags)
 
     def __del__(self):
         if getattr(self, "handle", None):

@@ -15,8 +15,9 @@
  *     (externals/D3D12RaytracingFallback/src/FallbackLayerUnitTests/fallbacklayerunittests.cpp
  *      :2569-2615, 2627-2701, 2831-2945, 3630-4078; BVHValidator.cpp:58-176) — see
  *     tests/test_oracle_reference_kats.py.
- *   - treelet reordering (FL/TreeletReorder.hlsl): NOT restated; the reference's own tests pin
- *     only topology sanity for it.  Oracle and CUDA both emit the plain Karras tree.
+ *   - treelet optimisation (FL/FindTreelets.hlsl, FL/TreeletReorder.hlsl): restated in oracle_treelet.cpp;
+ *     the reference's own tests pin only topology sanity for it (UT:2957-3068, re-run in
+ *     tests/test_oracle_reference_kats.py), the arithmetic is pinned by code inspection.
  *   - shading, RNG, accumulation, denoiser: PARITY UNPINNED by any reference test (the app has
  *     none); pinned by code inspection only, plus frozen known-answer vectors of our own.
  *
@@ -46,14 +47,17 @@ uint32_t orc_morton_code_from_centroid(const float c[3], const float aabb[6]);
 void orc_sort_pairs(const uint32_t *codes, uint32_t n, uint32_t *sorted_codes, uint32_t *perm);
 /* FL/BuildBVHSplits.hlsli:35-143; nodes[2n-1] = {parent,left,right}; leaves have left=right=0. */
 void orc_build_hierarchy(const uint32_t *sorted_codes, uint32_t n, rt_hierarchy_node *nodes);
+/* FL/TreeletReorder.cpp:38-109 on a hierarchy over n sorted triangles, in place. */
+void orc_treelet_optimise(uint32_t n, rt_hierarchy_node *hier, const rt_primitive *sorted_prims, uint32_t build_flags);
 /* initRand / nextRand: assets/shaders/RaytracingUtils.hlsli:26-45. */
 uint32_t orc_init_rand(uint32_t v0, uint32_t v1);
 float orc_next_rand(uint32_t *state);
 
 /* ---- acceleration structures ---- */
 
-/* BLAS over triangle geometries (host pointers in the descs).  Follows
- * FL/GpuBVH2Builder.cpp:137-328 minus the treelet pass. */
+/* BLAS over triangle geometries (host pointers in the descs).  Follows FL/GpuBVH2Builder.cpp:137-328 including the
+ * treelet pass: build_flags PREFER_FAST_BUILD -> 0 passes, PREFER_FAST_TRACE -> 3, otherwise 1
+ * (FL/TreeletReorder.cpp:66-80).  orc_blas_hierarchy returns the hierarchy AFTER that pass. */
 orc_blas *orc_blas_build(const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags);
 void orc_blas_free(orc_blas *b);
 uint32_t orc_blas_num_prims(const orc_blas *b);

@@ -336,7 +336,7 @@ void orc_build_hierarchy(const uint32_t *sorted_codes, uint32_t n, rt_hierarchy_
     build_hierarchy(sorted_codes, n, nodes);
 }
 
-orc_blas *orc_blas_build(const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t /*build_flags*/) {
+orc_blas *orc_blas_build(const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags) {
     orc_blas *b = new orc_blas();
     load_triangles(geoms, n_geoms, b->prims, b->meta);
     const uint32_t n = b->n = uint32_t(b->prims.size());
@@ -366,6 +366,8 @@ orc_blas *orc_blas_build(const rt_geometry_desc *geoms, uint32_t n_geoms, uint32
         sp[i] = b->prims[b->perm[i]];
         sm[i] = b->meta[b->perm[i]];
     }
+    // FL/GpuBVH2Builder.cpp:312-326: the treelet pass works on the hierarchy and the sorted triangles
+    treelet_optimise(n, b->hier.data(), sp, build_flags);
     fit_boxes(n, b->hier.data(), nodes, [&](uint32_t slot) { return triangle_leaf_box(sp[slot]); });
     make_update_cache(n, b->perm.data(), nodes, b->sort_cache, b->parents);
     return b;

@@ -68,6 +68,9 @@ static inline Box aabb_to_box(Aabb a) {
 static inline Aabb box_to_aabb(Box b) { return Aabb{b.center - b.half, b.center + b.half}; }
 
 void invert_affine(const float t[12], float out[12]);
+// FL/TreeletReorder.cpp:38-109 (oracle_treelet.cpp)
+uint32_t treelet_pass_count(uint32_t build_flags);
+void treelet_optimise(uint32_t n, rt_hierarchy_node *hier, const rt_primitive *sorted_prims, uint32_t build_flags);
 Aabb transform_aabb(Aabb box, const float m[12]);
 
 }  // namespace orc

@@ -39,9 +39,14 @@ def main():
     # build: a seeded soup with duplicate codes
     soup = scenes.triangle_soup(2000, seed=99, extent=50.0, edge=2.0)
     blas = oracle.Blas.from_mesh(soup)
-    np.savez_compressed(os.path.join(HERE, "build_soup2000.npz"), aabb=blas.scene_aabb(), morton=blas.morton(),
-                        perm=blas.perm(), hier=blas.hierarchy().view(np.uint32).reshape(-1, 3),
-                        nodes=T.parse_blas_blob(blas.blob())["nodes"].view(np.uint32).reshape(-1, 8))
+    build = dict(aabb=blas.scene_aabb(), morton=blas.morton(), perm=blas.perm())
+    # hierarchy + fitted nodes per treelet-pass count: default flags (1 pass), PREFER_FAST_BUILD (0: the plain Karras
+    # tree), PREFER_FAST_TRACE (3) — FL/TreeletReorder.cpp:66-80
+    for suffix, flags in (("", 0), ("_fast_build", T.BUILD_FLAG_PREFER_FAST_BUILD), ("_fast_trace", T.BUILD_FLAG_PREFER_FAST_TRACE)):
+        b = oracle.Blas.from_mesh(soup, build_flags=flags)
+        build["hier" + suffix] = b.hierarchy().view(np.uint32).reshape(-1, 3)
+        build["nodes" + suffix] = T.parse_blas_blob(b.blob())["nodes"].view(np.uint32).reshape(-1, 8)
+    np.savez_compressed(os.path.join(HERE, "build_soup2000.npz"), **build)
     # trace + render: Cornell 48x48
     case = cornell_case()
     tlas, recs = case.oracle(oracle)

@@ -32,11 +32,16 @@ def _mesh_cases():
 MESHES = _mesh_cases()
 
 
+# treelet pass count by build flag (FL/TreeletReorder.cpp:66-80): default 1, PREFER_FAST_BUILD 0, PREFER_FAST_TRACE 3
+BUILD_FLAGS = {"default": 0, "fast_build": T.BUILD_FLAG_PREFER_FAST_BUILD, "fast_trace": T.BUILD_FLAG_PREFER_FAST_TRACE}
+
+
+@pytest.mark.parametrize("variant", sorted(BUILD_FLAGS))
 @pytest.mark.parametrize("name", sorted(MESHES))
-def test_blas_stages_and_blob_bit_exact(name, ctx, orc):
+def test_blas_stages_and_blob_bit_exact(name, variant, ctx, orc):
     mesh = MESHES[name]
-    ref = orc.Blas.from_mesh(mesh)
-    acc = ctx.build_blas_from_mesh(mesh, keep_scratch=True)
+    ref = orc.Blas.from_mesh(mesh, build_flags=BUILD_FLAGS[variant])
+    acc = ctx.build_blas_from_mesh(mesh, keep_scratch=True, build_flags=BUILD_FLAGS[variant])
     ctx.sync()
     assert acc.n == ref.n == mesh.num_triangles
     np.testing.assert_array_equal(acc.stage("primitives").view(np.uint8), ref.unsorted_prims().view(np.uint8))

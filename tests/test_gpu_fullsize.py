@@ -175,14 +175,15 @@ def test_c4_build_1m_bit_exact_and_10m_properties(ctx, rt, orc):
     assert leaf.sum() == n and not leaf[: n - 1].any()
     slots = nodes["flags"][n - 1:] & 0x00FFFFFF
     assert np.array_equal(slots, np.arange(n, dtype=np.uint32))              # leaf i holds sorted slot i
-    # topology from the Karras pass (full 32-bit links; the reference blob keeps only 24 bits of the left index —
+    # topology from the Karras pass + one treelet pass (default build flags) (full 32-bit links; the reference blob keeps only 24 bits of the left index —
     # FL/RayTracingHelper.hlsli:112-118 — which wraps beyond 8.38 M primitives; the traversal section
     # that the kernels read carries full-width references)
     hier = gb.stage("hierarchy")
     left, right = hier["left"][: n - 1], hier["right"][: n - 1]
     refs = np.bincount(np.concatenate([left, right]), minlength=2 * n - 1)
     assert refs[0] == 0 and (refs[1:] == 1).all()                            # every node but the root has one parent
-    assert np.array_equal(hier["parent"][left], np.arange(n - 1)) and np.array_equal(hier["parent"][right], np.arange(n - 1))
+    parent = hier["parent"] & 0x7FFFFFFF  # bit 31 = bCollapseChildren, set by the treelet pass (FL/RayTracingHlslCompat.h:46-58)
+    assert np.array_equal(parent[left], np.arange(n - 1)) and np.array_equal(parent[right], np.arange(n - 1))
     blob_right = nodes["right"][: n - 1]
     assert ((blob_right == left) | (blob_right == right)).all()              # the blob's right child is one of the two
     assert ((nodes["flags"][: n - 1] & 0x00FFFFFF) == (np.where(blob_right == right, left, right) & 0x00FFFFFF)).all()

@@ -169,6 +169,135 @@ def test_hierarchy_is_a_proper_binary_radix_tree(orc):
     assert len(covered) == n - 1
 
 
+# ------------------------------------------------------------------------------------------------ treelet pass
+def _check_hierarchy(h, n):
+    """The walk of TestTreeletReordering (UT:3041-3066): every child's ParentIndex is its parent, n leaves reachable.
+    On the C++ side ParentIndex is a 31-bit field beside bCollapseChildren (FL/RayTracingHlslCompat.h:46-58), so the
+    reference's comparison ignores bit 31."""
+    stack, leaves, internal = [0], 0, 0
+    while stack:
+        v = stack.pop()
+        if v >= n - 1:
+            leaves += 1
+            continue
+        internal += 1
+        l, r = int(h["left"][v]), int(h["right"][v])
+        for c in (l, r):
+            p = int(h["parent"][c])
+            assert p & 0x7FFFFFFF == v, "incorrect parent index"
+        stack += [l, r]
+    assert leaves == n and internal == n - 1, "incorrectly constructed hierarchy"
+
+
+@pytest.mark.parametrize("flag", [T.BUILD_FLAG_PREFER_FAST_TRACE, T.BUILD_FLAG_PREFER_FAST_BUILD, 0])
+def test_treelet_reordering_reference_unit_test(flag, orc):
+    """TreeletReorderingFastTrace / FastBuild (UT:2947-3068): 16 point triangles at x = -i (i < 8) or +i, a heap-shaped
+    hierarchy (children 2i+1, 2i+2), then the parent/leaf-count walk."""
+    n = 16
+    tris = np.zeros((n, 3, 3), np.float32)
+    for i in range(n):
+        tris[i, :, 0] = -i if i < n // 2 else i
+    h = np.zeros(2 * n - 1, T.HIER_DTYPE)
+    for i in range(2 * n - 1):
+        h["parent"][i] = (i - 1) // 2 if i else 0
+        h["left"][i], h["right"][i] = 2 * i + 1, 2 * i + 2
+    out = orc.treelet_optimise(h, orc.prims_from_triangles(tris), flag)
+    _check_hierarchy(out, n)
+    if flag == T.BUILD_FLAG_PREFER_FAST_BUILD:  # zero passes (FL/TreeletReorder.cpp:66-69)
+        assert out.tobytes() == h.tobytes()
+    else:
+        assert out.tobytes() != h.tobytes(), "the interleaved point cloud must be re-partitioned"
+
+
+def _leaf_aabb(tri):
+    f32 = np.float32
+    mn, mx = tri.min(0), tri.max(0)
+    mn = np.minimum(mn, mx - f32(0.001))
+    c = (mn + mx) * f32(0.5)
+    hd = mx - c
+    return c - hd, c + hd
+
+
+def _area(mn, mx):
+    d = (mx - mn).astype(np.float32)
+    return np.float32(2.0) * ((d[0] * d[1] + d[0] * d[2]) + d[1] * d[2])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_treelet_of_seven_is_the_optimum_of_the_reference_cost_model(seed, orc):
+    """n = 7: the root is the only treelet, so the output tree must minimise the reference's own cost function
+    (TreeletReorder.hlsl:126-183, COMBINE_LEAF_NODES = 1), evaluated here by an independent memoised recursion."""
+    f32 = np.float32
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tris = (rng.random((7, 3, 3), dtype=np.float32) * f32(4.0)).astype(np.float32)
+    prims = orc.prims_from_triangles(tris)
+    codes, perm = orc.sort_pairs(orc.morton_codes(prims, orc.scene_aabb(prims)))
+    h0 = orc.build_hierarchy(codes)
+    out = orc.treelet_optimise(h0, prims[perm], 0)
+    _check_hierarchy(out, 7)
+    boxes = [_leaf_aabb(tris[perm[i]]) for i in range(7)]
+
+    def union(mask):
+        idx = [i for i in range(7) if mask >> i & 1]
+        return np.min([boxes[i][0] for i in idx], 0), np.max([boxes[i][1] for i in idx], 0)
+
+    root_area = _area(*union(127))
+    memo = {}
+
+    def best(mask):
+        if mask in memo:
+            return memo[mask]
+        k = bin(mask).count("1")
+        a = _area(*union(mask))
+        if k == 1:
+            r = f32(1.2) * a / root_area
+        else:
+            low, sub = None, (mask - 1) & mask
+            while sub:
+                c = best(sub) + best(mask ^ sub)
+                low = c if low is None or c < low else low
+                sub = (sub - 1) & mask
+            r = min(f32(1.2) * a + low, f32(1.0) * a * f32(k))
+        memo[mask] = f32(r)
+        return memo[mask]
+
+    def tree_cost(v):
+        """cost of the oracle's output subtree under the same model; returns (cost, leaf mask)"""
+        if v >= 6:
+            m = 1 << (v - 6)
+            return best(m), m
+        (cl, ml), (cr, mr) = tree_cost(int(out["left"][v])), tree_cost(int(out["right"][v]))
+        m = ml | mr
+        a = _area(*union(m))
+        return f32(min(f32(1.2) * a + (cl + cr), f32(1.0) * a * f32(bin(m).count("1")))), m
+
+    got, mask = tree_cost(0)
+    assert mask == 127
+    assert got == best(127)
+
+
+@pytest.mark.parametrize("flags", [0, T.BUILD_FLAG_PREFER_FAST_TRACE])
+def test_blas_with_treelet_pass_passes_reference_validator_and_traces_identically(flags, orc):
+    tris = ut_triangles(300, seed=11) * np.float32(0.01)
+    geoms = [dict(vertices=tris.reshape(-1, 3), stride=12, indices=None)]
+    plain = orc.Blas(geoms, T.BUILD_FLAG_PREFER_FAST_BUILD)
+    opt = orc.Blas(geoms, flags)
+    assert validate_bvh(opt.blob(), list(tris)) == 300
+    _check_hierarchy(opt.hierarchy(), 300)
+    assert opt.hierarchy().tobytes() != plain.hierarchy().tobytes()
+    np.testing.assert_array_equal(opt.perm(), plain.perm())          # the pass touches only the topology
+    rng = np.random.Generator(np.random.PCG64(5))
+    rays = np.zeros(2000, T.RAY_DTYPE)
+    rays["origin"] = rng.random((2000, 3), dtype=np.float32) * 10 - 5
+    d = rng.standard_normal((2000, 3)).astype(np.float32)
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["tmax"] = 1e30
+    a = orc.Tlas([plain], [scenes.IDENTITY_3X4]).trace(rays)
+    b = orc.Tlas([opt], [scenes.IDENTITY_3X4]).trace(rays)
+    np.testing.assert_array_equal(a["primitive_index"], b["primitive_index"])
+    np.testing.assert_array_equal(a["t"], b["t"])
+
+
 # ------------------------------------------------------------------------------------------------ tracing known answers
 def _hit_grid(hits):
     return (hits["primitive_index"] != T.NO_HIT).reshape(4, 6)
@@ -317,11 +446,15 @@ def test_update_with_unchanged_input_is_the_identity_and_matches_a_rebuild_when_
     blob0 = blas.blob()
     blas.update(g)
     np.testing.assert_array_equal(blas.blob(), blob0)
-    # power-of-two scale about the origin: every coordinate, centroid and box scales exactly, the Morton codes are equal
+    # power-of-two scale about the origin: every coordinate, centroid and box scales exactly, the Morton codes are equal.
+    # PREFER_FAST_BUILD: the treelet pass's cost model mixes normalised and raw areas (TreeletReorder.hlsl:126-183), so
+    # its topology is not scale invariant; the plain Karras tree is.
+    fast = T.BUILD_FLAG_ALLOW_UPDATE | T.BUILD_FLAG_PREFER_FAST_BUILD
+    blas = orc.Blas(g, build_flags=fast)
     moved = mesh.vertices.copy()
     moved["position"] *= np.float32(4.0)
     g2 = [dict(vertices=moved, stride=24, indices=mesh.indices)]
-    fresh = orc.Blas(g2, build_flags=T.BUILD_FLAG_ALLOW_UPDATE)
+    fresh = orc.Blas(g2, build_flags=fast)
     np.testing.assert_array_equal(fresh.perm(), blas.perm())
     blas.update(g2)
     a, b = T.parse_blas_blob(blas.blob()), T.parse_blas_blob(fresh.blob())
