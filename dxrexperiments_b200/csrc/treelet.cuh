@@ -118,42 +118,52 @@ __global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_
     uint32_t *hw = reinterpret_cast<uint32_t *>(hier);  // {parent, left, right} x 3 words
     const unsigned full = 0xffffffffu;
 
+    // children of `node`, known to every lane at the top of the loop
+    uint32_t cl = 0, cr = 0;
+    if (lane == 0) cl = __ldcg(hw + 3 * size_t(node) + 1), cr = __ldcg(hw + 3 * size_t(node) + 2);
+    cl = __shfl_sync(full, cl, 0), cr = __shfl_sync(full, cr, 0);
+
     while (true) {
-        // ---- FormTreelet (:40-83): lane i owns treelet leaf i
-        uint32_t my = 0xffffffffu;
+        // lane 0 starts the loads the climb at the end of this step needs; none of them is touched by this step
+        // (ReformTree leaves the root's parent link and box as they are: the box is the exact union of the same leaves)
+        uint32_t up = 0, ours = 0, pl = 0, pr = 0;
+        A6 rootBox{};
+        if (lane == 0 && node != 0) {
+            up = __ldcg(hw + 3 * size_t(node)) & ~kCollapseBit;
+            ours = __ldcg(num_tris + node);
+            rootBox = ld_aabb(aabbs, node);
+        }
+        // ---- FormTreelet (:40-83): lane i owns treelet leaf i and prefetches that node's children with its box
+        uint32_t my = 0xffffffffu, myL = 0, myR = 0;
         float myArea = 0.0f;
         A6 myBox{};
-        {
-            uint32_t l = 0, r = 0;
-            if (lane == 0) l = __ldcg(hw + 3 * size_t(node) + 1), r = __ldcg(hw + 3 * size_t(node) + 2);
-            l = __shfl_sync(full, l, 0), r = __shfl_sync(full, r, 0);
-            if (lane == 0) my = l, s_int[w][0] = node;
-            if (lane == 1) my = r;
-            if (lane < 2) myBox = ld_aabb(aabbs, my), myArea = area(myBox);
-        }
+        auto fetch = [&]() {
+            myBox = ld_aabb(aabbs, my);
+            if (my < nInternal) myL = __ldcg(hw + 3 * size_t(my) + 1), myR = __ldcg(hw + 3 * size_t(my) + 2);
+            myArea = area(myBox);
+        };
+        if (lane == 0) my = cl, s_int[w][0] = node;
+        if (lane == 1) my = cr;
+        if (lane < 2) fetch();
         bool formed = true;
         for (int size = 2; size < int(kFull); ++size) {
-            // "surfaceArea > largestSurfaceArea" from 0.0, scanning i upwards: the largest positive area, lowest i on ties
-            float best = (lane < size && my < nInternal && myArea > 0.0f) ? myArea : 0.0f;
-            int who = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(full, best, o);
-                const int ow = __shfl_xor_sync(full, who, o);
-                if (ob > best || (ob == best && ow < who)) best = ob, who = ow;
-            }
-            if (!(best > 0.0f)) {  // no splittable leaf with a positive area: leave the treelet alone (unreachable for finite input: leaf boxes are padded)
+            // "surfaceArea > largestSurfaceArea" from 0.0, scanning i upwards: the largest positive area, lowest i on ties.
+            // Positive floats order like their bit patterns: one integer max-reduction and one ballot.
+            const uint32_t key = (lane < size && my < nInternal && myArea > 0.0f) ? __float_as_uint(myArea) : 0u;
+            const uint32_t top = __reduce_max_sync(full, key);
+            if (top == 0u) {  // no splittable leaf with a positive area: leave the treelet alone (unreachable for finite input: leaf boxes are padded)
                 formed = false;
                 break;
             }
+            const int who = __ffs(__ballot_sync(full, key == top)) - 1;
             const uint32_t pick = __shfl_sync(full, my, who);
-            uint32_t l = 0, r = 0;
-            if (lane == 0) l = __ldcg(hw + 3 * size_t(pick) + 1), r = __ldcg(hw + 3 * size_t(pick) + 2), s_int[w][size - 1] = pick;
-            l = __shfl_sync(full, l, 0), r = __shfl_sync(full, r, 0);
+            const uint32_t l = __shfl_sync(full, myL, who), r = __shfl_sync(full, myR, who);
+            if (lane == 0) s_int[w][size - 1] = pick;
             if (lane == who) my = l;
             if (lane == size) my = r;
-            if (lane == who || lane == size) myBox = ld_aabb(aabbs, my), myArea = area(myBox);
+            if (lane == who || lane == size) fetch();
         }
+        if (lane == 0 && node != 0) pl = __ldcg(hw + 3 * size_t(up) + 1), pr = __ldcg(hw + 3 * size_t(up) + 2);
 
         if (formed) {
             if (lane < int(kFull)) {
@@ -173,17 +183,44 @@ __global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_
                     }
                 return u;
             };
+            {
+                // 127 subset areas, four per lane: subsets lane, lane+32, lane+64, lane+96 share the members given by the
+                // lane's five low bits, so that union is formed once and extended by leaves 5 and 6
+                A6 lo{{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t mask = lane + 32 * k;
-                if (mask) s_cost[w][mask] = area(subset_box(mask));  // intermediate value: raw surface area (:122)
+                for (int i = 0; i < 5; ++i)
+                    if (lane & (1 << i)) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) lo.mn[k] = fminf(lo.mn[k], s_box[w][i][k]), lo.mx[k] = fmaxf(lo.mx[k], s_box[w][i][3 + k]);
+                    }
+                A6 b5, b6;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    b5.mn[k] = s_box[w][5][k], b5.mx[k] = s_box[w][5][3 + k], b6.mn[k] = s_box[w][6][k], b6.mx[k] = s_box[w][6][3 + k];
+                const A6 u5 = combine(lo, b5);
+                if (lane) s_cost[w][lane] = area(lo);  // intermediate value: raw surface area (:122)
+                s_cost[w][lane + 32] = area(u5);
+                s_cost[w][lane + 64] = area(combine(lo, b6));
+                s_cost[w][lane + 96] = area(combine(u5, b6));
             }
             __syncwarp();
             const float rootArea = s_cost[w][kSubsets - 1];  // the root box is the union of the seven leaves
             __syncwarp();
             if (lane < int(kFull)) s_cost[w][1u << lane] = div_(mul_(1.2f, myArea), rootArea);  // CalculateCost (:24-28)
             __syncwarp();
-            for (int size = 2; size <= int(kFull); ++size) {
+            // Subset DP.  The reference's partition loop (:153-164) visits p = deposit(i, delta) for i = 1 .. 2^(size-1)-1 in
+            // increasing i and keeps the first minimum, so a range of i can be given to each lane and the lanes merged
+            // with (cost, i) ordered lexicographically.  Sizes 2-5: one lane per subset; size 6: four lanes per subset
+            // (7 x 31 partitions); size 7: all lanes on the one subset (63 partitions).
+            const float *cost = s_cost[w];
+            auto finish = [&](uint32_t mask, int size, float lowest, uint32_t bestPart) {
+                const float raw = cost[mask];
+                const float asLeaf = mul_(mul_(1.0f, raw), float(size));  // COMBINE_LEAF_NODES = 1
+                const float asInternal = add_(mul_(1.2f, raw), lowest);
+                s_cost[w][mask] = fminf(asInternal, asLeaf);
+                s_part[w][mask] = uint8_t(bestPart | (asLeaf < asInternal ? 0x80u : 0u));
+            };
+            for (int size = 2; size <= 5; ++size) {
                 const int begin = kSizeBegin[size - 2], end = kSizeBegin[size - 1];
                 for (int j = begin + lane; j < end; j += 32) {
                     const uint32_t mask = kSubsetBySize[j];
@@ -192,18 +229,62 @@ __global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_
                     const uint32_t delta = (mask - 1) & mask;
                     uint32_t p = (0u - delta) & mask;
                     do {
-                        const float c = add_(s_cost[w][p], s_cost[w][mask ^ p]);
+                        const float c = add_(cost[p], cost[mask ^ p]);
                         if (c < lowest) lowest = c, bestPart = p;
                         p = (p - delta) & mask;
                     } while (p != 0);
-                    const float raw = s_cost[w][mask];
-                    const float asLeaf = mul_(mul_(1.0f, raw), float(size));  // COMBINE_LEAF_NODES = 1
-                    const float asInternal = add_(mul_(1.2f, raw), lowest);
-                    s_cost[w][mask] = fminf(asInternal, asLeaf);
-                    s_part[w][mask] = uint8_t(bestPart | (asLeaf < asInternal ? 0x80u : 0u));
+                    finish(mask, size, lowest, bestPart);
                 }
                 __syncwarp();
             }
+            auto deposit = [](uint32_t i, uint32_t delta) {  // bits of i into the set positions of delta, lowest first
+                uint32_t r = 0;
+                while (delta) {
+                    const uint32_t low = delta & (0u - delta);
+                    if (i & 1u) r |= low;
+                    i >>= 1, delta ^= low;
+                }
+                return r;
+            };
+            auto merge = [&](float &lowest, uint32_t &first, uint32_t &bestPart, int o) {
+                const float ol = __shfl_xor_sync(full, lowest, o);
+                const uint32_t of = __shfl_xor_sync(full, first, o), op = __shfl_xor_sync(full, bestPart, o);
+                if (ol < lowest || (ol == lowest && of < first)) lowest = ol, first = of, bestPart = op;
+            };
+            {  // size 6
+                const uint32_t mask = kSubsetBySize[kSizeBegin[4] + min(lane >> 2, 6)];
+                const uint32_t delta = (mask - 1) & mask;
+                const uint32_t i0 = 1 + 8 * (lane & 3), i1 = min(i0 + 8, 32u);
+                float lowest = FLT_MAX;
+                uint32_t bestPart = 0, first = 0xffffffffu;
+                uint32_t p = deposit(i0, delta);
+                if (lane < 28)
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        const float c = add_(cost[p], cost[mask ^ p]);
+                        if (c < lowest) lowest = c, bestPart = p, first = i;
+                        p = (p - delta) & mask;
+                    }
+                merge(lowest, first, bestPart, 1);
+                merge(lowest, first, bestPart, 2);
+                if (lane < 28 && (lane & 3) == 0) finish(mask, 6, lowest, bestPart);
+            }
+            __syncwarp();
+            {  // size 7: delta = 0b1111110, deposit(i) = i << 1
+                const uint32_t mask = kSubsets - 1, delta = mask - 1;
+                float lowest = FLT_MAX;
+                uint32_t bestPart = 0, first = 0xffffffffu;
+#pragma unroll
+                for (uint32_t i = 1 + 2 * lane; i < 3 + 2 * lane; ++i)
+                    if (i < 64) {
+                        const uint32_t p = (i << 1) & delta;
+                        const float c = add_(cost[p], cost[mask ^ p]);
+                        if (c < lowest) lowest = c, bestPart = p, first = i;
+                    }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) merge(lowest, first, bestPart, o);
+                if (lane == 0) finish(mask, 7, lowest, bestPart);
+            }
+            __syncwarp();
             // ---- ReformTree (:195-266): lane 0 walks the partition, six lanes store the six nodes
             if (lane == 0) {
                 uint32_t stackMask[kFull], stackNode[kFull];
@@ -250,20 +331,18 @@ __global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_
         __syncwarp();
         uint32_t next = 0xffffffffu;
         if (lane == 0 && node != 0) {
-            const uint32_t parent = __ldcg(hw + 3 * size_t(node)) & ~kCollapseBit;
-            const uint32_t ours = __ldcg(num_tris + node);
-            const uint32_t other = atomicAdd(&num_tris[parent], ours);
+            const uint32_t other = atomicAdd(&num_tris[up], ours);
             if (other != 0) {  // second to arrive: both subtrees are final
                 __threadfence();
-                const uint32_t l = __ldcg(hw + 3 * size_t(parent) + 1), r = __ldcg(hw + 3 * size_t(parent) + 2);
-                st_aabb(aabbs, parent, combine(ld_aabb(aabbs, l), ld_aabb(aabbs, r)));
+                st_aabb(aabbs, up, combine(rootBox, ld_aabb(aabbs, pl == node ? pr : pl)));
                 __threadfence();
-                next = parent;
+                next = up;
             }
         }
         next = __shfl_sync(full, next, 0);
         if (next == 0xffffffffu) return;
         node = next;
+        cl = __shfl_sync(full, pl, 0), cr = __shfl_sync(full, pr, 0);
     }
 }
 
