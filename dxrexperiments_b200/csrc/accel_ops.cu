@@ -86,7 +86,7 @@ int rt_as_get_info(rt_context *ctx, const void *as, rt_as_info *info) {
     info->count = e.count;
     info->top_level = e.top_level;
     info->build_flags = e.build_flags;
-    info->_pad = 0;
+    info->has_procedural = e.has_procedural;
     info->blob_bytes = off.totalSize;
     info->total_bytes = e.total_bytes;
     info->compacted_bytes = e.compacted_bytes;

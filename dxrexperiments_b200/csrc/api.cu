@@ -52,6 +52,7 @@ int rt_context_destroy(rt_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws.base) cudaFree(ctx->ws.base);
     if (ctx->status) cudaFree(ctx->status);
+    if (ctx->hit_programs) cudaFree(ctx->hit_programs);
     if (ctx->ray_counts) cudaFree(ctx->ray_counts);
     if (ctx->ev_ready)
         for (auto &e : ctx->ev) cudaEventDestroy(e);
@@ -80,9 +81,20 @@ int rt_get_status(rt_context *ctx) {
     uint32_t s = 0;
     RT_CUDA(cudaMemcpyAsync(&s, ctx->status, 4, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s & 2u) {
+        // not sticky: it describes the dispatches since the last check, not the context
+        const uint32_t cleared = s & ~2u;
+        RT_CUDA(cudaMemcpyAsync(ctx->status, &cleared, 4, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     if (s & 1u) {
         rt_set_error("traversal stack overflow: a ray needed more than 64 stack entries");
         return RT_ERR_OVERFLOW;
+    }
+    if (s & 2u) {
+        rt_set_error("the acceleration structure holds procedural primitives but the dispatch's hit groups are of type TRIANGLES "
+                     "(no intersection program): every ray was reported as a miss; use rt_trace_rays_hit_groups");
+        return RT_ERR_UNSUPPORTED;
     }
     return RT_OK;
 }

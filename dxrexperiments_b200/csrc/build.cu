@@ -90,7 +90,7 @@ __global__ void k_decode_aabb(const uint32_t *enc, float *out) {
 struct LoadGeom {
     const uint8_t *vb;
     const void *ib;
-    uint32_t stride, index_format, num_tris, prim_offset, geom_index, flags, has_xf;
+    uint32_t stride, index_format, num_tris, prim_offset, geom_index, flags, has_xf, procedural;
     float xf[12];
 };
 
@@ -100,6 +100,22 @@ struct LoadGeom {
 __global__ void __launch_bounds__(kThreads) k_load_triangles(LoadGeom g, rt_packed_tri *recs, uint32_t *aabb_enc) {
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < g.num_tris; t += gridDim.x * blockDim.x) {
+        if (g.procedural) {
+            // FL/LoadProceduralGeometry.hlsl:16-42: the AABB is copied verbatim; scene AABB from min and max
+            // (CalculateSceneAABBFromPrimitives.hlsl:32-37)
+            const float *p = reinterpret_cast<const float *>(g.vb + size_t(t) * g.stride);
+            const float b[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = fminf(fminf(mn[k], b[k]), b[3 + k]);
+                mx[k] = fmaxf(fmaxf(mx[k], b[k]), b[3 + k]);
+            }
+            float4 *dst = reinterpret_cast<float4 *>(recs + g.prim_offset + t);
+            dst[0] = make_float4(b[0], b[1], b[2], b[3]);
+            dst[1] = make_float4(b[4], b[5], 0.0f, 0.0f);
+            dst[2] = make_float4(0.0f, __uint_as_float(t), __uint_as_float(g.geom_index), __uint_as_float(g.flags | RT_PACKED_PROCEDURAL));
+            continue;
+        }
         uint32_t idx[3];
         if (g.index_format == 32) {
             const uint32_t *ib = static_cast<const uint32_t *>(g.ib);
@@ -156,8 +172,10 @@ __global__ void __launch_bounds__(kThreads) k_morton_prims(const rt_packed_tri *
     const float4 *q = reinterpret_cast<const float4 *>(recs + i);
     const float4 q0 = q[0], q1 = q[1], q2 = q[2];
     const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
-    // (v0 + v1 + v2) / 3.0  (CalculateMortonCodesForPrimitives.hlsl:22-25)
-    f3 c = mk3(((v[0] + v[3]) + v[6]) / 3.0f, ((v[1] + v[4]) + v[7]) / 3.0f, ((v[2] + v[5]) + v[8]) / 3.0f);
+    // (v0 + v1 + v2) / 3.0  (CalculateMortonCodesForPrimitives.hlsl:22-25); procedural: (min + max) / 2.0 (:26-30)
+    f3 c = (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL)
+               ? mk3((v[0] + v[3]) / 2.0f, (v[1] + v[4]) / 2.0f, (v[2] + v[5]) / 2.0f)
+               : mk3(((v[0] + v[3]) + v[6]) / 3.0f, ((v[1] + v[4]) + v[7]) / 3.0f, ((v[2] + v[5]) + v[8]) / 3.0f);
     codes[i] = morton_from_centroid(c, aabb);
 }
 
@@ -366,10 +384,10 @@ __global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_packed_tri
     const uint4 *q = reinterpret_cast<const uint4 *>(recs + src);
     const uint4 q0 = __ldcs(q), q1 = __ldcs(q + 1), q2 = __ldcs(q + 2);  // each record is read exactly once
     uint32_t *d = reinterpret_cast<uint32_t *>(out_prims + dst);
-    d[0] = 1;  // TRIANGLE_TYPE
+    d[0] = (q2.w & RT_PACKED_PROCEDURAL) ? RT_PRIMITIVE_TYPE_PROCEDURAL : RT_PRIMITIVE_TYPE_TRIANGLE;
     d[1] = q0.x, d[2] = q0.y, d[3] = q0.z, d[4] = q0.w, d[5] = q1.x, d[6] = q1.y, d[7] = q1.z, d[8] = q1.w, d[9] = q2.x;
     uint32_t *m = reinterpret_cast<uint32_t *>(out_meta + dst);
-    m[0] = q2.z, m[1] = q2.y, m[2] = q2.w;  // {geometryContributionToHitGroupIndex, primitiveIndex, geometryFlags}
+    m[0] = q2.z, m[1] = q2.y, m[2] = q2.w & ~RT_PACKED_PROCEDURAL;  // {geometryContributionToHitGroupIndex, primitiveIndex, geometryFlags}
     uint4 *p = reinterpret_cast<uint4 *>(packed + dst);
     p[0] = q0, p[1] = q1, p[2] = q2;
 }
@@ -419,6 +437,7 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
     const uint32_t nInternal = n - 1;
     uint32_t node = nInternal + slot;
     Box box;
+    uint32_t leafFlags = slot | RT_NODE_LEAF_FLAG;
     if (TOP) {
         const rt_aabb_node &s = inst_boxes[perm[slot]];
         box.c[0] = s.center[0], box.c[1] = s.center[1], box.c[2] = s.center[2];
@@ -426,15 +445,22 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
     } else {
         const float *v = sorted_prims[slot].v;
         float mn[3], mx[3];
+        if (*reinterpret_cast<const uint32_t *>(sorted_prims + slot) == RT_PRIMITIVE_TYPE_PROCEDURAL) {
+            // ComputeLeafAABB, procedural branch (FL/BottomLevelComputeAABBs.hlsl:32-40): the AABB as given, flagged
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            mn[k] = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
-            mx[k] = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
-            mn[k] = fminf(mn[k], mx[k] - 0.001f);  // AABB_Min_Padding
+            for (int k = 0; k < 3; ++k) mn[k] = v[k], mx[k] = v[3 + k];
+            leafFlags |= RT_NODE_PROCEDURAL_FLAG;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
+                mx[k] = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
+                mn[k] = fminf(mn[k], mx[k] - 0.001f);  // AABB_Min_Padding
+            }
         }
         box = aabb_to_box(mn, mx);
     }
-    store_node(nodes, node, box, slot | RT_NODE_LEAF_FLAG, 1u);
+    store_node(nodes, node, box, leafFlags, 1u);
     if (n == 1) {
         ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
         ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
@@ -562,7 +588,8 @@ __global__ void k_write_headers(uint8_t *result, rt_bvh_offsets off, rt_ext_head
         e->off_wide = ext.off_wide, e->off_leaf = ext.off_leaf, e->off_wide4 = ext.off_wide4;
         e->off_sort_cache = ext.off_sort_cache, e->off_parents = ext.off_parents, e->build_flags = ext.build_flags;
         e->total_bytes = ext.total_bytes, e->compacted_bytes = ext.compacted_bytes;
-        e->_pad0 = e->_pad1 = e->_pad3 = 0;
+        e->has_procedural = ext.has_procedural;
+        e->_pad0 = e->_pad1 = 0;
         e->_pad2[0] = e->_pad2[1] = 0;
         if (ext.count == 0) {
             // empty TLAS: node 0 is a zero box with zero flags (FL/TopLevelPrepareForComputeAABBs.hlsl:40-48)
@@ -601,12 +628,16 @@ __device__ void invert_affine(const float *t, float *o) {
 
 // FL/TopLevelLoadAABBs.hlsli:58-100 fused with FL/CalculateSceneAABBFromBVHs.hlsl:16-40.
 __global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_desc *descs, uint32_t n, rt_aabb_node *boxes,
-                                                             rt_bvh_metadata *md, uint32_t *aabb_enc) {
+                                                             rt_bvh_metadata *md, uint32_t *aabb_enc, rt_ext_header *tlas_ext) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float smn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, smx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     if (i < n) {
         rt_instance_desc d = descs[i];
-        const rt_aabb_node *root = reinterpret_cast<const rt_aabb_node *>(reinterpret_cast<const uint8_t *>(uintptr_t(d.blas)) + 16);
+        const uint8_t *blas = reinterpret_cast<const uint8_t *>(uintptr_t(d.blas));
+        const rt_aabb_node *root = reinterpret_cast<const rt_aabb_node *>(blas + 16);
+        // a TLAS over a BLAS with procedural primitives needs hit groups with intersection programs (rt_trace_rays_hit_groups)
+        const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(reinterpret_cast<const rt_bvh_offsets *>(blas)->totalSize, 64));
+        if (be->has_procedural) atomicOr(&tlas_ext->has_procedural, 1u);
         float bmn[3], bmx[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {  // BoundingBoxToAABB
@@ -809,10 +840,14 @@ int rt_build_scratch_layout(uint32_t n, int top_level, rt_scratch_layout *out) {
     return RT_OK;
 }
 
+static inline bool is_procedural(const rt_geometry_desc &d) { return d.type == RT_GEOMETRY_TYPE_PROCEDURAL_AABBS; }
+static inline uint32_t geom_prims(const rt_geometry_desc &d) {  // FL/LoadPrimitivesPass.cpp:87-88,136
+    return is_procedural(d) ? d.vertex_count : (d.index_format == 0 ? d.vertex_count : d.index_count) / 3;
+}
 static uint32_t count_prims(const rt_geometry_desc *geoms, uint32_t n_geoms) {
     uint64_t n = 0;
-    for (uint32_t g = 0; g < n_geoms; ++g) n += (geoms[g].index_format == 0 ? geoms[g].vertex_count : geoms[g].index_count) / 3;
-    return uint32_t(n);
+    for (uint32_t g = 0; g < n_geoms; ++g) n += geom_prims(geoms[g]);
+    return uint32_t(std::min<uint64_t>(n, 0xffffffffull));
 }
 
 static inline bool allows_update(uint32_t f) { return (f & RT_BUILD_FLAG_ALLOW_UPDATE) != 0; }
@@ -947,8 +982,10 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
     return RT_OK;
 }
 
-static int write_headers(rt_context *ctx, uint32_t n, bool top, uint32_t flags, uint8_t *result, const ResultLayout &R) {
+static int write_headers(rt_context *ctx, uint32_t n, bool top, uint32_t flags, uint8_t *result, const ResultLayout &R,
+                         bool has_procedural = false) {
     rt_ext_header e{};
+    e.has_procedural = has_procedural ? 1u : 0u;
     e.magic = RT_EXT_MAGIC;
     e.count = n;
     e.root_ref = (n == 1) ? RT_NODE_LEAF_FLAG : 0u;
@@ -985,7 +1022,13 @@ int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geo
     RT_CUDA(cudaSetDevice(ctx->device));
     uint8_t *scratch = static_cast<uint8_t *>(scratch_), *result = static_cast<uint8_t *>(result_);
     cudaStream_t st = ctx->stream;
-    int rc = performs_update(build_flags) ? check_updatable(ctx, result, R, n, false) : write_headers(ctx, n, false, build_flags, result, R);
+    bool any_procedural = false;
+    for (uint32_t g = 0; g < n_geoms; ++g) {
+        RT_REQUIRE(geoms[g].type == RT_GEOMETRY_TYPE_TRIANGLES || is_procedural(geoms[g]), "unrecognized geometry type");  // LoadPrimitivesPass.cpp:124-127
+        any_procedural |= is_procedural(geoms[g]);
+    }
+    int rc = performs_update(build_flags) ? check_updatable(ctx, result, R, n, false)
+                                          : write_headers(ctx, n, false, build_flags, result, R, any_procedural);
     if (rc) return rc;
     uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
     k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
@@ -998,15 +1041,21 @@ int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geo
         lg.ib = d.index_buffer;
         lg.stride = d.vertex_stride_bytes;
         lg.index_format = d.index_format;
-        lg.num_tris = (d.index_format == 0 ? d.vertex_count : d.index_count) / 3;
-        RT_REQUIRE(d.vertex_buffer != nullptr || lg.num_tris == 0, "null vertex buffer");
-        RT_REQUIRE(d.index_format == 0 || d.index_format == 16 || d.index_format == 32, "index_format must be 0, 16 or 32");
-        RT_REQUIRE(d.index_format == 0 || d.index_buffer != nullptr, "null index buffer");
-        RT_REQUIRE(d.vertex_stride_bytes >= 12 && d.vertex_stride_bytes % 4 == 0, "vertex stride");
+        lg.num_tris = geom_prims(d);
+        lg.procedural = is_procedural(d);
+        RT_REQUIRE(d.vertex_buffer != nullptr || lg.num_tris == 0,
+                   lg.procedural ? "non-zero AABBCount provided with a null AABB buffer" : "null vertex buffer");  // LoadPrimitivesPass.cpp:130-133
+        if (lg.procedural) {
+            RT_REQUIRE(d.vertex_stride_bytes >= 24 && d.vertex_stride_bytes % 4 == 0, "AABB stride");
+        } else {
+            RT_REQUIRE(d.index_format == 0 || d.index_format == 16 || d.index_format == 32, "index_format must be 0, 16 or 32");
+            RT_REQUIRE(d.index_format == 0 || d.index_buffer != nullptr, "null index buffer");
+            RT_REQUIRE(d.vertex_stride_bytes >= 12 && d.vertex_stride_bytes % 4 == 0, "vertex stride");
+        }
         lg.prim_offset = offset;
         lg.geom_index = g;
         lg.flags = d.flags;
-        lg.has_xf = d.transform3x4 != nullptr;
+        lg.has_xf = !lg.procedural && d.transform3x4 != nullptr;
         if (lg.has_xf) {
             RT_CUDA(cudaMemcpyAsync(lg.xf, d.transform3x4, 48, cudaMemcpyDefault, st));
             RT_CUDA(cudaStreamSynchronize(st));
@@ -1044,7 +1093,8 @@ int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, ui
     uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
     k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
     k_load_instances<<<rt_div_up(n, kThreads), kThreads, 0, st>>>(descs, n, reinterpret_cast<rt_aabb_node *>(scratch + L.elems),
-                                                                 reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), aabb_enc);
+                                                                 reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), aabb_enc,
+                                                                 reinterpret_cast<rt_ext_header *>(result + R.ext));
     ctx->launches += 2;
     RT_LAUNCH_CHECK();
     return build_common(ctx, n, true, build_flags, scratch, result, L, R);

@@ -61,7 +61,8 @@ struct rt_context {
     const void *tlas = nullptr;
 
     rt_workspace ws;
-    uint32_t *status = nullptr;          // device word: bit0 = traversal stack overflow
+    uint32_t *status = nullptr;          // device word: bit0 = traversal stack overflow, bit1 = procedural primitives reached by a triangles-only dispatch
+    rt_hit_group_programs *hit_programs = nullptr;  // device copy of the table rt_trace_rays_hit_groups was last given
     unsigned long long *ray_counts = nullptr;  // device u64[32]: [0..2] rays traced; [8..12], [16..20], [24..28] rt_trace_stats of the primary / secondary / shadow stages
     // stage timing (optional)
     bool timing = false;
@@ -112,7 +113,7 @@ struct rt_ext_header {  // 128 bytes, located at align64(reference blob size)
     uint64_t off_sort_cache;  // count x u32: load-order element -> sorted slot (RearrangeTriangles.hlsl:25-28)
     uint64_t off_parents;     // (2*count-1) x u32: parent of every node (ComputeAABBs.hlsli:160-164)
     uint32_t build_flags;     // RT_BUILD_FLAG_* of the build that produced this buffer
-    uint32_t _pad3;
+    uint32_t has_procedural;  // BLAS: built from >= 1 procedural-AABB geometry; TLAS: some instance's BLAS was
     uint64_t total_bytes;      // bytes of the result buffer in use (what rt_*_prebuild reported as result_bytes)
     uint64_t compacted_bytes;  // bytes a COMPACT copy needs: total_bytes minus the two update caches
     uint64_t _pad2[2];
@@ -158,6 +159,10 @@ struct __align__(16) rt_packed_tri {
     uint32_t geometry_flags;
 };
 static_assert(sizeof(rt_packed_tri) == 48, "packed tri");
+// A procedural primitive travels in the same 48-byte record: v[0..5] = AABB min, max, v[6..8] = 0, and this bit in
+// geometry_flags (never a D3D12 geometry flag); the reference-format Primitive / PrimitiveMetaData carry type 2 and
+// the plain flags.
+#define RT_PACKED_PROCEDURAL 0x80000000u
 
 // Packed instance (TLAS leaf): world->object 3x4, ids, and the BLAS traversal pointers. 96 B.
 struct __align__(16) rt_packed_instance {

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kBlock, RT_PRIMARY_MIN_BLOCKS) k_primary(const
         const uint32_t x = L.x0 + lx, y = L.y0 + ly;
         f3 o, d;
         primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
-        TraceAccel A = resolve_tlas(tlas);
+        TraceAccel A = resolve_tlas(tlas, status);
         TraceHit h;
         if (STATS || !RT_PRIMARY_WIDE4)  // instrumented: BVH2 in the reference's visit order
             trace_ray<false, STATS>(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, 0, h,
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const 
                                                         uint32_t plane, float4 *hitA, uint32_t *hitRec, uint8_t *vis, uint32_t *status,
                                                         unsigned long long *stats) {
     const uint32_t cnt = count[0], n = cnt * mult;
-    TraceAccel A = resolve_tlas(tlas);
+    TraceAccel A = resolve_tlas(tlas, status);
     TraceCtr ctr{0, 0, 0, 0};
     uint32_t traced = 0;
     for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
@@ -504,10 +504,30 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Laun
 }
 
 // ------------------------------------------------------------------------------------------------ standalone kernels
+// Traversal with the hit groups' any-hit / intersection programs and procedural primitives: one thread
+// per ray over the BVH2 wide nodes in the reference's visit order, so every candidate reaches the programs in the
+// order the reference's traversal would present it.
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock) k_trace_rays_hit_groups(const void *tlas, const rt_ray *rays, uint64_t n, uint32_t rayFlags,
+                                                                  uint32_t mask, uint32_t rayContribution, uint32_t geomMultiplier,
+                                                                  HitPrograms programs, rt_hit *hits, uint32_t *status) {
+    const TraceAccel A = resolve_tlas(tlas);
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
+        const float4 a = rp[0], b = rp[1];
+        TraceHit h;
+        trace_ray<ANY, false, true>(A, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, rayFlags, mask, rayContribution, geomMultiplier, h, nullptr,
+                                    status, programs);
+        uint4 *hp = reinterpret_cast<uint4 *>(hits + i);
+        hp[0] = make_uint4(__float_as_uint(h.t), __float_as_uint(h.u), __float_as_uint(h.v), h.prim);
+        hp[1] = make_uint4(h.inst_index, h.geom_index, h.inst_id, h.leaf_slot);
+    }
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(kBlock) k_trace_rays(const void *tlas, const rt_ray *rays, uint64_t n, uint32_t rayFlags, uint32_t mask,
                                                        rt_hit *hits, unsigned long long *stats, uint32_t *status) {
-    TraceAccel A = resolve_tlas(tlas);
+    TraceAccel A = resolve_tlas(tlas, status);
     TraceCtr c{0, 0, 0, 0};
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + i);
@@ -703,6 +723,35 @@ static int trace_common(rt_context *ctx, const void *tlas, const rt_ray *rays, u
             done += chunk;
         }
     }
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+int rt_trace_rays_hit_groups(rt_context *ctx, const void *tlas, const rt_ray *rays, uint64_t n, uint32_t flags, uint32_t mask,
+                             uint32_t ray_contribution, uint32_t geometry_multiplier, const rt_hit_group_programs *programs,
+                             uint32_t n_programs, rt_hit *hits) {
+    RT_REQUIRE(ctx && tlas && (n == 0 || (rays && hits)), "null argument");
+    RT_REQUIRE(n_programs == 0 || programs != nullptr, "null hit-group program table");
+    RT_REQUIRE(n_programs <= 4096, "more than 4096 hit-group records");
+    for (uint32_t i = 0; i < n_programs; ++i) {
+        // an unknown shader identifier is a std::logic_error in RtBindings (libs/DXRFramework/RtBindings.cpp:77-79)
+        RT_REQUIRE(programs[i].any_hit < RT_ANYHIT_COUNT, "unknown any-hit program");
+        RT_REQUIRE(programs[i].intersection < RT_INTERSECTION_COUNT, "unknown intersection program");
+    }
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) return RT_OK;
+    if (n_programs) {
+        if (!ctx->hit_programs) RT_CUDA(cudaMalloc(&ctx->hit_programs, 4096 * sizeof(rt_hit_group_programs)));
+        // stream-ordered copy of a pageable host table: staged by the runtime before the call returns
+        RT_CUDA(cudaMemcpyAsync(ctx->hit_programs, programs, n_programs * sizeof(rt_hit_group_programs), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const HitPrograms hp{n_programs ? ctx->hit_programs : nullptr, n_programs};
+    const int grid = int(std::min<uint64_t>(rt_div_up(n, kBlock), uint64_t(ctx->num_sms) * 16));
+    if (flags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH)
+        k_trace_rays_hit_groups<true><<<grid, kBlock, 0, ctx->stream>>>(tlas, rays, n, flags, mask, ray_contribution, geometry_multiplier, hp, hits, ctx->status);
+    else
+        k_trace_rays_hit_groups<false><<<grid, kBlock, 0, ctx->stream>>>(tlas, rays, n, flags, mask, ray_contribution, geometry_multiplier, hp, hits, ctx->status);
+    ctx->launches++;
     RT_LAUNCH_CHECK();
     return RT_OK;
 }

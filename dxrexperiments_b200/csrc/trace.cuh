@@ -154,7 +154,10 @@ __device__ __forceinline__ bool ray_triangle(float &hitT, float &bu, float &bv, 
     return true;
 }
 
-__device__ __forceinline__ TraceAccel resolve_tlas(const void *tlas_result) {
+// `status` != nullptr: the caller's kernels know triangles only (hit groups of type TRIANGLES).  A TLAS that reaches
+// procedural primitives is then a hit-group type mismatch: status bit 1 is raised (rt_get_status -> RT_ERR_UNSUPPORTED)
+// and every ray misses.  rt_trace_rays_hit_groups is the entry point that runs intersection programs.
+__device__ __forceinline__ TraceAccel resolve_tlas(const void *tlas_result, uint32_t *status = nullptr) {
     const uint8_t *base = static_cast<const uint8_t *>(tlas_result);
     const rt_bvh_offsets *off = reinterpret_cast<const rt_bvh_offsets *>(base);
     const rt_ext_header *e = reinterpret_cast<const rt_ext_header *>(base + align_up(off->totalSize, 64));
@@ -164,6 +167,10 @@ __device__ __forceinline__ TraceAccel resolve_tlas(const void *tlas_result) {
     a.inst = reinterpret_cast<const rt_packed_instance *>(base + e->off_leaf);
     a.root_ref = e->root_ref;
     a.count = e->count;
+    if (status != nullptr && e->has_procedural) {
+        if (threadIdx.x == 0) atomicOr(status, 2u);
+        a.count = 0;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) a.root_c[k] = e->root_center[k], a.root_h[k] = e->root_half[k];
     return a;
@@ -347,10 +354,88 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
 
 // Fallback_TraceRay without shader call-outs.  ANY = RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH.
 // rayContribution / geomMultiplier feed the hit-group record index exactly as TraverseFunction.hlsli:684-687.
-template <bool ANY, bool STATS>
+// ---------------------------------------------------------------------------------------------------------------
+// Compiled-in any-hit / intersection programs (rt_types.h RT_ANYHIT_*, RT_INTERSECTION_*) and the machinery the
+// reference runs around application shaders: InvokeAnyHit / IgnoreHit / AcceptHitAndEndSearch
+// (FL/TraverseFunction.hlsli:102-117) and Fallback_ReportHit (:136-158).  Same arithmetic, operation for operation,
+// as the CPU restatement the parity tests check it against (the library is built with -fmad=false).
+struct HitPrograms {
+    const rt_hit_group_programs *table;  // one entry per hit-group record; nullptr = no any-hit / intersection programs
+    uint32_t count;
+};
+#define RT_AH_END_SEARCH (-1)
+#define RT_AH_IGNORE 0
+#define RT_AH_ACCEPT 1
+
+__device__ __forceinline__ int run_any_hit(uint32_t program, float ax, float ay) {
+    switch (program) {
+        case RT_ANYHIT_IGNORE: return RT_AH_IGNORE;
+        case RT_ANYHIT_END_SEARCH: return RT_AH_END_SEARCH;
+        case RT_ANYHIT_CUTOUT: return ((int(floorf(8.0f * ax)) + int(floorf(8.0f * ay))) & 1) ? RT_AH_IGNORE : RT_AH_ACCEPT;
+        default: return RT_AH_ACCEPT;
+    }
+}
+
+struct ReportCtx {
+    float tmin, tCur;
+    uint32_t rayFlags, anyHit;
+    int anyHitResult;
+    bool committed;
+    float t, ax, ay;
+    uint32_t kind;
+};
+
+__device__ __forceinline__ int report_hit(ReportCtx &c, float tHit, uint32_t hitKind, float ax, float ay) {
+    if (tHit < c.tmin || c.tCur <= tHit) return 0;
+    int ret = RT_AH_ACCEPT;
+    bool opaque = true;  // "geomOpaque = true; // TODO" and instance flags 0 in the reference (:147-149)
+    if (c.rayFlags & RT_RAY_FLAG_FORCE_OPAQUE) opaque = true;
+    else if (c.rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
+    if (c.anyHit > 0 && !opaque) ret = c.anyHitResult = run_any_hit(c.anyHit, ax, ay);
+    if (ret != RT_AH_IGNORE) {
+        c.tCur = tHit;
+        c.committed = true;
+        c.t = tHit, c.ax = ax, c.ay = ay, c.kind = hitKind;
+        if (c.rayFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) ret = RT_AH_END_SEARCH;
+    }
+    return ret;
+}
+
+__device__ __forceinline__ float dot3_(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+
+__device__ __forceinline__ void intersect_box(ReportCtx &c, f3 o, f3 d, f3 mn, f3 mx) {
+    const f3 t0 = mk3((mn.x - o.x) / d.x, (mn.y - o.y) / d.y, (mn.z - o.z) / d.z);
+    const f3 t1 = mk3((mx.x - o.x) / d.x, (mx.y - o.y) / d.y, (mx.z - o.z) / d.z);
+    const float tNear = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+    const float tFar = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+    if (!(tNear <= tFar)) return;
+    if (report_hit(c, tNear, RT_HIT_KIND_BOX_ENTER, 0.0f, 0.0f) == 0) report_hit(c, tFar, RT_HIT_KIND_BOX_EXIT, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ void intersect_sphere(ReportCtx &c, f3 o, f3 d, f3 mn, f3 mx) {
+    const f3 ctr = mk3((mn.x + mx.x) * 0.5f, (mn.y + mx.y) * 0.5f, (mn.z + mx.z) * 0.5f);
+    const f3 h = mk3(mx.x - ctr.x, mx.y - ctr.y, mx.z - ctr.z);
+    const float r = fminf(fminf(h.x, h.y), h.z);
+    if (!(r > 0.0f)) return;
+    const f3 oc = mk3(o.x - ctr.x, o.y - ctr.y, o.z - ctr.z);
+    const float a = dot3_(d, d), b = dot3_(oc, d), cc = dot3_(oc, oc) - r * r;
+    const float disc = b * b - a * cc;
+    if (!(disc >= 0.0f) || !(a > 0.0f)) return;
+    const float s = sqrtf(disc);
+    const float tA = (-b - s) / a, tB = (-b + s) / a;
+    const float nAx = (oc.x + d.x * tA) / r, nAy = (oc.y + d.y * tA) / r;
+    const float nBx = (oc.x + d.x * tB) / r, nBy = (oc.y + d.y * tB) / r;
+    if (report_hit(c, tA, RT_HIT_KIND_SPHERE_ENTER, nAx, nAy) == 0) report_hit(c, tB, RT_HIT_KIND_SPHERE_EXIT, nBx, nBy);
+}
+
+// HOOKS = true: hit groups may carry any-hit / intersection programs and the BLAS may hold procedural primitives
+// (rt_trace_rays_hit_groups); hit.leaf_slot then carries HitKind() in bits 31:24.  HOOKS = false is the application's
+// case — all-triangle geometry and, at most, a no-op any-hit shader — and compiles to exactly the loop it was.
+template <bool ANY, bool STATS, bool HOOKS = false>
 __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float oy, float oz, float tmin, float dx, float dy,
                                           float dz, float tmax, uint32_t rayFlags, uint32_t mask, uint32_t rayContribution,
-                                          uint32_t geomMultiplier, TraceHit &hit, TraceCtr *ctr, uint32_t *status) {
+                                          uint32_t geomMultiplier, TraceHit &hit, TraceCtr *ctr, uint32_t *status,
+                                          HitPrograms programs = HitPrograms{nullptr, 0}) {
     hit.prim = RT_NO_HIT;
     hit.t = tmax;
     hit.u = hit.v = 0.0f;
@@ -369,6 +454,7 @@ __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float o
     int blasBase = -1;  // stack height at which the current BLAS was entered
     uint32_t instIndex = 0, instFlags = 0, instOffset = 0, instId = 0;
     int cull = 0;
+    f3 objO = mk3(ox, oy, oz), objD = mk3(dx, dy, dz);  // ObjectRayOrigin() / ObjectRayDirection() (HOOKS only)
 
     float tUnused;
     if (!ray_box(tUnused, tCur, world, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2])) return false;
@@ -404,6 +490,7 @@ __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float o
                     f3 o2 = xform_point(m, mk3(ox, oy, oz));
                     f3 d2 = xform_vector(m, mk3(dx, dy, dz));
                     cur = make_ray_pre<!STATS>(o2.x, o2.y, o2.z, d2.x, d2.y, d2.z);
+                    if (HOOKS) objO = o2, objD = d2;
                     nodes = reinterpret_cast<const rt_wide_node *>(uintptr_t(uint64_t(m4.x) | (uint64_t(m4.y) << 32)));
                     tris = reinterpret_cast<const rt_packed_tri *>(uintptr_t(uint64_t(m4.z) | (uint64_t(m4.w) << 32)));
                     bottom = true;
@@ -423,7 +510,45 @@ __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float o
                 else if (rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
                 const bool culled = (opaque && (rayFlags & RT_RAY_FLAG_CULL_OPAQUE)) || (!opaque && (rayFlags & RT_RAY_FLAG_CULL_NON_OPAQUE));
                 ref = RT_SENTINEL;
-                if (!culled) {
+                if (HOOKS) {
+                    const uint32_t geomIndex = __float_as_uint(p2.z);
+                    const uint32_t record = rayContribution + geomIndex * geomMultiplier + instOffset;
+                    rt_hit_group_programs prog{RT_ANYHIT_NONE, RT_INTERSECTION_NONE};
+                    if (programs.table != nullptr && record < programs.count) prog = programs.table[record];
+                    bool endSearch = false, commit = false;
+                    float ct = 0.0f, cu = 0.0f, cv = 0.0f;
+                    uint32_t kind = 0;
+                    if (!culled && (gflags & RT_PACKED_PROCEDURAL)) {
+                        // :656-671
+                        ReportCtx rc{tmin, tCur, rayFlags, prog.any_hit, RT_AH_ACCEPT, false, 0.0f, 0.0f, 0.0f, 0u};
+                        if (prog.intersection == RT_INTERSECTION_BOX)
+                            intersect_box(rc, objO, objD, mk3(p0.x, p0.y, p0.z), mk3(p0.w, p1.x, p1.y));
+                        else if (prog.intersection == RT_INTERSECTION_SPHERE)
+                            intersect_sphere(rc, objO, objD, mk3(p0.x, p0.y, p0.z), mk3(p0.w, p1.x, p1.y));
+                        commit = rc.committed, ct = rc.t, cu = rc.ax, cv = rc.ay, kind = rc.kind;
+                        endSearch = rc.anyHitResult == RT_AH_END_SEARCH;
+                    } else if (!culled) {
+                        float t0 = tCur, bu, bv;
+                        if (ray_triangle(t0, bu, bv, cull, cur, p0, p1, p2.x) && t0 < tCur && t0 > tmin) {
+                            // :699-722 (under ACCEPT_FIRST_HIT an ignored candidate still ends the search, :721)
+                            int ret = RT_AH_ACCEPT;
+                            if (!opaque && prog.any_hit) ret = run_any_hit(prog.any_hit, bu, bv);
+                            commit = ret != RT_AH_IGNORE, ct = t0, cu = bu, cv = bv, kind = RT_HIT_KIND_TRIANGLE_FRONT_FACE;
+                            endSearch = ret == RT_AH_END_SEARCH || ANY;
+                        }
+                    }
+                    if (commit) {
+                        tCur = ct;
+                        hit.t = ct, hit.u = cu, hit.v = cv;
+                        hit.prim = __float_as_uint(p2.y);
+                        hit.geom_index = geomIndex;
+                        hit.inst_index = instIndex;
+                        hit.inst_id = instId;
+                        hit.leaf_slot = slot | (kind << 24);
+                        hit.record = record;
+                    }
+                    if (endSearch) return hit.prim != RT_NO_HIT;
+                } else if (!culled) {
                     float t0 = tCur, bu, bv;
                     if (ray_triangle(t0, bu, bv, cull, cur, p0, p1, p2.x) && t0 < tCur && t0 > tmin) {
                         tCur = t0;
@@ -464,6 +589,7 @@ __device__ __forceinline__ bool trace_ray(const TraceAccel &A, float ox, float o
             if (bottom && sp == blasBase) {
                 bottom = false;
                 cur = world;
+                if (HOOKS) objO = mk3(ox, oy, oz), objD = mk3(dx, dy, dz);
                 nodes = A.wide;
                 blasBase = -1;
             }

@@ -61,7 +61,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
     // Rays are drawn kind-major, so a warp holds one kind.  Standalone launches pass the ray count in `mult`.
     const uint32_t cnt = count ? count[0] : 0u;
     const uint32_t n = count ? cnt * mult : mult;
-    const TraceAccel A = resolve_tlas(tlas);
+    const TraceAccel A = resolve_tlas(tlas, status);
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     constexpr unsigned FULL = 0xffffffffu;

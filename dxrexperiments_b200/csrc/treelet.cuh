@@ -74,13 +74,19 @@ __global__ void __launch_bounds__(256) k_find_treelets(uint32_t n, const rt_hier
         const float4 *q = reinterpret_cast<const float4 *>(tris + slot);
         const float4 q0 = q[0], q1 = q[1], q2 = q[2];
         const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+        if (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL) {
+            // GetProceduralPrimitiveAABB: the AABB as given, no box round trip (FindTreelets.hlsl:25-28)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float mn = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
-            const float mx = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
-            mn = fminf(mn, sub_(mx, 0.001f));  // AABB_Min_Padding
-            const float c = mul_(add_(mn, mx), 0.5f), h = sub_(mx, c);
-            a.mn[k] = sub_(c, h), a.mx[k] = add_(c, h);
+            for (int k = 0; k < 3; ++k) a.mn[k] = v[k], a.mx[k] = v[3 + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float mn = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
+                const float mx = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
+                mn = fminf(mn, sub_(mx, 0.001f));  // AABB_Min_Padding
+                const float c = mul_(add_(mn, mx), 0.5f), h = sub_(mx, c);
+                a.mn[k] = sub_(c, h), a.mx[k] = add_(c, h);
+            }
         }
     }
     uint32_t count = 1;

@@ -84,6 +84,7 @@ def _load():
         "rt_denoise": (i32, [vp, vp, vp, vp, vp, u32, u32, vp]),
         "rt_trace_rays": (i32, [vp, vp, vp, u64, u32, u32, vp]),
         "rt_trace_rays_stats": (i32, [vp, vp, vp, u64, u32, u32, vp, vp]),
+        "rt_trace_rays_hit_groups": (i32, [vp, vp, vp, u64, u32, u32, u32, u32, vp, u32, vp]),
         "rt_generate_primary_rays": (i32, [vp, vp, u32, u32, C.c_float, vp]),
         "rt_scale_buffer": (i32, [vp, vp, u64, C.c_float]),
     }
@@ -190,7 +191,8 @@ class Context:
         result = self.alloc(info.result_bytes)
         check(lib.rt_blas_build(self.handle, descs, len(geoms), build_flags, scratch.ptr, scratch.nbytes, result.ptr,
                                 result.nbytes))
-        n = sum((g.get("index_count", 0) if g.get("index_format", 32 if g.get("indices") is not None else 0) else
+        n = sum(g["aabb_count"] if "aabbs" in g else
+                (g.get("index_count", 0) if g.get("index_format", 32 if g.get("indices") is not None else 0) else
                  g["vertex_count"]) // 3 for g in geoms)
         acc = Accel(self, result, n, top=False, scratch=scratch if keep_scratch else None, keep=list(geoms),
                     build_flags=build_flags)
@@ -279,6 +281,20 @@ class Context:
         self.status()
         return (hits, st) if stats else hits
 
+    def trace_hit_groups(self, tlas, rays: np.ndarray, programs, ray_flags: int = 0, mask: int = 0xFF,
+                         ray_contribution: int = 0, geometry_multiplier: int = 0):
+        """Traversal with any-hit / intersection programs; programs: (R, 2) uint32 {any_hit, intersection}."""
+        rays = np.ascontiguousarray(rays, dtype=T.RAY_DTYPE)
+        n = rays.shape[0]
+        progs = np.ascontiguousarray(programs, np.uint32).reshape(-1, 2)
+        d_rays = self.upload(rays.view(np.uint8).reshape(-1))
+        d_hits = self.alloc(max(32 * n, 32))
+        check(lib.rt_trace_rays_hit_groups(self.handle, tlas.result.ptr, d_rays.ptr, n, ray_flags, mask, ray_contribution,
+                                           geometry_multiplier, progs.ctypes.data, progs.shape[0], d_hits.ptr))
+        hits = d_hits.download(T.HIT_DTYPE, n)
+        self.status()
+        return hits
+
     def primary_rays(self, frame, width, height, jitter_scale=30.0) -> np.ndarray:
         d = self.alloc(32 * width * height)
         check(lib.rt_generate_primary_rays(self.handle, C.byref(frame), width, height, jitter_scale, d.ptr))
@@ -322,6 +338,13 @@ class Context:
 def _geometry_descs(geoms):
     descs = (T.GeometryDesc * len(geoms))()
     for d, g in zip(descs, geoms):
+        if "aabbs" in g:  # procedural-primitive geometry: {aabbs: Buffer|ptr, aabb_count, stride, flags}
+            d.type = T.GEOMETRY_TYPE_PROCEDURAL_AABBS
+            d.vertex_buffer = _ptr(g["aabbs"])
+            d.vertex_count = g["aabb_count"]
+            d.vertex_stride_bytes = g.get("stride", 24)
+            d.flags = g.get("flags", T.GEOMETRY_FLAG_OPAQUE)
+            continue
         d.vertex_buffer = _ptr(g["vertices"])
         d.vertex_count = g["vertex_count"]
         d.vertex_stride_bytes = g.get("stride", 24)

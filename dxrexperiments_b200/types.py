@@ -50,7 +50,7 @@ class DenoiserParams(C.Structure):  # include/DenoiseCompositor.h:41-49
 class GeometryDesc(C.Structure):
     _fields_ = [("vertex_buffer", C.c_void_p), ("vertex_count", C.c_uint32), ("vertex_stride_bytes", C.c_uint32),
                 ("index_buffer", C.c_void_p), ("index_count", C.c_uint32), ("index_format", C.c_uint32),
-                ("transform3x4", C.c_void_p), ("flags", C.c_uint32), ("_pad", C.c_uint32)]
+                ("transform3x4", C.c_void_p), ("flags", C.c_uint32), ("type", C.c_uint32)]
 
 
 class InstanceDesc(C.Structure):  # D3D12_RAYTRACING_FALLBACK_INSTANCE_DESC
@@ -80,7 +80,7 @@ class PrebuildInfo(C.Structure):
 
 
 class AsInfo(C.Structure):  # rt_as_info
-    _fields_ = [("count", C.c_uint32), ("top_level", C.c_uint32), ("build_flags", C.c_uint32), ("_pad", C.c_uint32),
+    _fields_ = [("count", C.c_uint32), ("top_level", C.c_uint32), ("build_flags", C.c_uint32), ("has_procedural", C.c_uint32),
                 ("blob_bytes", C.c_uint64), ("total_bytes", C.c_uint64), ("compacted_bytes", C.c_uint64)]
 
 
@@ -110,7 +110,12 @@ assert VERTEX_DTYPE.itemsize == 24
 NO_HIT = 0xFFFFFFFF
 LEAF_FLAG = 0x80000000
 
+PROCEDURAL_FLAG = 0x40000000
 RAY_FLAG_NONE = 0x00
+RAY_FLAG_FORCE_OPAQUE = 0x01
+RAY_FLAG_FORCE_NON_OPAQUE = 0x02
+RAY_FLAG_CULL_OPAQUE = 0x40
+RAY_FLAG_CULL_NON_OPAQUE = 0x80
 RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH = 0x04
 RAY_FLAG_SKIP_CLOSEST_HIT_SHADER = 0x08
 RAY_FLAG_CULL_BACK_FACING_TRIANGLES = 0x10
@@ -126,7 +131,15 @@ COPY_MODE_CLONE, COPY_MODE_COMPACT = 0, 1
 INSTANCE_FLAG_NONE = 0
 INSTANCE_FLAG_TRIANGLE_CULL_DISABLE = 0x1
 INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE = 0x2
+INSTANCE_FLAG_FORCE_OPAQUE = 0x4
+INSTANCE_FLAG_FORCE_NON_OPAQUE = 0x8
+GEOMETRY_FLAG_NONE = 0
 GEOMETRY_FLAG_OPAQUE = 0x1
+GEOMETRY_TYPE_TRIANGLES, GEOMETRY_TYPE_PROCEDURAL_AABBS = 0, 1
+PRIMITIVE_TYPE_TRIANGLE, PRIMITIVE_TYPE_PROCEDURAL = 1, 2
+ANYHIT_NONE, ANYHIT_ACCEPT, ANYHIT_IGNORE, ANYHIT_END_SEARCH, ANYHIT_CUTOUT = 0, 1, 2, 3, 4
+INTERSECTION_NONE, INTERSECTION_BOX, INTERSECTION_SPHERE = 0, 1, 2
+HIT_KIND_TRIANGLE_FRONT_FACE = 0xFE
 
 
 def parse_blas_blob(blob: np.ndarray):

@@ -135,7 +135,7 @@ typedef struct rt_as_info {
     uint32_t count;      /* triangles or instances */
     uint32_t top_level;  /* 1 for a TLAS */
     uint32_t build_flags;
-    uint32_t _pad;
+    uint32_t has_procedural; /* BLAS built from procedural-AABB geometry / TLAS reaching such a BLAS */
     uint64_t blob_bytes;      /* BVHOffsets.totalSize: the reference-format blob at the head of the buffer */
     uint64_t total_bytes;     /* bytes in use = result_bytes of the matching prebuild */
     uint64_t compacted_bytes; /* bytes a COMPACT copy needs */
@@ -201,6 +201,21 @@ int rt_trace_rays(rt_context *ctx, const void *tlas_result, const rt_ray *rays, 
 /* Same with per-ray work counters accumulated into *stats (device memory, 5 x u64 = rt_trace_stats). */
 int rt_trace_rays_stats(rt_context *ctx, const void *tlas_result, const rt_ray *rays, uint64_t n, uint32_t ray_flags,
                         uint32_t instance_mask, rt_hit *hits, rt_trace_stats *stats_dev);
+/*
+ * Fallback_TraceRay WITH the hit groups' any-hit and intersection programs, over triangle and procedural-AABB geometry
+ * (replaces: the Traverse loop's shader call-outs FL/TraverseFunction.hlsli:651-722 — InvokeAnyHit :102-117,
+ * Fallback_ReportHit :136-158 — and the hit-group lookup GetAnyHitAndIntersectionStateId; on the host side
+ * RtProgram::Desc::addHitGroup(idx, closestHit, anyHit, intersection), libs/DXRFramework/RtProgram.h:51).
+ * `programs` is a HOST array with one entry per hit-group record, indexed by
+ * ray_contribution + GeometryContributionToHitGroupIndex * geometry_multiplier + InstanceContributionToHitGroupIndex;
+ * records beyond n_programs have no any-hit and no intersection program.  hits[i].leaf_slot carries HitKind() in bits
+ * 31:24 (0xFE for triangles); for a procedural hit bary[] holds the intersection program's two attribute floats.
+ * rt_dispatch_rays / rt_trace_rays know hit groups of type TRIANGLES only: given a TLAS that reaches procedural
+ * primitives they report every ray as a miss and rt_get_status returns RT_ERR_UNSUPPORTED.
+ */
+int rt_trace_rays_hit_groups(rt_context *ctx, const void *tlas_result, const rt_ray *rays, uint64_t n, uint32_t ray_flags,
+                             uint32_t instance_mask, uint32_t ray_contribution, uint32_t geometry_multiplier,
+                             const rt_hit_group_programs *programs, uint32_t n_programs, rt_hit *hits);
 /* RayGen's camera rays (ProgressiveRaytracing.hlsl:17-31) written out as records. */
 int rt_generate_primary_rays(rt_context *ctx, const rt_per_frame_constants *frame, uint32_t width, uint32_t height,
                              float jitter_scale, rt_ray *rays);

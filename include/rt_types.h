@@ -98,6 +98,12 @@ typedef struct rt_vertex {
 
 /* ------------------------------------------------------------------ acceleration structure inputs */
 
+/* D3D12_RAYTRACING_GEOMETRY_TYPE (FL/LoadPrimitivesPass.cpp:73,124-127). */
+enum {
+    RT_GEOMETRY_TYPE_TRIANGLES = 0,
+    RT_GEOMETRY_TYPE_PROCEDURAL_AABBS = 1
+};
+
 enum {
     RT_GEOMETRY_FLAG_NONE = 0,
     RT_GEOMETRY_FLAG_OPAQUE = 0x1,
@@ -135,10 +141,13 @@ enum {
 };
 
 /*
- * One triangle geometry of a bottom-level build.  `vertex_buffer`/`index_buffer`/`transform3x4`
+ * One geometry of a bottom-level build.  `vertex_buffer`/`index_buffer`/`transform3x4`
  * are DEVICE pointers for rt_core (HOST pointers for the CPU oracle, which reuses the struct).
  * index_format: 0 = no index buffer, 16 = uint16, 32 = uint32.
  * (externals/D3D12RaytracingFallback/src/LoadPrimitivesPass.cpp:60-115)
+ * type == RT_GEOMETRY_TYPE_PROCEDURAL_AABBS (D3D12_RAYTRACING_GEOMETRY_AABBS_DESC, LoadPrimitivesPass.cpp:122-152,
+ * FL/LoadProceduralGeometry.hlsl): `vertex_buffer` is the AABB buffer ({float min[3], max[3]} at the start of every
+ * `vertex_stride_bytes`), `vertex_count` is AABBCount; index buffer and transform are ignored.
  */
 typedef struct rt_geometry_desc {
     const void *vertex_buffer;
@@ -149,7 +158,7 @@ typedef struct rt_geometry_desc {
     uint32_t index_format;
     const float *transform3x4; /* 12 floats, row major, or NULL */
     uint32_t flags;            /* RT_GEOMETRY_FLAG_* */
-    uint32_t _pad;
+    uint32_t type;             /* RT_GEOMETRY_TYPE_* (0 = triangles, so zero-initialised descs keep their meaning) */
 } rt_geometry_desc;
 
 /* 64 B, byte-compatible with D3D12_RAYTRACING_FALLBACK_INSTANCE_DESC. */
@@ -185,8 +194,10 @@ typedef struct rt_aabb_node {
 #define RT_NODE_PROCEDURAL_FLAG 0x40000000u
 
 #pragma pack(push, 1)
+#define RT_PRIMITIVE_TYPE_TRIANGLE 1u   /* TRIANGLE_TYPE, FL/RayTracingHlslCompat.h:140 */
+#define RT_PRIMITIVE_TYPE_PROCEDURAL 2u /* PROCEDURAL_PRIMITIVE_TYPE, :141 */
 typedef struct rt_primitive {
-    uint32_t type; /* 1 = triangle */
+    uint32_t type; /* 1 = triangle (v = 3 vertices), 2 = procedural (v[0..5] = AABB min, max; v[6..8] = 0) */
     float v[9];
 } rt_primitive; /* 40 B */
 
@@ -229,6 +240,38 @@ typedef struct rt_hit {
     uint32_t instance_id;     /* InstanceID() */
     uint32_t leaf_slot;       /* sorted triangle slot inside the BLAS (debug / parity) */
 } rt_hit; /* 32 B */
+
+/*
+ * Hit groups with any-hit / intersection shaders (RtProgram::Desc::addHitGroup(idx, chs, ahs, is), RtProgram.h:51).
+ * The reference links DXIL entry points; here the "shader library" is CUDA code compiled into librt_core, and a hit
+ * group names its programs by id.  One entry per hit-group record, indexed exactly as the shader table is
+ * (RayContributionToHitGroupIndex + GeometryContributionToHitGroupIndex * Multiplier + InstanceContribution...,
+ * FL/TraverseFunction.hlsli:658-661,684-687).
+ */
+enum {
+    RT_ANYHIT_NONE = 0,       /* no any-hit shader in the hit group (state id 0): the hit is accepted */
+    RT_ANYHIT_ACCEPT = 1,     /* a no-op shader, e.g. the application's ShadowAnyHit (ProgressiveRaytracing.hlsl:172-176) */
+    RT_ANYHIT_IGNORE = 2,     /* IgnoreHit() on every candidate */
+    RT_ANYHIT_END_SEARCH = 3, /* AcceptHitAndEndSearch() on every candidate */
+    RT_ANYHIT_CUTOUT = 4,     /* alpha-test stand-in: IgnoreHit() when (int(8*attr.x) + int(8*attr.y)) is odd */
+    RT_ANYHIT_COUNT = 5
+};
+enum {
+    RT_INTERSECTION_NONE = 0,   /* hit group of type TRIANGLES */
+    RT_INTERSECTION_BOX = 1,    /* the primitive's AABB itself: ReportHit(entry t, or exit t when the origin is inside) */
+    RT_INTERSECTION_SPHERE = 2, /* sphere inscribed in the AABB (centre = box centre, radius = smallest half extent) */
+    RT_INTERSECTION_COUNT = 3
+};
+#define RT_HIT_KIND_TRIANGLE_FRONT_FACE 0xFEu /* the only triangle hit kind the reference reports (:688) */
+#define RT_HIT_KIND_BOX_ENTER 0u
+#define RT_HIT_KIND_BOX_EXIT 1u
+#define RT_HIT_KIND_SPHERE_ENTER 0u
+#define RT_HIT_KIND_SPHERE_EXIT 1u
+
+typedef struct rt_hit_group_programs {
+    uint32_t any_hit;      /* RT_ANYHIT_* */
+    uint32_t intersection; /* RT_INTERSECTION_* */
+} rt_hit_group_programs;
 
 /* Per-ray traversal work counters used for the roofline. */
 typedef struct rt_trace_stats {

@@ -72,6 +72,7 @@ def lib():
         L.orc_tlas_perm.argtypes = [vp]
         L.orc_tlas_perm.restype = vp
         L.orc_trace.argtypes = [vp, vp, u64, u32, u32, vp, vp, i32]
+        L.orc_trace_hit_groups.argtypes = [vp, vp, u64, u32, u32, u32, u32, vp, u32, vp, i32]
         L.orc_render_progressive.argtypes = [vp, vp, u32, vp, vp, u32, u32, vp, i32, vp, vp]
         L.orc_render_realtime.argtypes = [vp, vp, u32, vp, vp, u32, u32, vp, vp, i32, vp]
         L.orc_denoise.argtypes = [vp, vp, vp, vp, u32, u32, vp, i32]
@@ -117,6 +118,12 @@ def morton_codes(prims: np.ndarray, aabb: np.ndarray) -> np.ndarray:
     return out
 
 
+def morton_code_from_centroid(centroid, aabb) -> int:
+    c = np.ascontiguousarray(centroid, np.float32)
+    a = np.ascontiguousarray(aabb, np.float32)
+    return int(lib().orc_morton_code_from_centroid(_ptr(c), _ptr(a)))
+
+
 def sort_pairs(codes: np.ndarray):
     codes = np.ascontiguousarray(codes, np.uint32)
     s = np.zeros_like(codes)
@@ -157,7 +164,7 @@ def next_rand(state: int):
 class Blas:
     def __init__(self, geoms, build_flags: int = 0):
         """geoms: list of dicts {vertices (V,k) float32 array or structured, stride, indices (uint16/uint32 or None),
-        transform (12,) or None, flags}."""
+        transform (12,) or None, flags}, or {aabbs (A,6+) float32, stride, flags} for procedural-primitive geometry."""
         descs = self._descs(geoms)
         self.handle = lib().orc_blas_build(descs, len(geoms), build_flags)
         self.n = int(lib().orc_blas_num_prims(self.handle))
@@ -179,6 +186,15 @@ class Blas:
         self._keep = []
         descs = (T.GeometryDesc * len(geoms))()
         for d, g in zip(descs, geoms):
+            if "aabbs" in g:
+                vb = np.ascontiguousarray(g["aabbs"], np.float32)
+                self._keep.append(vb)
+                d.type = T.GEOMETRY_TYPE_PROCEDURAL_AABBS
+                d.vertex_buffer = vb.ctypes.data
+                d.vertex_stride_bytes = int(g.get("stride", vb.strides[0]))
+                d.vertex_count = vb.shape[0]
+                d.flags = int(g.get("flags", T.GEOMETRY_FLAG_OPAQUE))
+                continue
             vb = np.ascontiguousarray(g["vertices"])
             self._keep.append(vb)
             d.vertex_buffer = vb.ctypes.data
@@ -290,6 +306,16 @@ class Tlas:
         hits = np.zeros(rays.shape[0], dtype=T.HIT_DTYPE)
         st = stats if stats is not None else T.TraceStats()
         lib().orc_trace(self.handle, _ptr(rays), rays.shape[0], ray_flags, mask, _ptr(hits), C.byref(st), threads)
+        return hits
+
+    def trace_hit_groups(self, rays: np.ndarray, programs, ray_flags: int = 0, mask: int = 0xFF, ray_contribution: int = 0,
+                         geometry_multiplier: int = 0, threads: int = 1):
+        """programs: (R, 2) uint32 {any_hit, intersection} per hit-group record.  leaf_slot carries HitKind() << 24."""
+        rays = np.ascontiguousarray(rays, dtype=T.RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=T.HIT_DTYPE)
+        progs = np.ascontiguousarray(programs, np.uint32).reshape(-1, 2)
+        lib().orc_trace_hit_groups(self.handle, _ptr(rays), rays.shape[0], ray_flags, mask, ray_contribution, geometry_multiplier,
+                                   _ptr(progs), progs.shape[0], _ptr(hits), threads)
         return hits
 
 

@@ -86,6 +86,11 @@ const uint32_t *orc_tlas_sorted_morton(const orc_tlas *t);
 const uint32_t *orc_tlas_perm(const orc_tlas *t);
 
 /* ---- traversal: FL/TraverseFunction.hlsli:520-799 + TraverseShader.hlsli:21-73 ---- */
+/* Traversal with the hit groups' any-hit / intersection programs (rt_types.h RT_ANYHIT_*, RT_INTERSECTION_*);
+ * leaf_slot carries HitKind() in bits 31:24. */
+void orc_trace_hit_groups(const orc_tlas *t, const rt_ray *rays, uint64_t n, uint32_t ray_flags, uint32_t instance_mask,
+                          uint32_t ray_contribution, uint32_t geometry_multiplier, const rt_hit_group_programs *programs,
+                          uint32_t n_programs, rt_hit *hits, int threads);
 void orc_trace(const orc_tlas *t, const rt_ray *rays, uint64_t n, uint32_t ray_flags, uint32_t instance_mask,
                rt_hit *hits, rt_trace_stats *stats /* nullable, accumulated */, int threads);
 

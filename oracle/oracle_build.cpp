@@ -17,6 +17,22 @@ static void load_triangles(const rt_geometry_desc *geoms, uint32_t n_geoms, std:
     for (uint32_t g = 0; g < n_geoms; ++g) {
         const rt_geometry_desc &d = geoms[g];
         const uint8_t *vb = static_cast<const uint8_t *>(d.vertex_buffer);
+        if (d.type == RT_GEOMETRY_TYPE_PROCEDURAL_AABBS) {
+            // FL/LoadProceduralGeometry.hlsl:16-42, FL/LoadPrimitivesPass.cpp:122-152; pinned by UT:2616-2664
+            for (uint32_t t = 0; t < d.vertex_count; ++t) {
+                rt_primitive p;  // CreateProceduralGeometryPrimitive: NullPrimitive() + type + {min, max}
+                p.type = RT_PRIMITIVE_TYPE_PROCEDURAL;
+                std::memcpy(p.v, vb + size_t(t) * d.vertex_stride_bytes, 24);
+                p.v[6] = p.v[7] = p.v[8] = 0.0f;
+                prims.push_back(p);
+                rt_primitive_meta m;
+                m.geometryContributionToHitGroupIndex = g;
+                m.primitiveIndex = t;
+                m.geometryFlags = d.flags;
+                meta.push_back(m);
+            }
+            continue;
+        }
         uint32_t ntri = (d.index_format == 0 ? d.vertex_count : d.index_count) / 3;
         for (uint32_t t = 0; t < ntri; ++t) {
             uint32_t idx[3];
@@ -238,8 +254,13 @@ static void make_update_cache(uint32_t n, const uint32_t *perm, const rt_aabb_no
 }
 
 static Box triangle_leaf_box(const rt_primitive &p) {
-    // GetBoxDataFromTriangle: FL/RayTracingHelper.hlsli:273-285
     const float *v = p.v;
+    if (p.type == RT_PRIMITIVE_TYPE_PROCEDURAL) {
+        // ComputeLeafAABB, procedural branch (FL/BottomLevelComputeAABBs.hlsl:32-40): no padding
+        Aabb a{mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5])};
+        return aabb_to_box(a);
+    }
+    // GetBoxDataFromTriangle: FL/RayTracingHelper.hlsli:273-285
     f3 v0 = mk(v[0], v[1], v[2]), v1 = mk(v[3], v[4], v[5]), v2 = mk(v[6], v[7], v[8]);
     Aabb a;
     a.mn = vmin(vmin(v0, v1), v2);
@@ -301,7 +322,8 @@ extern "C" {
 void orc_scene_aabb(const rt_primitive *prims, uint32_t n, float out[6]) {
     f3 mn = mk(FLT_MAX, FLT_MAX, FLT_MAX), mx = mk(-FLT_MAX, -FLT_MAX, -FLT_MAX);
     for (uint32_t i = 0; i < n; ++i)
-        for (int k = 0; k < 3; ++k) {
+        // triangles: all three vertices; procedural: min and max (CalculateSceneAABBFromPrimitives.hlsl:26-37)
+        for (int k = 0; k < (prims[i].type == RT_PRIMITIVE_TYPE_PROCEDURAL ? 2 : 3); ++k) {
             f3 v = mk(prims[i].v[3 * k], prims[i].v[3 * k + 1], prims[i].v[3 * k + 2]);
             mn = vmin(mn, v);
             mx = vmax(mx, v);
@@ -312,8 +334,11 @@ void orc_scene_aabb(const rt_primitive *prims, uint32_t n, float out[6]) {
 void orc_morton_codes(const rt_primitive *prims, uint32_t n, const float aabb[6], uint32_t *codes) {
     for (uint32_t i = 0; i < n; ++i) {
         const float *v = prims[i].v;
-        // GetCentroid: (tri.v0 + tri.v1 + tri.v2) / 3.0  (CalculateMortonCodesForPrimitives.hlsl:22-25)
-        f3 c = ((mk(v[0], v[1], v[2]) + mk(v[3], v[4], v[5])) + mk(v[6], v[7], v[8])) / 3.0f;
+        // GetCentroid: (tri.v0 + tri.v1 + tri.v2) / 3.0  (CalculateMortonCodesForPrimitives.hlsl:22-25);
+        // procedural: (aabb.min + aabb.max) / 2.0 (:26-30)
+        f3 c = prims[i].type == RT_PRIMITIVE_TYPE_PROCEDURAL
+                   ? (mk(v[0], v[1], v[2]) + mk(v[3], v[4], v[5])) / 2.0f
+                   : ((mk(v[0], v[1], v[2]) + mk(v[3], v[4], v[5])) + mk(v[6], v[7], v[8])) / 3.0f;
         codes[i] = morton_from_centroid(c, aabb);
     }
 }
@@ -369,6 +394,8 @@ orc_blas *orc_blas_build(const rt_geometry_desc *geoms, uint32_t n_geoms, uint32
     // FL/GpuBVH2Builder.cpp:312-326: the treelet pass works on the hierarchy and the sorted triangles
     treelet_optimise(n, b->hier.data(), sp, build_flags);
     fit_boxes(n, b->hier.data(), nodes, [&](uint32_t slot) { return triangle_leaf_box(sp[slot]); });
+    for (uint32_t slot = 0; slot < n; ++slot)  // flags.x = primitiveIndex | IsLeafFlag | IsProceduralGeometryFlag
+        if (sp[slot].type == RT_PRIMITIVE_TYPE_PROCEDURAL) nodes[n - 1 + slot].flags |= RT_NODE_PROCEDURAL_FLAG;  // BottomLevelComputeAABBs.hlsl:34
     make_update_cache(n, b->perm.data(), nodes, b->sort_cache, b->parents);
     return b;
 }

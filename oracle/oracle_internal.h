@@ -114,6 +114,7 @@ struct HitInfo {
     float bary[2] = {0, 0};
     uint32_t primitiveIndex = RT_NO_HIT, instanceIndex = 0, geometryIndex = 0, instanceId = 0, leafSlot = 0;
     uint32_t hitGroupContribution = 0;  // instanceContribution + rayContribution + geom*multiplier
+    uint32_t hitKind = 0;               // HitKind(): 0xFE for triangles, the intersection program's value otherwise
 };
 
 struct TraceCounters {
@@ -122,6 +123,7 @@ struct TraceCounters {
 
 // Fallback_TraceRay without the shader call-out: FL/TraverseShader.hlsli:21-73.
 HitInfo trace_ray(const orc_tlas *t, f3 origin, float tmin, f3 dir, float tmax, uint32_t rayFlags, uint32_t mask,
-                  uint32_t rayContribution, uint32_t geomMultiplier, TraceCounters *ctr);
+                  uint32_t rayContribution, uint32_t geomMultiplier, TraceCounters *ctr,
+                  const rt_hit_group_programs *programs = nullptr, uint32_t n_programs = 0);
 
 }  // namespace orc

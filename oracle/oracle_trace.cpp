@@ -94,8 +94,81 @@ static bool ray_triangle(float &hitT, float bary[2], uint32_t instanceFlags, uin
     return true;
 }
 
+// ---------------------------------------------------------------- compiled-in any-hit / intersection programs
+// The reference links application HLSL here (Fallback_CallIndirect(stateId)); the programs below are OURS (the
+// application has only the no-op ShadowAnyHit and no intersection shader), so they are "parity unpinned" — what IS
+// restated from the reference is the machinery around them: InvokeAnyHit / IgnoreHit / AcceptHitAndEndSearch
+// (FL/TraverseFunction.hlsli:102-117), Fallback_ReportHit (:136-158) and the leaf handling (:635-735).
+enum { kEndSearch = -1, kIgnore = 0, kAccept = 1 };  // :11-13
+
+static int run_any_hit(uint32_t program, float ax, float ay) {
+    // InvokeAnyHit: Fallback_SetAnyHitResult(ACCEPT); call; return Fallback_AnyHitResult()
+    switch (program) {
+        case RT_ANYHIT_IGNORE: return kIgnore;
+        case RT_ANYHIT_END_SEARCH: return kEndSearch;
+        case RT_ANYHIT_CUTOUT: return ((int(floorf(8.0f * ax)) + int(floorf(8.0f * ay))) & 1) ? kIgnore : kAccept;
+        default: return kAccept;  // RT_ANYHIT_ACCEPT: no-op body
+    }
+}
+
+struct ReportCtx {  // the Fallback_* registers ReportHit touches
+    float tmin;
+    float *tCurrent;
+    uint32_t rayFlags, anyHit;
+    int anyHitResult;  // Fallback_AnyHitResult()
+    bool committed;
+    float t, ax, ay;
+    uint32_t kind;
+};
+
+// Fallback_ReportHit: FL/TraverseFunction.hlsli:136-158.  geomOpaque is the literal `true` and the instance flags the
+// literal 0 there ("TODO" in the reference), so an any-hit shader runs for a procedural hit only under
+// RAY_FLAG_FORCE_NON_OPAQUE.
+static int report_hit(ReportCtx &c, float tHit, uint32_t hitKind, float ax, float ay) {
+    if (tHit < c.tmin || *c.tCurrent <= tHit) return 0;
+    int ret = kAccept;
+    bool opaque = true;
+    if (c.rayFlags & RT_RAY_FLAG_FORCE_OPAQUE) opaque = true;
+    else if (c.rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
+    if (c.anyHit > 0 && !opaque) ret = c.anyHitResult = run_any_hit(c.anyHit, ax, ay);
+    if (ret != kIgnore) {
+        *c.tCurrent = tHit;  // Fallback_CommitHit
+        c.committed = true;
+        c.t = tHit, c.ax = ax, c.ay = ay, c.kind = hitKind;
+        if (c.rayFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) ret = kEndSearch;
+    }
+    return ret;
+}
+
+static inline float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+
+// RT_INTERSECTION_BOX: slab test of the object-space ray against the primitive's own AABB.
+static void intersect_box(ReportCtx &c, f3 o, f3 d, f3 mn, f3 mx) {
+    f3 t0 = (mn - o) / d, t1 = (mx - o) / d;
+    float tNear = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+    float tFar = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+    if (!(tNear <= tFar)) return;
+    if (report_hit(c, tNear, RT_HIT_KIND_BOX_ENTER, 0.0f, 0.0f) == 0) report_hit(c, tFar, RT_HIT_KIND_BOX_EXIT, 0.0f, 0.0f);
+}
+
+// RT_INTERSECTION_SPHERE: the sphere inscribed in the AABB; attributes = (normal.x, normal.y).
+static void intersect_sphere(ReportCtx &c, f3 o, f3 d, f3 mn, f3 mx) {
+    f3 ctr = (mn + mx) * 0.5f, h = mx - ctr;
+    float r = fminf(fminf(h.x, h.y), h.z);
+    if (!(r > 0.0f)) return;
+    f3 oc = o - ctr;
+    float a = dot3(d, d), b = dot3(oc, d), cc = dot3(oc, oc) - r * r;
+    float disc = b * b - a * cc;
+    if (!(disc >= 0.0f) || !(a > 0.0f)) return;
+    float s = sqrtf(disc);
+    float tA = (-b - s) / a, tB = (-b + s) / a;
+    f3 nA = (oc + d * tA) / r, nB = (oc + d * tB) / r;
+    if (report_hit(c, tA, RT_HIT_KIND_SPHERE_ENTER, nA.x, nA.y) == 0) report_hit(c, tB, RT_HIT_KIND_SPHERE_EXIT, nB.x, nB.y);
+}
+
 HitInfo trace_ray(const orc_tlas *tl, f3 origin, float tmin, f3 dir, float tmax, uint32_t rayFlags, uint32_t mask,
-                  uint32_t rayContribution, uint32_t geomMultiplier, TraceCounters *ctr) {
+                  uint32_t rayContribution, uint32_t geomMultiplier, TraceCounters *ctr, const rt_hit_group_programs *programs,
+                  uint32_t n_programs) {
     HitInfo hit;
     float tCurrent = tmax;  // Fallback_TraceRayBegin: RayTCurrent() = TMax
     if (tl->n == 0) return hit;
@@ -109,7 +182,7 @@ HitInfo trace_ray(const orc_tlas *tl, f3 origin, float tmin, f3 dir, float tmax,
 
     RayData world = get_ray_data(origin, dir);
     RayData cur = world;
-    f3 curOrigin = origin;
+    f3 curOrigin = origin, curDir = dir;
     bool bottom = false;
     uint32_t nodesToProcess[2] = {0, 0};
     const rt_aabb_node *nodes = tnodes;
@@ -144,6 +217,7 @@ HitInfo trace_ray(const orc_tlas *tl, f3 origin, float tmin, f3 dir, float tmax,
                         instanceFlags = RT_INSTANCE_FLAGS(md.instanceDesc);
                         curOrigin = xform_point(md.instanceDesc.transform, origin);
                         f3 objDir = xform_vector(md.instanceDesc.transform, dir);
+                        curDir = objDir;
                         cur = get_ray_data(curOrigin, objDir);
                         nodesToProcess[1] = 1;
                     }
@@ -157,27 +231,48 @@ HitInfo trace_ray(const orc_tlas *tl, f3 origin, float tmin, f3 dir, float tmax,
                     if (rayFlags & RT_RAY_FLAG_FORCE_OPAQUE) opaque = true;
                     else if (rayFlags & RT_RAY_FLAG_FORCE_NON_OPAQUE) opaque = false;
                     bool culled = (opaque && (rayFlags & RT_RAY_FLAG_CULL_OPAQUE)) || (!opaque && (rayFlags & RT_RAY_FLAG_CULL_NON_OPAQUE));
-                    if (!culled) {
-                        const float *v = blas->sorted_prims()[leafIndex].v;
+                    const uint32_t record = rayContribution + pm.geometryContributionToHitGroupIndex * geomMultiplier + instanceOffset;
+                    const rt_hit_group_programs none = {RT_ANYHIT_NONE, RT_INTERSECTION_NONE};
+                    const rt_hit_group_programs &prog = (programs && record < n_programs) ? programs[record] : none;
+                    auto commit = [&](float t, float a0, float a1, uint32_t kind) {
+                        tCurrent = t;
+                        hit.hit = true;
+                        hit.t = t;
+                        hit.bary[0] = a0, hit.bary[1] = a1;
+                        hit.primitiveIndex = pm.primitiveIndex;
+                        hit.geometryIndex = pm.geometryContributionToHitGroupIndex;
+                        hit.instanceIndex = instanceIndex;
+                        hit.instanceId = instanceId;
+                        hit.leafSlot = leafIndex;
+                        hit.hitGroupContribution = record;
+                        hit.hitKind = kind;
+                    };
+                    const float *v = blas->sorted_prims()[leafIndex].v;
+                    if (!culled && (node.flags & RT_NODE_PROCEDURAL_FLAG)) {
+                        // :656-671 — the intersection shader of the hit group runs with the object-space ray; it
+                        // calls ReportHit; the search ends only if an any-hit shader said AcceptHitAndEndSearch
+                        // (the END_SEARCH that ReportHit returns under ACCEPT_FIRST_HIT is not looked at, :670).
+                        ReportCtx rc{tmin, &tCurrent, rayFlags, prog.any_hit, kAccept, false, 0, 0, 0, 0};
+                        if (prog.intersection == RT_INTERSECTION_BOX)
+                            intersect_box(rc, curOrigin, curDir, mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]));
+                        else if (prog.intersection == RT_INTERSECTION_SPHERE)
+                            intersect_sphere(rc, curOrigin, curDir, mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]));
+                        if (rc.committed) commit(rc.t, rc.ax, rc.ay, rc.kind);
+                        endSearch = rc.anyHitResult == kEndSearch;
+                    } else if (!culled) {
                         float t0 = tCurrent, bary[2];
                         bool ok = ray_triangle(t0, bary, instanceFlags, rayFlags, curOrigin, cur, mk(v[0], v[1], v[2]),
                                                mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]));
                         // TestLeafNodeIntersections :385
                         if (ok && t0 < tCurrent && t0 > tmin) {
-                            // The app registers a no-op any-hit shader only for the shadow hit group and all
-                            // geometry is OPAQUE (libs/DXRFramework/Helpers/BottomLevelASGenerator.cpp:109-110);
-                            // a non-opaque hit with a no-op any-hit shader is accepted as well, so commit.
-                            tCurrent = t0;
-                            hit.hit = true;
-                            hit.t = t0;
-                            hit.bary[0] = bary[0], hit.bary[1] = bary[1];
-                            hit.primitiveIndex = pm.primitiveIndex;
-                            hit.geometryIndex = pm.geometryContributionToHitGroupIndex;
-                            hit.instanceIndex = instanceIndex;
-                            hit.instanceId = instanceId;
-                            hit.leafSlot = leafIndex;
-                            hit.hitGroupContribution = rayContribution + pm.geometryContributionToHitGroupIndex * geomMultiplier + instanceOffset;
-                            if (rayFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) endSearch = true;
+                            // :699-722.  Opaque: commit.  Non-opaque: the hit group's any-hit shader (if any) decides;
+                            // the application registers only the no-op ShadowAnyHit and all its geometry is OPAQUE
+                            // (libs/DXRFramework/Helpers/BottomLevelASGenerator.cpp:109-110).  Literal quirk kept:
+                            // under ACCEPT_FIRST_HIT an IGNOREd candidate still ends the search (:721).
+                            int ret = kAccept;
+                            if (!opaque && prog.any_hit) ret = run_any_hit(prog.any_hit, bary[0], bary[1]);
+                            if (ret != kIgnore) commit(t0, bary[0], bary[1], RT_HIT_KIND_TRIANGLE_FRONT_FACE);
+                            endSearch = ret == kEndSearch || (rayFlags & RT_RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH);
                         }
                     }
                     if (endSearch) {
@@ -207,6 +302,7 @@ HitInfo trace_ray(const orc_tlas *tl, f3 origin, float tmin, f3 dir, float tmax,
         bottom = false;
         cur = world;
         curOrigin = origin;
+        curDir = dir;
         nodes = tnodes;
     }
     return hit;
@@ -234,6 +330,26 @@ static void parallel_for(uint64_t n, int threads, F f) {
             }
         });
     for (auto &th : pool) th.join();
+}
+
+extern "C" void orc_trace_hit_groups(const orc_tlas *t, const rt_ray *rays, uint64_t n, uint32_t ray_flags, uint32_t instance_mask,
+                                     uint32_t ray_contribution, uint32_t geometry_multiplier,
+                                     const rt_hit_group_programs *programs, uint32_t n_programs, rt_hit *hits, int threads) {
+    parallel_for(n, threads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            const rt_ray &r = rays[i];
+            HitInfo h = trace_ray(t, mk(r.origin[0], r.origin[1], r.origin[2]), r.tmin, mk(r.direction[0], r.direction[1], r.direction[2]),
+                                  r.tmax, ray_flags, instance_mask, ray_contribution, geometry_multiplier, nullptr, programs, n_programs);
+            rt_hit &o = hits[i];
+            o.t = h.hit ? h.t : r.tmax;
+            o.bary[0] = h.bary[0], o.bary[1] = h.bary[1];
+            o.primitive_index = h.hit ? h.primitiveIndex : RT_NO_HIT;
+            o.instance_index = h.instanceIndex;
+            o.geometry_index = h.geometryIndex;
+            o.instance_id = h.instanceId;
+            o.leaf_slot = h.leafSlot | (h.hit ? h.hitKind << 24 : 0u);  // HitKind() in bits 31:24
+        }
+    });
 }
 
 extern "C" void orc_trace(const orc_tlas *t, const rt_ray *rays, uint64_t n, uint32_t ray_flags, uint32_t instance_mask,

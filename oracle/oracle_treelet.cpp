@@ -165,9 +165,13 @@ struct Pass {
                 // ComputeLeafAABB (FindTreelets.hlsl:16-29): BoundingBoxToAABB(GetBoxDataFromTriangle(...))
                 const float *p = sorted_prims[v - nInternal].v;
                 f3 v0 = mk(p[0], p[1], p[2]), v1 = mk(p[3], p[4], p[5]), v2 = mk(p[6], p[7], p[8]);
-                Aabb a{vmin(vmin(v0, v1), v2), vmax(vmax(v0, v1), v2)};
-                a.mn = vmin(a.mn, a.mx - mk(0.001f, 0.001f, 0.001f));  // AABB_Min_Padding
-                aabb[v] = box_to_aabb(aabb_to_box(a));
+                if (sorted_prims[v - nInternal].type == RT_PRIMITIVE_TYPE_PROCEDURAL) {
+                    aabb[v] = Aabb{v0, v1};  // GetProceduralPrimitiveAABB, no box round trip (FindTreelets.hlsl:25-28)
+                } else {
+                    Aabb a{vmin(vmin(v0, v1), v2), vmax(vmax(v0, v1), v2)};
+                    a.mn = vmin(a.mn, a.mx - mk(0.001f, 0.001f, 0.001f));  // AABB_Min_Padding
+                    aabb[v] = box_to_aabb(aabb_to_box(a));
+                }
                 count[v] = 1;
             } else {
                 const uint32_t l = hier[v].left, r = hier[v].right;
