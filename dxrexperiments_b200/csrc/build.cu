@@ -205,64 +205,62 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint32_t *key
     hist[threadIdx.x * gridDim.x + blockIdx.x] = s[threadIdx.x];
 }
 
-// Exclusive scan of the digit-major histogram hist[256][G] (flattened order) by one 1024-thread block: each warp
-// scans 8 rows with coalesced 32-wide steps, a 256-entry scan of the row totals follows, then the row bases are
-// added in a second coalesced sweep.  (A per-thread serial scan of contiguous segments took 134 us per pass.)
-__global__ void __launch_bounds__(1024) k_scan_hist(uint32_t *hist, uint32_t G) {
-    __shared__ uint32_t row_total[kRadix];
-    __shared__ uint32_t row_base[kRadix];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 32 warps x 8 rows
-    for (int r = 0; r < kRadix / 32; ++r) {
-        const int row = warp * (kRadix / 32) + r;
-        uint32_t *p = hist + size_t(row) * G;
-        uint32_t run = 0;
-        for (uint32_t c0 = 0; c0 < G; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            const uint32_t v = c < G ? p[c] : 0u;
-            uint32_t incl = v;
+// Exclusive scan of the digit-major histogram hist[256][G] in flattened order, split in two: block d scans row d
+// (G <= 4 x SMs entries) and leaves the row total in row_total[d]; the 256 row totals are scanned by every scatter
+// block for itself (k_radix_scatter).  One 1024-thread block doing the whole table took 50 us per pass.
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /* [8] */, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (c < G) p[c] = run + incl - v;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) row_total[row] = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {  // exclusive scan of the 256 row totals
-        uint32_t run = 0;
-        for (int c0 = 0; c0 < kRadix; c0 += 32) {
-            const uint32_t v = row_total[c0 + lane];
-            uint32_t incl = v;
+    uint32_t base = 0, tot = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            row_base[c0 + lane] = run + incl - v;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) base += c;
+        tot += c;
     }
+    total = tot;
     __syncthreads();
-    for (int r = 0; r < kRadix / 32; ++r) {
-        const int row = warp * (kRadix / 32) + r;
-        const uint32_t b = row_base[row];
-        if (b == 0) continue;
-        uint32_t *p = hist + size_t(row) * G;
-        for (uint32_t c = lane; c < G; c += 32) p[c] += b;
-    }
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_scan_rows(uint32_t *hist, uint32_t G, uint32_t *row_total) {
+    __shared__ uint32_t s_warp[kSortWarps];
+    uint32_t *p = hist + size_t(blockIdx.x) * G;
+    const uint32_t per = (G + kSortThreads - 1) / kSortThreads;  // consecutive entries per thread
+    const uint32_t c0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; ++k) sum += (c0 + k < G) ? p[c0 + k] : 0u;
+    uint32_t total;
+    uint32_t run = block_exclusive_scan_256(sum, s_warp, total);
+    for (uint32_t k = 0; k < per; ++k)
+        if (c0 + k < G) {
+            const uint32_t v = p[c0 + k];
+            p[c0 + k] = run;
+            run += v;
+        }
+    if (threadIdx.x == 0) row_total[blockIdx.x] = total;
 }
 
 template <bool IOTA>
 __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t n,
                                                                 int shift, uint32_t tiles_per_block, const uint32_t *offsets,
-                                                                uint32_t *keys_out, uint32_t *vals_out) {
+                                                                const uint32_t *row_total, uint32_t *keys_out, uint32_t *vals_out) {
     __shared__ uint32_t warp_count[kSortWarps][kRadix];
     __shared__ uint32_t base[kRadix];
+    __shared__ uint32_t s_warp[kSortWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = offsets[threadIdx.x * gridDim.x + blockIdx.x];
+    {
+        uint32_t unused;
+        const uint32_t row_base = block_exclusive_scan_256(row_total[threadIdx.x], s_warp, unused);
+        base[threadIdx.x] = row_base + offsets[threadIdx.x * gridDim.x + blockIdx.x];
+    }
     const uint64_t block_begin = uint64_t(blockIdx.x) * tiles_per_block * kSortTile;
     for (uint32_t tile = 0; tile < tiles_per_block; ++tile) {
         const uint64_t tile_begin = block_begin + uint64_t(tile) * kSortTile;
@@ -335,7 +333,16 @@ struct KarrasDev {
     }
 };
 
-__global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, uint32_t n, rt_hierarchy_node *nodes) {
+// `local` (may be null): local[i] = 1 when every leaf under internal node i lies in one kFitBlock-aligned block of
+// sorted slots — such a node's whole subtree is fitted inside one thread block's shared memory by k_fit_local.
+#ifndef RT_FIT_BLOCK
+#define RT_FIT_BLOCK 512
+#endif
+constexpr int kFitBlock = RT_FIT_BLOCK;
+#ifndef RT_FIT_LOCAL
+#define RT_FIT_LOCAL 1  // 0: the global-atomic k_fit for every level (A/B measurements)
+#endif
+__global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, uint32_t n, rt_hierarchy_node *nodes, uint8_t *local) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= int(n) - 1) return;
     KarrasDev k{codes, int(n)};
@@ -372,24 +379,55 @@ __global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, u
     nodes[idx].right = b;
     nodes[a].parent = idx;
     nodes[b].parent = idx;
+    if (local) local[idx] = (first / kFitBlock == last / kFitBlock) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------ rearrange
 // FL/RearrangeTriangles.hlsl:18-36: out[dst] = in[perm[dst]]; also emits the packed 48-byte triangle.
 __global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_packed_tri *recs, const uint32_t *perm, uint32_t n,
                                                              rt_primitive *out_prims, rt_primitive_meta *out_meta, rt_packed_tri *packed) {
-    uint32_t dst = blockIdx.x * blockDim.x + threadIdx.x;
-    if (dst >= n) return;
-    const uint32_t src = perm[dst];
-    const uint4 *q = reinterpret_cast<const uint4 *>(recs + src);
-    const uint4 q0 = __ldcs(q), q1 = __ldcs(q + 1), q2 = __ldcs(q + 2);  // each record is read exactly once
-    uint32_t *d = reinterpret_cast<uint32_t *>(out_prims + dst);
-    d[0] = (q2.w & RT_PACKED_PROCEDURAL) ? RT_PRIMITIVE_TYPE_PROCEDURAL : RT_PRIMITIVE_TYPE_TRIANGLE;
-    d[1] = q0.x, d[2] = q0.y, d[3] = q0.z, d[4] = q0.w, d[5] = q1.x, d[6] = q1.y, d[7] = q1.z, d[8] = q1.w, d[9] = q2.x;
-    uint32_t *m = reinterpret_cast<uint32_t *>(out_meta + dst);
-    m[0] = q2.z, m[1] = q2.y, m[2] = q2.w & ~RT_PACKED_PROCEDURAL;  // {geometryContributionToHitGroupIndex, primitiveIndex, geometryFlags}
-    uint4 *p = reinterpret_cast<uint4 *>(packed + dst);
-    p[0] = q0, p[1] = q1, p[2] = q2;
+    // The block's kThreads gathered records are staged in shared memory and written out as three contiguous runs
+    // (packed 48 B, Primitive 40 B, PrimitiveMetaData 12 B per element) with coalesced stores; one thread writing its
+    // own 40 + 12 + 48 bytes word by word kept the load/store unit saturated (ncu: lg_throttle) at 4 TB/s.
+    __shared__ uint4 s_rec[kThreads * 3];
+    const uint32_t b0 = blockIdx.x * kThreads;
+    const uint32_t cnt = min(uint32_t(kThreads), n - b0);
+    if (threadIdx.x < cnt) {
+        const uint32_t src = perm[b0 + threadIdx.x];
+        const uint4 *q = reinterpret_cast<const uint4 *>(recs + src);
+        // each record is read exactly once
+        s_rec[3 * threadIdx.x] = __ldcs(q), s_rec[3 * threadIdx.x + 1] = __ldcs(q + 1), s_rec[3 * threadIdx.x + 2] = __ldcs(q + 2);
+    }
+    __syncthreads();
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_rec);  // 12 words per element
+    {   // packed: 3 x 16 bytes per element, 16-byte aligned
+        uint4 *dst = reinterpret_cast<uint4 *>(packed + b0);
+        for (uint32_t i = threadIdx.x; i < 3 * cnt; i += kThreads) dst[i] = s_rec[i];
+    }
+    {   // Primitive: {type, 9 floats}; the array starts 16-byte aligned and a full block is 640 x 16 bytes
+        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(out_prims) + size_t(b0) * 10);
+        const uint32_t words = 10 * cnt;
+        auto word = [&](uint32_t w) -> uint32_t {
+            const uint32_t e = w / 10, f = w - 10 * e;
+            return f == 0 ? ((sw[12 * e + 11] & RT_PACKED_PROCEDURAL) ? RT_PRIMITIVE_TYPE_PROCEDURAL : RT_PRIMITIVE_TYPE_TRIANGLE) : sw[12 * e + f - 1];
+        };
+        for (uint32_t i = threadIdx.x; 4 * i < words; i += kThreads) {
+            const uint32_t w = 4 * i;
+            if (w + 4 <= words) {
+                dst[i] = make_uint4(word(w), word(w + 1), word(w + 2), word(w + 3));
+            } else {
+                uint32_t *d = reinterpret_cast<uint32_t *>(dst + i);
+                for (uint32_t k = 0; w + k < words; ++k) d[k] = word(w + k);
+            }
+        }
+    }
+    {   // PrimitiveMetaData: {geometryContributionToHitGroupIndex, primitiveIndex, geometryFlags}, 4-byte aligned
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out_meta) + size_t(b0) * 3;
+        for (uint32_t w = threadIdx.x; w < 3 * cnt; w += kThreads) {
+            const uint32_t e = w / 3, f = w - 3 * e;
+            dst[w] = f == 0 ? sw[12 * e + 10] : (f == 1 ? sw[12 * e + 9] : (sw[12 * e + 11] & ~RT_PACKED_PROCEDURAL));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ bottom-up fit
@@ -515,13 +553,203 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
     }
 }
 
+// k_fit for a full bottom-level build with the lower levels of the tree fitted inside the thread block.  A block owns
+// kFitBlock consecutive sorted slots; a parent flagged `local` (k_hierarchy; kept valid by k_treelet_reorder) has its
+// whole subtree among them.  The block works in rounds over a shared-memory ready queue: a node enters the queue when
+// its second child has been fitted (shared arrival counter), and the nodes of a round are handed to consecutive
+// threads, so the warps stay dense where the one-thread-per-leaf climb of k_fit runs at 6-7 of 32 lanes (ncu) and pays
+// a global atomic plus two device-wide fences per level.  Child boxes and subtree sizes are exchanged through shared
+// memory.  Nodes whose parent is not local — about log2(n) per block — leave through an exit list and finish with
+// k_fit's global climb.  Results (reference nodes, wide nodes, child order) are those of k_fit, bit for bit: the child
+// order depends only on the subtree sizes and the Karras order, never on who arrives first.
+__device__ __forceinline__ void fit_merge_store(uint32_t parent, uint32_t l, uint32_t r, uint32_t lc, uint32_t rc, Box bl, Box br,
+                                                uint32_t nInternal, rt_aabb_node *nodes, rt_wide_node *wide, rt_ext_header *ext, Box &box) {
+    if (rc < lc) {  // smaller subtree on the left; ties keep the Karras order
+        uint32_t t = l; l = r; r = t;
+        Box tb = bl; bl = br; br = tb;
+    }
+    float mn[3], mx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // GetBoxFromChildBoxes: FL/RayTracingHelper.hlsli:297-307
+        mn[k] = fminf(bl.c[k] - bl.h[k], br.c[k] - br.h[k]);
+        mx[k] = fmaxf(bl.c[k] + bl.h[k], br.c[k] + br.h[k]);
+    }
+    box = aabb_to_box(mn, mx);
+    store_node(nodes, parent, box, l & 0x00ffffffu, r);
+    const uint32_t lref = l >= nInternal ? (RT_NODE_LEAF_FLAG | (l - nInternal)) : l;
+    const uint32_t rref = r >= nInternal ? (RT_NODE_LEAF_FLAG | (r - nInternal)) : r;
+    float4 *w = reinterpret_cast<float4 *>(wide + parent);
+    w[0] = make_float4(bl.c[0], bl.c[1], bl.c[2], __uint_as_float(lref));
+    w[1] = make_float4(bl.h[0], bl.h[1], bl.h[2], __uint_as_float(rref));
+    w[2] = make_float4(br.c[0], br.c[1], br.c[2], 0.0f);
+    w[3] = make_float4(br.h[0], br.h[1], br.h[2], 0.0f);
+    if (parent == 0) {
+        ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
+        ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
+    }
+}
+
+__global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hierarchy_node *hier, uint32_t *counters, rt_aabb_node *nodes,
+                                                         const rt_packed_tri *packed, rt_wide_node *wide, rt_ext_header *ext,
+                                                         const uint8_t *local, uint32_t *exit_nodes, uint16_t *exit_sizes) {
+    // shared index of a node: leaf -> slot - b0 in [0, B); internal -> B + index - b0 in [B, 2B)
+    __shared__ float s_box[2 * kFitBlock][6];
+    __shared__ uint32_t s_size[2 * kFitBlock];
+    __shared__ uint32_t s_arrive[kFitBlock];
+    __shared__ uint32_t s_queue[2][kFitBlock];  // ready internal nodes of this / the next round
+    __shared__ uint32_t s_exit[2 * kFitBlock];   // fitted nodes whose parent is not local
+    __shared__ uint32_t s_qn[2], s_en;
+    // the hierarchy records and flags of this block's internal nodes (a local node's index lies in [b0, b0 + B)),
+    // fetched once and coalesced: the rounds below then run without a dependent global load
+    __shared__ uint32_t s_hier[3 * kFitBlock];
+    __shared__ uint8_t s_local[kFitBlock];
+    const uint32_t b0 = blockIdx.x * kFitBlock;
+    const uint32_t nInternal = n - 1;
+    const uint32_t *hw = reinterpret_cast<const uint32_t *>(hier);
+    s_arrive[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_qn[threadIdx.x] = 0;
+    if (threadIdx.x == 2) s_en = 0;
+    {
+        const uint32_t cnt = b0 < nInternal ? min(uint32_t(kFitBlock), nInternal - b0) : 0u;
+        for (uint32_t i = threadIdx.x; i < 3 * cnt; i += kFitBlock) s_hier[i] = __ldg(hw + 3 * size_t(b0) + i);
+        s_local[threadIdx.x] = threadIdx.x < cnt ? __ldg(local + b0 + threadIdx.x) : uint8_t(0);
+    }
+    __syncthreads();
+    // a fitted node reports to its parent: the second arrival makes the parent ready
+    auto report = [&](uint32_t node, uint32_t parent, int next) {
+        if (parent - b0 < uint32_t(kFitBlock) && s_local[parent - b0]) {
+            if (atomicAdd(&s_arrive[parent - b0], 1u) == 1u) s_queue[next][atomicAdd(&s_qn[next], 1u)] = parent;
+        } else {
+            s_exit[atomicAdd(&s_en, 1u)] = node;
+        }
+    };
+    const uint32_t slot = b0 + threadIdx.x;
+    if (slot < n) {
+        Box box;
+        uint32_t leafFlags = slot | RT_NODE_LEAF_FLAG;
+        // the 48-byte packed record k_rearrange_tris wrote next to the reference-format Primitive: same nine floats
+        // through three aligned 16-byte loads instead of ten 4-byte loads at stride 40
+        const float4 *q = reinterpret_cast<const float4 *>(packed + slot);
+        const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+        const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+        float mn[3], mx[3];
+        if (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) mn[k] = v[k], mx[k] = v[3 + k];
+            leafFlags |= RT_NODE_PROCEDURAL_FLAG;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
+                mx[k] = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
+                mn[k] = fminf(mn[k], mx[k] - 0.001f);  // AABB_Min_Padding
+            }
+        }
+        box = aabb_to_box(mn, mx);
+        const uint32_t node = nInternal + slot;
+        store_node(nodes, node, box, leafFlags, 1u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s_box[threadIdx.x][k] = box.c[k], s_box[threadIdx.x][3 + k] = box.h[k];
+        s_size[threadIdx.x] = 1;
+        if (n == 1) {
+            ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
+            ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
+        } else {
+            report(node, __ldg(hw + 3 * size_t(node)) & ~treelet::kCollapseBit, 0);
+        }
+    }
+    __syncthreads();
+    // one ready node: fit it from its children's shared boxes, publish its own, report to its parent
+    auto fit_ready = [&](uint32_t p, int next) {
+        const uint32_t *rec = s_hier + 3 * (p - b0);
+        const uint32_t up = rec[0] & ~treelet::kCollapseBit, l = rec[1], r = rec[2];
+        const uint32_t li = l >= nInternal ? l - nInternal - b0 : kFitBlock + l - b0;
+        const uint32_t ri = r >= nInternal ? r - nInternal - b0 : kFitBlock + r - b0;
+        Box bl, br, box;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bl.c[k] = s_box[li][k], bl.h[k] = s_box[li][3 + k], br.c[k] = s_box[ri][k], br.h[k] = s_box[ri][3 + k];
+        const uint32_t lc = s_size[li], rc = s_size[ri];
+        fit_merge_store(p, l, r, lc, rc, bl, br, nInternal, nodes, wide, ext, box);
+        const uint32_t pi = kFitBlock + p - b0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s_box[pi][k] = box.c[k], s_box[pi][3 + k] = box.h[k];
+        s_size[pi] = lc + rc;
+        if (p != 0) report(p, up, next);
+    };
+    // Rounds.  The number of ready nodes never grows (a node fitted in one round readies at most its one parent), so
+    // once a round fits in a warp the rest of the chain — typically ten more levels of one to thirty nodes — is run
+    // by warp 0 alone with warp barriers while the other warps wait once, instead of every warp paying two block
+    // barriers per level (ncu: the barrier was the top stall of this kernel).
+    int cur = 0;
+    for (; s_qn[cur] > 32; cur ^= 1) {  // block-uniform: s_qn[cur] is stable between the two barriers
+        if (threadIdx.x < s_qn[cur]) fit_ready(s_queue[cur][threadIdx.x], cur ^ 1);
+        __syncthreads();
+        if (threadIdx.x == 0) s_qn[cur] = 0;
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        for (;; cur ^= 1) {
+            const uint32_t q = s_qn[cur];
+            if (q == 0) break;
+            if (threadIdx.x < q) fit_ready(s_queue[cur][threadIdx.x], cur ^ 1);
+            __syncwarp();
+            if (threadIdx.x == 0) s_qn[cur] = 0;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // The few nodes whose parent's subtree crosses the block boundary go to a global exit list (k_fit_exits): climbing
+    // here would keep the whole block resident behind a handful of threads waiting on global atomics.
+    __shared__ uint32_t s_base;
+    const uint32_t en = s_en;
+    if (threadIdx.x == 0 && en) s_base = atomicAdd(&counters[nInternal], en);  // counters[n-1] is no node's counter
+    __syncthreads();
+    if (threadIdx.x < en) {
+        const uint32_t node = s_exit[threadIdx.x];
+        const uint32_t si = node >= nInternal ? node - nInternal - b0 : kFitBlock + node - b0;
+        exit_nodes[s_base + threadIdx.x] = node;
+        exit_sizes[s_base + threadIdx.x] = uint16_t(s_size[si]);
+    }
+}
+
+// Second half of k_fit_local: one thread per exit-list entry climbs through global memory exactly as k_fit does.
+__global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hierarchy_node *hier, uint32_t *counters, rt_aabb_node *nodes,
+                                                        rt_wide_node *wide, rt_ext_header *ext, const uint32_t *exit_nodes,
+                                                        const uint16_t *exit_sizes) {
+    const uint32_t nInternal = n - 1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= __ldcg(&counters[nInternal])) return;
+    const uint32_t *hw = reinterpret_cast<const uint32_t *>(hier);
+    uint32_t node = exit_nodes[i];
+    uint32_t count = exit_sizes[i];
+    Box box = load_node_box(nodes, node);
+    while (true) {
+        const uint32_t parent = __ldg(hw + 3 * size_t(node)) & ~treelet::kCollapseBit;
+        const uint32_t l = __ldg(hw + 3 * size_t(parent) + 1), r = __ldg(hw + 3 * size_t(parent) + 2);
+        __threadfence();
+        const uint32_t other = atomicAdd(&counters[parent], count);
+        if (other == 0) return;  // first to arrive: the sibling will fit the parent
+        __threadfence();
+        const bool isLeft = (l == node);
+        const Box sb = load_node_box(nodes, isLeft ? r : l);
+        fit_merge_store(parent, l, r, isLeft ? count : other, isLeft ? other : count, isLeft ? box : sb, isLeft ? sb : box, nInternal, nodes,
+                        wide, ext, box);
+        if (parent == 0) return;
+        count += other;
+        node = parent;
+    }
+}
+
 // BVH2 -> BVH4 for the traversal kernels.  Thread i opens node i's two children and then, twice, the internal slot
 // with the largest surface area (half-extent product sum), reading the child boxes straight from the BVH2 wide nodes.
 __global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide, uint32_t n_internal, rt_wide4_node *wide4) {
+    // the block's kThreads x 128-byte nodes leave through shared memory as one contiguous run of 16-byte stores; slot
+    // k of thread t sits at t * 8 + (k ^ (t & 7)) so that neither side has bank conflicts
+    __shared__ float4 s_out[kThreads * 8];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_internal) return;
     float4 c[4], h[4];  // {center, ref}, {half, -}
     int cnt = 2;
+    if (i < n_internal) {
     {
         const float4 *w = reinterpret_cast<const float4 *>(wide + i);
         const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
@@ -553,16 +781,26 @@ __global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide
         }
         cnt++;
     }
-    float4 *o = reinterpret_cast<float4 *>(wide4 + i);
+    float4 *o = s_out + threadIdx.x * 8;
+    const int sw = threadIdx.x & 7;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (k < cnt) {
-            o[2 * k] = c[k];
-            o[2 * k + 1] = make_float4(h[k].x, h[k].y, h[k].z, 0.0f);
+            o[(2 * k) ^ sw] = c[k];
+            o[(2 * k + 1) ^ sw] = make_float4(h[k].x, h[k].y, h[k].z, 0.0f);
         } else {
-            o[2 * k] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_WIDE4_EMPTY));
-            o[2 * k + 1] = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
+            o[(2 * k) ^ sw] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_WIDE4_EMPTY));
+            o[(2 * k + 1) ^ sw] = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
         }
+    }
+    }
+    __syncthreads();
+    const uint32_t b0 = blockIdx.x * blockDim.x;
+    const uint32_t valid = 8 * min(uint32_t(kThreads), n_internal - b0);
+    float4 *dst = reinterpret_cast<float4 *>(wide4 + b0);
+    for (uint32_t g = threadIdx.x; g < valid; g += kThreads) {
+        const uint32_t t = g >> 3, e = g & 7;
+        dst[g] = s_out[t * 8 + (e ^ (t & 7))];
     }
 }
 
@@ -807,11 +1045,12 @@ int sort_pairs(rt_context *ctx, uint8_t *scratch, const Layout &L, uint32_t n) {
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = pass * kRadixBits;
         k_radix_hist<<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, n, shift, sp.tiles_per_block, hist);
-        k_scan_hist<<<1, 1024, 0, ctx->stream>>>(hist, sp.blocks);
+        uint32_t *row_total = hist + size_t(kRadix) * sp.blocks;
+        k_scan_rows<<<kRadix, kSortThreads, 0, ctx->stream>>>(hist, sp.blocks, row_total);
         if (pass == 0)
-            k_radix_scatter<true><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, kout, vout);
+            k_radix_scatter<true><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, row_total, kout, vout);
         else
-            k_radix_scatter<false><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, kout, vout);
+            k_radix_scatter<false><<<sp.blocks, kSortThreads, 0, ctx->stream>>>(kin, vin, n, shift, sp.tiles_per_block, hist, row_total, kout, vout);
         ctx->launches += 3;
         kin = kout, vin = vout;
         if (kout == kB) kout = kC, vout = vC; else kout = kB, vout = vB;
@@ -905,6 +1144,8 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
     rt_hierarchy_node *hier = reinterpret_cast<rt_hierarchy_node *>(scratch + L.hier);
     uint32_t *sort_cache = reinterpret_cast<uint32_t *>(result + R.sort_cache);
     uint32_t *parents = reinterpret_cast<uint32_t *>(result + R.parents);
+    // one byte per internal node in the sort's dead ping-pong buffer (the sorted pairs end up in keysC / valsC)
+    uint8_t *fit_local = (!top && RT_FIT_LOCAL) ? scratch + L.keysB : nullptr;
     if (update) {
         k_invert_cache<<<grid, kThreads, 0, st>>>(sort_cache, n, perm);
         ctx->launches++;
@@ -922,7 +1163,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
         const uint32_t *sorted_codes = reinterpret_cast<uint32_t *>(scratch + L.keysC);
         RT_CUDA(cudaMemsetAsync(hier, 0, 12ull * (2ull * n - 1), st));
         if (n > 1) {
-            k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier);
+            k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier, fit_local);
             ctx->launches++;
         }
     }
@@ -952,7 +1193,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
                 RT_CUDA(cudaMemsetAsync(tl_base, 0, 4, st));
                 treelet::k_find_treelets<<<grid, kThreads, 0, st>>>(n, hier, packed, counters, tl_aabb, tl_base, min_tris);
                 treelet::k_treelet_reorder<<<rt_div_up(n / min_tris, treelet::kWarps), 32 * treelet::kWarps, 0, st>>>(n, hier, counters,
-                                                                                                                    tl_aabb, tl_base);
+                                                                                                                    tl_aabb, tl_base, fit_local);
                 ctx->launches += 2;
             }
         }
@@ -970,6 +1211,17 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
     } else {
         if (update)
             k_fit<false, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
+        else if (RT_FIT_LOCAL) {
+            // exit list in the sort's dead ping-pong buffers: node ids in valsB, subtree sizes (<= kFitBlock) behind the flags
+            uint32_t *exit_nodes = reinterpret_cast<uint32_t *>(scratch + L.valsB);
+            uint16_t *exit_sizes = reinterpret_cast<uint16_t *>(scratch + L.keysB + align_up(n, 256));
+            k_fit_local<<<rt_div_up(n, kFitBlock), kFitBlock, 0, st>>>(n, hier, counters, nodes, packed, wide, ext, fit_local, exit_nodes, exit_sizes);
+            if (n > 1) {
+                // every block leaves at least one and on average ~log2(kFitBlock) entries; n bounds it
+                k_fit_exits<<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, wide, ext, exit_nodes, exit_sizes);
+                ctx->launches++;
+            }
+        }
         else
             k_fit<false, false><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
     }

@@ -109,8 +109,11 @@ __global__ void __launch_bounds__(256) k_find_treelets(uint32_t n, const rt_hier
 
 // FL/TreeletReorder.hlsl:312-345: one warp per base treelet root; optimise, then climb while this warp is the second
 // child to arrive.
+// `local` (may be null): the per-node "subtree lies in one fit block" flags of k_hierarchy.  Re-forming a treelet
+// whose root is not local can move leaves from outside the block under one of its inner nodes, so those nodes lose the
+// flag; a treelet under a local root only permutes nodes and leaves of that block, and the flags stay true.
 __global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_hierarchy_node *hier, uint32_t *num_tris,
-                                                                 float *aabbs, const uint32_t *base) {
+                                                                 float *aabbs, const uint32_t *base, uint8_t *local) {
     __shared__ float s_cost[kWarps][kSubsets];
     __shared__ float s_box[kWarps][kFull][6];
     __shared__ uint32_t s_leaf[kWarps][8], s_int[kWarps][8];
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_
                 __stcg(hw + 3 * size_t(l), up);
                 __stcg(hw + 3 * size_t(r), up);
                 st_aabb(aabbs, nd, subset_box(mk & (kSubsets - 1)));
+                if (local != nullptr && nd != node && __ldcg(local + node) == 0) __stcg(local + nd, uint8_t(0));
             }
         }
 

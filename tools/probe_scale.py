@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--render", default="", help="comma list of icosphere subdivision levels to render at 1080p")
     ap.add_argument("--spp", type=int, default=4)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--flags", type=int, default=0, help="RT_BUILD_FLAG_* of the build probe (8 = PREFER_FAST_BUILD: no treelet pass)")
     args = ap.parse_args()
     import torch
 
@@ -44,13 +45,13 @@ def main():
         desc[0].index_buffer, desc[0].index_count, desc[0].index_format = ib.ptr, mesh.indices.size, 32
         desc[0].flags = T.GEOMETRY_FLAG_OPAQUE
         info = T.PrebuildInfo()
-        rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, 0, C.byref(info)))
+        rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, args.flags, C.byref(info)))
         scr, res = ctx.alloc(info.scratch_bytes), ctx.alloc(info.result_bytes)
         times = []
         for r in range(args.reps + 2):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, 0, scr.ptr, scr.nbytes, res.ptr, res.nbytes))
+            rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, args.flags, scr.ptr, scr.nbytes, res.ptr, res.nbytes))
             e1.record(stream)
             torch.cuda.synchronize()
             if r >= 2:
