@@ -253,8 +253,9 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
                                                                 int shift, uint32_t tiles_per_block, const uint32_t *offsets,
                                                                 const uint32_t *row_total, uint32_t *keys_out, uint32_t *vals_out) {
     __shared__ uint32_t warp_count[kSortWarps][kRadix];
-    __shared__ uint32_t base[kRadix];
+    __shared__ uint32_t base[kRadix], tile_start[kRadix], tile_count[kRadix];
     __shared__ uint32_t s_warp[kSortWarps];
+    __shared__ uint32_t s_key[kSortTile], s_val[kSortTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
         uint32_t unused;
@@ -269,17 +270,31 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
         for (int w = 0; w < kSortWarps; ++w) warp_count[w][threadIdx.x] = 0;
         __syncthreads();
         uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+        // all of the tile's loads are in flight before the first rank is computed (the ranking below synchronises the
+        // warp per item, which kept the compiler from hoisting them: ncu showed one exposed global load per item)
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) {
             const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
             const bool valid = i < n;
-            key[r] = valid ? keys_in[i] : 0xffffffffu;
-            val[r] = valid ? (IOTA ? uint32_t(i) : vals_in[i]) : 0u;
+            key[r] = valid ? __ldcs(keys_in + i) : 0xffffffffu;
+            val[r] = valid ? (IOTA ? uint32_t(i) : __ldcs(vals_in + i)) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
+            const bool valid = i < n;
             const uint32_t d = (key[r] >> shift) & (kRadix - 1);
-            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            // lanes holding the same digit, from one ballot per digit bit: MATCH.ANY resolves one distinct value at a
+            // time (~30 per warp here) and eight warps queue for it per scheduler — it was the kernel's bottleneck
+            unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int b = 0; b < kRadixBits; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
             rank[r] = 0;
             if (valid) {
-                const unsigned peers = __match_any_sync(active, d);
                 const int leader = __ffs(peers) - 1;
                 uint32_t prev = 0;
                 if (lane == leader) {
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
             __syncwarp();
         }
         __syncthreads();
-        {  // per-digit exclusive prefix over the warps of this tile; advance the running base
+        {  // per-digit exclusive prefix over the warps of this tile
             const int d = threadIdx.x;
             uint32_t off = 0;
 #pragma unroll
@@ -301,21 +316,41 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
                 warp_count[w][d] = off;
                 off += c;
             }
-            // base[d] is read by the scatter below and bumped afterwards: keep the old value in a register
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < kSortItems; ++r) {
-                const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
-                if (i < n) {
-                    const uint32_t dd = (key[r] >> shift) & (kRadix - 1);
-                    const uint32_t pos = base[dd] + warp_count[warp][dd] + rank[r];
-                    keys_out[pos] = key[r];
-                    vals_out[pos] = val[r];
-                }
-            }
-            __syncthreads();
-            base[d] += off;
+            // where digit d's run starts inside the tile once the tile is sorted by digit
+            uint32_t unused;
+            const uint32_t start = block_exclusive_scan_256(off, s_warp, unused);
+            tile_start[d] = start;
+            tile_count[d] = off;
         }
+        __syncthreads();
+        // The tile is first sorted by digit in shared memory, then written out position by position: neighbouring
+        // threads hold neighbours of one digit run, so each run leaves as contiguous, sector-filling stores.  Scattering
+        // straight from the ranking registers issued 4-byte writes to ~32 different sectors per warp instruction.
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
+            if (i < n) {
+                const uint32_t dd = (key[r] >> shift) & (kRadix - 1);
+                const uint32_t local = tile_start[dd] + warp_count[warp][dd] + rank[r];
+                s_key[local] = key[r];
+                s_val[local] = val[r];
+            }
+        }
+        __syncthreads();
+        const uint32_t tile_valid = uint32_t(min(uint64_t(kSortTile), uint64_t(n) - tile_begin));
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            const uint32_t idx = r * kSortThreads + threadIdx.x;
+            if (idx < tile_valid) {
+                const uint32_t k = s_key[idx];
+                const uint32_t dd = (k >> shift) & (kRadix - 1);
+                const uint32_t pos = base[dd] + (idx - tile_start[dd]);
+                keys_out[pos] = k;
+                vals_out[pos] = s_val[idx];
+            }
+        }
+        __syncthreads();
+        base[threadIdx.x] += tile_count[threadIdx.x];
         __syncthreads();
     }
 }
@@ -609,6 +644,17 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
     s_arrive[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_qn[threadIdx.x] = 0;
     if (threadIdx.x == 2) s_en = 0;
+    // every global load of the block is issued before the first barrier: one DRAM latency, not two
+    const uint32_t slot = b0 + threadIdx.x;
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    uint32_t leafParent = 0;
+    if (slot < n) {
+        // the 48-byte packed record k_rearrange_tris wrote next to the reference-format Primitive: same nine floats
+        // through three aligned 16-byte loads instead of ten 4-byte loads at stride 40
+        const float4 *q = reinterpret_cast<const float4 *>(packed + slot);
+        q0 = q[0], q1 = q[1], q2 = q[2];
+        if (n > 1) leafParent = __ldg(hw + 3 * size_t(nInternal + slot)) & ~treelet::kCollapseBit;
+    }
     {
         const uint32_t cnt = b0 < nInternal ? min(uint32_t(kFitBlock), nInternal - b0) : 0u;
         for (uint32_t i = threadIdx.x; i < 3 * cnt; i += kFitBlock) s_hier[i] = __ldg(hw + 3 * size_t(b0) + i);
@@ -623,14 +669,9 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
             s_exit[atomicAdd(&s_en, 1u)] = node;
         }
     };
-    const uint32_t slot = b0 + threadIdx.x;
     if (slot < n) {
         Box box;
         uint32_t leafFlags = slot | RT_NODE_LEAF_FLAG;
-        // the 48-byte packed record k_rearrange_tris wrote next to the reference-format Primitive: same nine floats
-        // through three aligned 16-byte loads instead of ten 4-byte loads at stride 40
-        const float4 *q = reinterpret_cast<const float4 *>(packed + slot);
-        const float4 q0 = q[0], q1 = q[1], q2 = q[2];
         const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
         float mn[3], mx[3];
         if (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL) {
@@ -655,7 +696,7 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
             ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
             ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
         } else {
-            report(node, __ldg(hw + 3 * size_t(node)) & ~treelet::kCollapseBit, 0);
+            report(node, leafParent, 0);
         }
     }
     __syncthreads();
