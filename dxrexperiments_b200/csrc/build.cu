@@ -630,14 +630,14 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
     // shared index of a node: leaf -> slot - b0 in [0, B); internal -> B + index - b0 in [B, 2B)
     __shared__ float s_box[2 * kFitBlock][6];
     __shared__ uint32_t s_size[2 * kFitBlock];
-    __shared__ uint32_t s_arrive[kFitBlock];
+    __shared__ uint32_t s_arrive[kFitBlock];     // children fitted so far; 2 = this node was fitted by this block
     __shared__ uint32_t s_queue[2][kFitBlock];  // ready internal nodes of this / the next round
-    __shared__ uint32_t s_exit[2 * kFitBlock];   // fitted nodes whose parent is not local
-    __shared__ uint32_t s_qn[2], s_en;
+    __shared__ uint32_t s_exit[kFitBlock];       // fitted nodes whose parent is not local (roots of disjoint subtrees)
+    __shared__ uint32_t s_qn[2], s_en, s_base;
     // the hierarchy records and flags of this block's internal nodes (a local node's index lies in [b0, b0 + B)),
-    // fetched once and coalesced: the rounds below then run without a dependent global load
+    // fetched once and coalesced: the rounds below run out of shared memory alone
     __shared__ uint32_t s_hier[3 * kFitBlock];
-    __shared__ uint8_t s_local[kFitBlock];
+    __shared__ uint8_t s_local[kFitBlock], s_proc[kFitBlock];
     const uint32_t b0 = blockIdx.x * kFitBlock;
     const uint32_t nInternal = n - 1;
     const uint32_t *hw = reinterpret_cast<const uint32_t *>(hier);
@@ -646,6 +646,8 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
     if (threadIdx.x == 2) s_en = 0;
     // every global load of the block is issued before the first barrier: one DRAM latency, not two
     const uint32_t slot = b0 + threadIdx.x;
+    const uint32_t cntLeaf = min(uint32_t(kFitBlock), n - b0);
+    const uint32_t cntInt = b0 < nInternal ? min(uint32_t(kFitBlock), nInternal - b0) : 0u;
     float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
     uint32_t leafParent = 0;
     if (slot < n) {
@@ -655,11 +657,8 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
         q0 = q[0], q1 = q[1], q2 = q[2];
         if (n > 1) leafParent = __ldg(hw + 3 * size_t(nInternal + slot)) & ~treelet::kCollapseBit;
     }
-    {
-        const uint32_t cnt = b0 < nInternal ? min(uint32_t(kFitBlock), nInternal - b0) : 0u;
-        for (uint32_t i = threadIdx.x; i < 3 * cnt; i += kFitBlock) s_hier[i] = __ldg(hw + 3 * size_t(b0) + i);
-        s_local[threadIdx.x] = threadIdx.x < cnt ? __ldg(local + b0 + threadIdx.x) : uint8_t(0);
-    }
+    for (uint32_t i = threadIdx.x; i < 3 * cntInt; i += kFitBlock) s_hier[i] = __ldg(hw + 3 * size_t(b0) + i);
+    s_local[threadIdx.x] = threadIdx.x < cntInt ? __ldg(local + b0 + threadIdx.x) : uint8_t(0);
     __syncthreads();
     // a fitted node reports to its parent: the second arrival makes the parent ready
     auto report = [&](uint32_t node, uint32_t parent, int next) {
@@ -669,15 +668,20 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
             s_exit[atomicAdd(&s_en, 1u)] = node;
         }
     };
+    auto shared_index = [&](uint32_t node) { return node >= nInternal ? node - nInternal - b0 : kFitBlock + node - b0; };
+    auto load_box = [&](uint32_t si) {
+        Box b;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) b.c[k] = s_box[si][k], b.h[k] = s_box[si][3 + k];
+        return b;
+    };
     if (slot < n) {
-        Box box;
-        uint32_t leafFlags = slot | RT_NODE_LEAF_FLAG;
         const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
         float mn[3], mx[3];
-        if (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL) {
+        const bool procedural = (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL) != 0;
+        if (procedural) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) mn[k] = v[k], mx[k] = v[3 + k];
-            leafFlags |= RT_NODE_PROCEDURAL_FLAG;
         } else {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -686,41 +690,44 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
                 mn[k] = fminf(mn[k], mx[k] - 0.001f);  // AABB_Min_Padding
             }
         }
-        box = aabb_to_box(mn, mx);
-        const uint32_t node = nInternal + slot;
-        store_node(nodes, node, box, leafFlags, 1u);
+        const Box box = aabb_to_box(mn, mx);
 #pragma unroll
         for (int k = 0; k < 3; ++k) s_box[threadIdx.x][k] = box.c[k], s_box[threadIdx.x][3 + k] = box.h[k];
         s_size[threadIdx.x] = 1;
+        s_proc[threadIdx.x] = procedural ? 1 : 0;
         if (n == 1) {
             ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
             ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
         } else {
-            report(node, leafParent, 0);
+            report(nInternal + slot, leafParent, 0);
         }
     }
     __syncthreads();
-    // one ready node: fit it from its children's shared boxes, publish its own, report to its parent
+    // One ready node: its box from its children's shared boxes (GetBoxFromChildBoxes, FL/RayTracingHelper.hlsli:297-307),
+    // published in shared memory; nothing is stored to global memory here.
     auto fit_ready = [&](uint32_t p, int next) {
         const uint32_t *rec = s_hier + 3 * (p - b0);
-        const uint32_t up = rec[0] & ~treelet::kCollapseBit, l = rec[1], r = rec[2];
-        const uint32_t li = l >= nInternal ? l - nInternal - b0 : kFitBlock + l - b0;
-        const uint32_t ri = r >= nInternal ? r - nInternal - b0 : kFitBlock + r - b0;
-        Box bl, br, box;
+        const uint32_t up = rec[0] & ~treelet::kCollapseBit;
+        uint32_t li = shared_index(rec[1]), ri = shared_index(rec[2]);
+        if (s_size[ri] < s_size[li]) {  // operand order of the reference's min/max: smaller subtree first
+            const uint32_t t = li; li = ri; ri = t;
+        }
+        const Box bl = load_box(li), br = load_box(ri);
+        float mn[3], mx[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) bl.c[k] = s_box[li][k], bl.h[k] = s_box[li][3 + k], br.c[k] = s_box[ri][k], br.h[k] = s_box[ri][3 + k];
-        const uint32_t lc = s_size[li], rc = s_size[ri];
-        fit_merge_store(p, l, r, lc, rc, bl, br, nInternal, nodes, wide, ext, box);
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(bl.c[k] - bl.h[k], br.c[k] - br.h[k]);
+            mx[k] = fmaxf(bl.c[k] + bl.h[k], br.c[k] + br.h[k]);
+        }
+        const Box box = aabb_to_box(mn, mx);
         const uint32_t pi = kFitBlock + p - b0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) s_box[pi][k] = box.c[k], s_box[pi][3 + k] = box.h[k];
-        s_size[pi] = lc + rc;
+        s_size[pi] = s_size[li] + s_size[ri];
         if (p != 0) report(p, up, next);
     };
     // Rounds.  The number of ready nodes never grows (a node fitted in one round readies at most its one parent), so
-    // once a round fits in a warp the rest of the chain — typically ten more levels of one to thirty nodes — is run
-    // by warp 0 alone with warp barriers while the other warps wait once, instead of every warp paying two block
-    // barriers per level (ncu: the barrier was the top stall of this kernel).
+    // once a round fits in a warp the rest of the chain is run by warp 0 alone with warp barriers.
     int cur = 0;
     for (; s_qn[cur] > 32; cur ^= 1) {  // block-uniform: s_qn[cur] is stable between the two barriers
         if (threadIdx.x < s_qn[cur]) fit_ready(s_queue[cur][threadIdx.x], cur ^ 1);
@@ -739,17 +746,67 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
         }
     }
     __syncthreads();
-    // The few nodes whose parent's subtree crosses the block boundary go to a global exit list (k_fit_exits): climbing
-    // here would keep the whole block resident behind a handful of threads waiting on global atomics.
-    __shared__ uint32_t s_base;
+    // Write-out.  Everything this block fitted is described by shared memory (boxes, subtree sizes, hierarchy records),
+    // so the reference nodes and the wide nodes leave as contiguous runs of 16-byte stores — the rounds above issued
+    // none.  (One thread storing its own node's 32 + 64 bytes touched 32 sectors per warp instruction.)
     const uint32_t en = s_en;
     if (threadIdx.x == 0 && en) s_base = atomicAdd(&counters[nInternal], en);  // counters[n-1] is no node's counter
+    {   // leaves: {center, slot | flags}, {halfDim, 1}
+        float4 *dst = reinterpret_cast<float4 *>(nodes + nInternal + b0);
+        for (uint32_t g = threadIdx.x; g < 2 * cntLeaf; g += kFitBlock) {
+            const uint32_t e = g >> 1;
+            const float *bx = s_box[e];
+            if (g & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(1u));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float((b0 + e) | RT_NODE_LEAF_FLAG | (s_proc[e] ? RT_NODE_PROCEDURAL_FLAG : 0u)));
+        }
+    }
+    // child order of a fitted node: smaller subtree on the left; ties keep the Karras order
+    auto children = [&](uint32_t e, uint32_t &l, uint32_t &r, uint32_t &li, uint32_t &ri) {
+        l = s_hier[3 * e + 1], r = s_hier[3 * e + 2];
+        li = shared_index(l), ri = shared_index(r);
+        if (s_size[ri] < s_size[li]) {
+            uint32_t t = l; l = r; r = t;
+            t = li; li = ri; ri = t;
+        }
+    };
+    {   // internal reference nodes: {center, left}, {halfDim, right}
+        float4 *dst = reinterpret_cast<float4 *>(nodes + b0);
+        for (uint32_t g = threadIdx.x; g < 2 * cntInt; g += kFitBlock) {
+            const uint32_t e = g >> 1;
+            if (s_arrive[e] != 2) continue;
+            uint32_t l, r, li, ri;
+            children(e, l, r, li, ri);
+            const float *bx = s_box[kFitBlock + e];
+            if (g & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(r));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float(l & 0x00ffffffu));
+        }
+    }
+    {   // wide nodes: both child boxes and child references
+        float4 *dst = reinterpret_cast<float4 *>(wide + b0);
+        for (uint32_t g = threadIdx.x; g < 4 * cntInt; g += kFitBlock) {
+            const uint32_t e = g >> 2, part = g & 3;
+            if (s_arrive[e] != 2) continue;
+            uint32_t l, r, li, ri;
+            children(e, l, r, li, ri);
+            const float *bx = s_box[part < 2 ? li : ri];
+            const uint32_t lref = l >= nInternal ? (RT_NODE_LEAF_FLAG | (l - nInternal)) : l;
+            const uint32_t rref = r >= nInternal ? (RT_NODE_LEAF_FLAG | (r - nInternal)) : r;
+            const uint32_t w = part == 0 ? lref : (part == 1 ? rref : 0u);
+            if (part & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(w));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float(w));
+        }
+    }
+    if (b0 == 0 && nInternal > 0 && threadIdx.x == 0 && s_arrive[0] == 2) {  // the whole tree was local
+        const float *bx = s_box[kFitBlock];
+        ext->root_center[0] = bx[0], ext->root_center[1] = bx[1], ext->root_center[2] = bx[2];
+        ext->root_half[0] = bx[3], ext->root_half[1] = bx[4], ext->root_half[2] = bx[5];
+    }
     __syncthreads();
+    // the nodes whose parent's subtree crosses the block boundary continue in k_fit_exits
     if (threadIdx.x < en) {
         const uint32_t node = s_exit[threadIdx.x];
-        const uint32_t si = node >= nInternal ? node - nInternal - b0 : kFitBlock + node - b0;
         exit_nodes[s_base + threadIdx.x] = node;
-        exit_sizes[s_base + threadIdx.x] = uint16_t(s_size[si]);
+        exit_sizes[s_base + threadIdx.x] = uint16_t(s_size[shared_index(node)]);
     }
 }
 
