@@ -360,11 +360,14 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
 struct KarrasDev {
     const uint32_t *codes;
     int n;
+    // The reference's delta: clz(ca ^ cb), or clz(a ^ b) + 31 when the codes are equal.  Evaluated as one 64-bit clz
+    // of {code, index}: equal for differing codes, the reference's value + 1 for equal ones — a strictly monotone map
+    // (differing codes give <= 31, equal ones >= 39), and the hierarchy only ever compares these values.
     __device__ __forceinline__ int lcp(int a, int b) const {
         if (a < 0 || b < 0 || a >= n || b >= n) return -1;
-        uint32_t ca = codes[a], cb = codes[b];
-        if (ca != cb) return __clz(int(ca ^ cb));
-        return __clz(a ^ b) + 31;
+        const unsigned long long ka = (static_cast<unsigned long long>(__ldg(codes + a)) << 32) | uint32_t(a);
+        const unsigned long long kb = (static_cast<unsigned long long>(__ldg(codes + b)) << 32) | uint32_t(b);
+        return __clzll(static_cast<long long>(ka ^ kb));
     }
 };
 
