@@ -20,10 +20,10 @@
 #include "trace.cuh"
 
 #ifndef RT_FETCH_THRESHOLD
-#define RT_FETCH_THRESHOLD 12
+#define RT_FETCH_THRESHOLD 24
 #endif
 #ifndef RT_LEAF_THRESHOLD
-#define RT_LEAF_THRESHOLD 8
+#define RT_LEAF_THRESHOLD 4
 #endif
 constexpr int kFetchThreshold = RT_FETCH_THRESHOLD;  // refill when >= this many lanes are idle
 constexpr int kLeafThreshold = RT_LEAF_THRESHOLD;    // run a leaf phase when >= this many lanes hold a leaf
