@@ -116,10 +116,11 @@ __device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, un
 
 // ------------------------------------------------------------------------------------------------ K1
 #ifndef RT_PRIMARY_WIDE4
-#define RT_PRIMARY_WIDE4 0  // coherent camera rays: BVH2 wins on L1-resident scenes (5.2 vs 4.2 Grays/s on C2), the 4-wide nodes only beyond ~1 M triangles (2.3 vs 2.1)
+#define RT_PRIMARY_WIDE4 1  // coherent camera rays over the 4-wide nodes at 6 blocks/SM (80 registers): with the treelet-optimised tree
+                           // 5.84 vs 5.40 Grays/s on C2, 3.29 vs 2.79 on 1.3 M triangles (before the treelet pass the BVH2 loop won on C2)
 #endif
 #ifndef RT_PRIMARY_MIN_BLOCKS
-#define RT_PRIMARY_MIN_BLOCKS 8
+#define RT_PRIMARY_MIN_BLOCKS 6
 #endif
 template <bool STATS>
 __global__ void __launch_bounds__(kBlock, RT_PRIMARY_MIN_BLOCKS) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status,

@@ -46,7 +46,8 @@ struct TraceSink {  // where results go; only the members of the kernel's MODE a
 #define RT_PERSIST_MIN_BLOCKS 8
 #endif
 #ifndef RT_POP_CULL
-#define RT_POP_CULL 1
+#define RT_POP_CULL 0  // 1: keep each pushed node's entry distance and drop it at pop time behind a committed hit.  With the
+                       // treelet-optimised tree the second stack costs more than the skipped visits save (A/B: -6 % on secondary rays)
 #endif
 #ifndef RT_PERSIST_WIDE4
 #define RT_PERSIST_WIDE4 1  // 1: traverse the 4-wide nodes (rt_wide4_node); 0: the BVH2 wide nodes (A/B measurements)
@@ -73,7 +74,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
 
     uint32_t stack[RT_STACK_SIZE];
 #if RT_PERSIST_WIDE4
-    uint32_t stackT[MODE == 1 ? 1 : RT_STACK_SIZE];  // entry distance of each pushed node (culled at pop)
+    uint32_t stackT[(MODE == 1 || !RT_POP_CULL) ? 1 : RT_STACK_SIZE];  // entry distance of each pushed node (culled at pop)
 #endif
     // per-lane ray state
     bool alive = false;
@@ -241,7 +242,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             if (alive && !atLeaf) {
 #if RT_PERSIST_WIDE4
                 // one 128-byte node = four child boxes (two BVH2 levels per dependent fetch)
-                ref = wide4_step<MODE != 1>(nodes, ref, cur, tCur, stack, stackT, sp, status);
+                ref = wide4_step<(MODE != 1) && RT_POP_CULL>(nodes, ref, cur, tCur, stack, stackT, sp, status);
 #else
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
