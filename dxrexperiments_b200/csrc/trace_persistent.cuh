@@ -242,7 +242,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             if (alive && !atLeaf) {
 #if RT_PERSIST_WIDE4
                 // one 128-byte node = four child boxes (two BVH2 levels per dependent fetch)
-                ref = wide4_step<(MODE != 1) && RT_POP_CULL>(nodes, ref, cur, tCur, stack, stackT, sp, status);
+                ref = wide4_step<(MODE != 1) && RT_POP_CULL, MODE != 1>(nodes, ref, cur, tCur, stack, stackT, sp, status);
 #else
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
