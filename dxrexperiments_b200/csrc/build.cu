@@ -360,14 +360,11 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
 struct KarrasDev {
     const uint32_t *codes;
     int n;
-    // The reference's delta: clz(ca ^ cb), or clz(a ^ b) + 31 when the codes are equal.  Evaluated as one 64-bit clz
-    // of {code, index}: equal for differing codes, the reference's value + 1 for equal ones — a strictly monotone map
-    // (differing codes give <= 31, equal ones >= 39), and the hierarchy only ever compares these values.
     __device__ __forceinline__ int lcp(int a, int b) const {
         if (a < 0 || b < 0 || a >= n || b >= n) return -1;
-        const unsigned long long ka = (static_cast<unsigned long long>(__ldg(codes + a)) << 32) | uint32_t(a);
-        const unsigned long long kb = (static_cast<unsigned long long>(__ldg(codes + b)) << 32) | uint32_t(b);
-        return __clzll(static_cast<long long>(ka ^ kb));
+        uint32_t ca = codes[a], cb = codes[b];
+        if (ca != cb) return __clz(int(ca ^ cb));
+        return __clz(a ^ b) + 31;
     }
 };
 
@@ -600,8 +597,57 @@ __global__ void __launch_bounds__(kThreads) k_fit(uint32_t n, const rt_hierarchy
 // memory.  Nodes whose parent is not local — about log2(n) per block — leave through an exit list and finish with
 // k_fit's global climb.  Results (reference nodes, wide nodes, child order) are those of k_fit, bit for bit: the child
 // order depends only on the subtree sizes and the Karras order, never on who arrives first.
+// The 4-wide node of `parent` from its two (already ordered) children and, through the children's finished wide nodes,
+// its grandchildren: open, twice, the internal child with the largest surface area — k_collapse4's rule.  Used by
+// k_fit_exits, where every subtree below `parent` is complete and published (fence + counter) before we got here.
+__device__ __forceinline__ void collapse4_store(uint32_t parent, const Box &bl, uint32_t lref, const Box &br, uint32_t rref,
+                                                const rt_wide_node *wide, rt_wide4_node *wide4) {
+    float4 c[4], h[4];
+    int cnt = 2;
+    c[0] = make_float4(bl.c[0], bl.c[1], bl.c[2], __uint_as_float(lref)), h[0] = make_float4(bl.h[0], bl.h[1], bl.h[2], 0.0f);
+    c[1] = make_float4(br.c[0], br.c[1], br.c[2], __uint_as_float(rref)), h[1] = make_float4(br.h[0], br.h[1], br.h[2], 0.0f);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        int best = -1;
+        float bestArea = -1.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt && !(__float_as_uint(c[k].w) & RT_NODE_LEAF_FLAG)) {
+                const float a = h[k].x * h[k].y + h[k].y * h[k].z + h[k].z * h[k].x;
+                if (a > bestArea) bestArea = a, best = k;
+            }
+        }
+        if (best < 0) break;
+        float4 bc = c[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (k == best) bc = c[k];
+        const float4 *w = reinterpret_cast<const float4 *>(wide + __float_as_uint(bc.w));
+        const float4 w0 = __ldcg(w), w1 = __ldcg(w + 1), w2 = __ldcg(w + 2), w3 = __ldcg(w + 3);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k == best) c[k] = w0, h[k] = w1;
+            if (k == cnt) c[k] = make_float4(w2.x, w2.y, w2.z, w1.w), h[k] = w3;
+        }
+        cnt++;
+    }
+    float4 *o = reinterpret_cast<float4 *>(wide4 + parent);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < cnt) {
+            o[2 * k] = c[k];
+            o[2 * k + 1] = make_float4(h[k].x, h[k].y, h[k].z, 0.0f);
+        } else {
+            o[2 * k] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_WIDE4_EMPTY));
+            o[2 * k + 1] = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
+        }
+    }
+}
+
+template <bool WIDE4 = false>
 __device__ __forceinline__ void fit_merge_store(uint32_t parent, uint32_t l, uint32_t r, uint32_t lc, uint32_t rc, Box bl, Box br,
-                                                uint32_t nInternal, rt_aabb_node *nodes, rt_wide_node *wide, rt_ext_header *ext, Box &box) {
+                                                uint32_t nInternal, rt_aabb_node *nodes, rt_wide_node *wide, rt_ext_header *ext, Box &box,
+                                                rt_wide4_node *wide4 = nullptr) {
     if (rc < lc) {  // smaller subtree on the left; ties keep the Karras order
         uint32_t t = l; l = r; r = t;
         Box tb = bl; bl = br; br = tb;
@@ -621,17 +667,22 @@ __device__ __forceinline__ void fit_merge_store(uint32_t parent, uint32_t l, uin
     w[1] = make_float4(bl.h[0], bl.h[1], bl.h[2], __uint_as_float(rref));
     w[2] = make_float4(br.c[0], br.c[1], br.c[2], 0.0f);
     w[3] = make_float4(br.h[0], br.h[1], br.h[2], 0.0f);
+    if (WIDE4) collapse4_store(parent, bl, lref, br, rref, wide, wide4);
     if (parent == 0) {
         ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
         ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
     }
 }
 
+constexpr size_t kFitLocalDynSmem = sizeof(float) * 6 * 2 * kFitBlock + sizeof(uint32_t) * 4 * kFitBlock;
 __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hierarchy_node *hier, uint32_t *counters, rt_aabb_node *nodes,
-                                                         const rt_packed_tri *packed, rt_wide_node *wide, rt_ext_header *ext,
-                                                         const uint8_t *local, uint32_t *exit_nodes, uint16_t *exit_sizes) {
+                                                         const rt_packed_tri *packed, rt_wide_node *wide, rt_wide4_node *wide4,
+                                                         rt_ext_header *ext, const uint8_t *local, uint32_t *exit_nodes,
+                                                         uint16_t *exit_sizes) {
     // shared index of a node: leaf -> slot - b0 in [0, B); internal -> B + index - b0 in [B, 2B)
-    __shared__ float s_box[2 * kFitBlock][6];
+    extern __shared__ __align__(16) uint8_t s_dyn[];  // kFitLocalDynSmem bytes: the boxes and the 4-wide child lists
+    float(*s_box)[6] = reinterpret_cast<float(*)[6]>(s_dyn);
+    uint32_t(*s_w4)[4] = reinterpret_cast<uint32_t(*)[4]>(s_dyn + sizeof(float) * 6 * 2 * kFitBlock);
     __shared__ uint32_t s_size[2 * kFitBlock];
     __shared__ uint32_t s_arrive[kFitBlock];     // children fitted so far; 2 = this node was fitted by this block
     __shared__ uint32_t s_queue[2][kFitBlock];  // ready internal nodes of this / the next round
@@ -799,6 +850,61 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
             else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float(w));
         }
     }
+    // 4-wide traversal nodes of the fitted nodes (what k_collapse4 derives from the wide nodes, here straight from
+    // shared memory): open, twice, the internal child with the largest surface area; the child lists first ...
+    if (threadIdx.x < cntInt && s_arrive[threadIdx.x] == 2) {
+        uint32_t ref[4] = {RT_WIDE4_EMPTY, RT_WIDE4_EMPTY, RT_WIDE4_EMPTY, RT_WIDE4_EMPTY}, si[4] = {0, 0, 0, 0};
+        int cnt = 2;
+        auto to_ref = [&](uint32_t node) { return node >= nInternal ? (RT_NODE_LEAF_FLAG | (node - nInternal)) : node; };
+        {
+            uint32_t l, r, li, ri;
+            children(threadIdx.x, l, r, li, ri);
+            ref[0] = to_ref(l), ref[1] = to_ref(r), si[0] = li, si[1] = ri;
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            int best = -1;
+            float bestArea = -1.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < cnt && !(ref[k] & RT_NODE_LEAF_FLAG)) {
+                    const float *h = s_box[si[k]] + 3;
+                    const float a = h[0] * h[1] + h[1] * h[2] + h[2] * h[0];
+                    if (a > bestArea) bestArea = a, best = k;
+                }
+            }
+            if (best < 0) break;
+            uint32_t opened = ref[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (k == best) opened = ref[k];
+            uint32_t l, r, li, ri;
+            children(opened - b0, l, r, li, ri);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k == best) ref[k] = to_ref(l), si[k] = li;
+                if (k == cnt) ref[k] = to_ref(r), si[k] = ri;
+            }
+            cnt++;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_w4[threadIdx.x][k] = ref[k];
+    }
+    __syncthreads();
+    {   // ... then the 128-byte nodes as one contiguous run
+        float4 *dst = reinterpret_cast<float4 *>(wide4 + b0);
+        for (uint32_t g = threadIdx.x; g < 8 * cntInt; g += kFitBlock) {
+            const uint32_t e = g >> 3, part = g & 7;
+            if (s_arrive[e] != 2) continue;
+            const uint32_t ref = s_w4[e][part >> 1];
+            if (ref == RT_WIDE4_EMPTY) {
+                dst[g] = (part & 1) ? make_float4(-1.0f, -1.0f, -1.0f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_WIDE4_EMPTY));
+            } else {
+                const float *bx = s_box[(ref & RT_NODE_LEAF_FLAG) ? (ref & 0x00ffffffu) - b0 : kFitBlock + ref - b0];
+                dst[g] = (part & 1) ? make_float4(bx[3], bx[4], bx[5], 0.0f) : make_float4(bx[0], bx[1], bx[2], __uint_as_float(ref));
+            }
+        }
+    }
     if (b0 == 0 && nInternal > 0 && threadIdx.x == 0 && s_arrive[0] == 2) {  // the whole tree was local
         const float *bx = s_box[kFitBlock];
         ext->root_center[0] = bx[0], ext->root_center[1] = bx[1], ext->root_center[2] = bx[2];
@@ -815,8 +921,8 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
 
 // Second half of k_fit_local: one thread per exit-list entry climbs through global memory exactly as k_fit does.
 __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hierarchy_node *hier, uint32_t *counters, rt_aabb_node *nodes,
-                                                        rt_wide_node *wide, rt_ext_header *ext, const uint32_t *exit_nodes,
-                                                        const uint16_t *exit_sizes) {
+                                                        rt_wide_node *wide, rt_wide4_node *wide4, rt_ext_header *ext,
+                                                        const uint32_t *exit_nodes, const uint16_t *exit_sizes) {
     const uint32_t nInternal = n - 1;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= __ldcg(&counters[nInternal])) return;
@@ -833,8 +939,8 @@ __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hie
         __threadfence();
         const bool isLeft = (l == node);
         const Box sb = load_node_box(nodes, isLeft ? r : l);
-        fit_merge_store(parent, l, r, isLeft ? count : other, isLeft ? other : count, isLeft ? box : sb, isLeft ? sb : box, nInternal, nodes,
-                        wide, ext, box);
+        fit_merge_store<true>(parent, l, r, isLeft ? count : other, isLeft ? other : count, isLeft ? box : sb, isLeft ? sb : box, nInternal,
+                              nodes, wide, ext, box, wide4);
         if (parent == 0) return;
         count += other;
         node = parent;
@@ -843,14 +949,20 @@ __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hie
 
 // BVH2 -> BVH4 for the traversal kernels.  Thread i opens node i's two children and then, twice, the internal slot
 // with the largest surface area (half-extent product sum), reading the child boxes straight from the BVH2 wide nodes.
-__global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide, uint32_t n_internal, rt_wide4_node *wide4) {
+// `done` (may be null): done[i] != 0 = node i's 4-wide node was already written by k_fit_local.
+__global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide, uint32_t n_internal, rt_wide4_node *wide4,
+                                                        const uint8_t *done) {
+    __shared__ uint8_t s_done[kThreads];
     // the block's kThreads x 128-byte nodes leave through shared memory as one contiguous run of 16-byte stores; slot
     // k of thread t sits at t * 8 + (k ^ (t & 7)) so that neither side has bank conflicts
     __shared__ float4 s_out[kThreads * 8];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float4 c[4], h[4];  // {center, ref}, {half, -}
     int cnt = 2;
-    if (i < n_internal) {
+    const bool skip = i < n_internal && done != nullptr && done[i] != 0;
+    if (__syncthreads_and(skip || i >= n_internal)) return;  // nothing left to do in this block (the common case after k_fit_local)
+    s_done[threadIdx.x] = skip ? 1 : 0;
+    if (i < n_internal && !skip) {
     {
         const float4 *w = reinterpret_cast<const float4 *>(wide + i);
         const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
@@ -901,7 +1013,7 @@ __global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide
     float4 *dst = reinterpret_cast<float4 *>(wide4 + b0);
     for (uint32_t g = threadIdx.x; g < valid; g += kThreads) {
         const uint32_t t = g >> 3, e = g & 7;
-        dst[g] = s_out[t * 8 + (e ^ (t & 7))];
+        if (!s_done[t]) dst[g] = s_out[t * 8 + (e ^ (t & 7))];
     }
 }
 
@@ -1304,6 +1416,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
         }
     }
     RT_CUDA(cudaMemsetAsync(counters, 0, 4ull * n, st));
+    bool fitted_locally = false;
     if (top) {
         if (update)
             k_fit<true, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, nullptr, boxes, perm, wide, ext, parents);
@@ -1316,10 +1429,15 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
             // exit list in the sort's dead ping-pong buffers: node ids in valsB, subtree sizes (<= kFitBlock) behind the flags
             uint32_t *exit_nodes = reinterpret_cast<uint32_t *>(scratch + L.valsB);
             uint16_t *exit_sizes = reinterpret_cast<uint16_t *>(scratch + L.keysB + align_up(n, 256));
-            k_fit_local<<<rt_div_up(n, kFitBlock), kFitBlock, 0, st>>>(n, hier, counters, nodes, packed, wide, ext, fit_local, exit_nodes, exit_sizes);
+            RT_CUDA(cudaFuncSetAttribute(k_fit_local, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFitLocalDynSmem)));  // per device
+            k_fit_local<<<rt_div_up(n, kFitBlock), kFitBlock, kFitLocalDynSmem, st>>>(n, hier, counters, nodes, packed, wide,
+                                                                                      reinterpret_cast<rt_wide4_node *>(result + R.wide4), ext,
+                                                                                      fit_local, exit_nodes, exit_sizes);
+            fitted_locally = true;
             if (n > 1) {
                 // every block leaves at least one and on average ~log2(kFitBlock) entries; n bounds it
-                k_fit_exits<<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, wide, ext, exit_nodes, exit_sizes);
+                k_fit_exits<<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, wide, reinterpret_cast<rt_wide4_node *>(result + R.wide4), ext,
+                                                       exit_nodes, exit_sizes);
                 ctx->launches++;
             }
         }
@@ -1327,8 +1445,8 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
             k_fit<false, false><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
     }
     ctx->launches++;
-    if (n > 1) {
-        k_collapse4<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(wide, n - 1, reinterpret_cast<rt_wide4_node *>(result + R.wide4));
+    if (n > 1 && !fitted_locally) {  // k_fit_local / k_fit_exits write the 4-wide nodes themselves
+        k_collapse4<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(wide, n - 1, reinterpret_cast<rt_wide4_node *>(result + R.wide4), nullptr);
         ctx->launches++;
     }
     RT_LAUNCH_CHECK();
