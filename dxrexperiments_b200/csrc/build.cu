@@ -371,7 +371,7 @@ struct KarrasDev {
 // `local` (may be null): local[i] = 1 when every leaf under internal node i lies in one kFitBlock-aligned block of
 // sorted slots — such a node's whole subtree is fitted inside one thread block's shared memory by k_fit_local.
 #ifndef RT_FIT_BLOCK
-#define RT_FIT_BLOCK 512
+#define RT_FIT_BLOCK 256
 #endif
 constexpr int kFitBlock = RT_FIT_BLOCK;
 #ifndef RT_FIT_LOCAL
