@@ -132,3 +132,43 @@ def test_build_argument_errors(ctx, rt):
     d[0].index_format = 8
     assert rt.lib.rt_blas_build(ctx.handle, d, 1, 0, scratch.ptr, scratch.nbytes, result.ptr, result.nbytes) == -1
     assert b"index_format" in rt.lib.rt_last_error()
+
+
+@pytest.mark.parametrize("n", [255, 256, 257, 511, 512, 513, 767, 1023, 1025, 4097, 65537])
+def test_blob_bit_exact_around_fit_block_boundaries(n, ctx, orc):
+    """k_fit_local fits 256 sorted slots per thread block in shared memory and hands the boundary-crossing nodes to
+    k_fit_exits: sizes at, just below and just above multiples of the block size, for 0 and 1 treelet passes."""
+    mesh = scenes.triangle_soup(n, seed=1000 + n, extent=20.0, edge=1.5)
+    for flags in (T.BUILD_FLAG_PREFER_FAST_BUILD, 0):
+        ref = orc.Blas.from_mesh(mesh, build_flags=flags)
+        acc = ctx.build_blas_from_mesh(mesh, build_flags=flags)
+        np.testing.assert_array_equal(acc.blob(), ref.blob())
+
+
+@pytest.mark.parametrize("kind", ["identical", "two_clusters", "line"])
+def test_blob_bit_exact_degenerate_distributions(kind, ctx, orc):
+    """Trees the Morton order makes maximally unbalanced or tie-dominated: every triangle identical (all codes equal:
+    the hierarchy is decided by the index tie rule alone), two tight clusters far apart, triangles on a line."""
+    n = 3000
+    mesh = scenes.triangle_soup(n, seed=77, extent=1.0, edge=0.2)
+    pos = mesh.vertices["position"]
+    if kind == "identical":
+        pos[:] = np.tile(pos[:3], (n, 1))
+    elif kind == "two_clusters":
+        pos[: 3 * (n // 2)] *= np.float32(1e-3)
+        pos[3 * (n // 2):] = pos[3 * (n // 2):] * np.float32(1e-3) + np.float32(1000.0)
+    else:
+        pos[:, 1] = 0.0
+        pos[:, 2] = 0.0
+    for flags in (T.BUILD_FLAG_PREFER_FAST_BUILD, 0, T.BUILD_FLAG_PREFER_FAST_TRACE):
+        ref = orc.Blas.from_mesh(mesh, build_flags=flags)
+        acc = ctx.build_blas_from_mesh(mesh, build_flags=flags)
+        np.testing.assert_array_equal(acc.blob(), ref.blob())
+    # and the traversal section built next to it answers like the oracle's tree
+    otlas = orc.Tlas([orc.Blas.from_mesh(mesh)], [scenes.IDENTITY_3X4])
+    gtlas = ctx.build_tlas([ctx.build_blas_from_mesh(mesh)], [scenes.IDENTITY_3X4])
+    from helpers import random_rays
+    lo, hi = pos.min(axis=0) - 1.0, pos.max(axis=0) + 1.0
+    rays = random_rays(20000, seed=9, lo=lo, hi=hi)
+    ho, hg = otlas.trace(rays, threads=8), ctx.trace(gtlas, rays)
+    np.testing.assert_array_equal(hg["t"], ho["t"])
