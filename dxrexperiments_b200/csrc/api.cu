@@ -51,6 +51,9 @@ int rt_context_destroy(rt_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws.base) cudaFree(ctx->ws.base);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->status) cudaFree(ctx->status);
     if (ctx->hit_programs) cudaFree(ctx->hit_programs);
     if (ctx->ray_counts) cudaFree(ctx->ray_counts);

@@ -114,6 +114,9 @@ __device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, un
     }
 }
 
+#ifndef RT_OVERLAP_SHADOW
+#define RT_OVERLAP_SHADOW 1
+#endif
 // ------------------------------------------------------------------------------------------------ K1
 #ifndef RT_PRIMARY_WIDE4
 #define RT_PRIMARY_WIDE4 1  // coherent camera rays over the 4-wide nodes at 6 blocks/SM (80 registers): with the treelet-optimised tree
@@ -668,17 +671,36 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     k_shade_primary<<<rt_div_up(P, kBlock), kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
                                                              ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
+    // The depth-0 shadow wave and the secondary-ray chain (trace -> shade -> depth-1 shadow wave) both depend only on
+    // k_shade_primary and meet again in k_resolve.  Outside the instrumented / per-stage-timed modes the shadow wave
+    // runs on a side stream: its persistent blocks move in as the other kernels' blocks drain, so the tails of the
+    // trace kernels (8-20 % of each launch with warps running out of rays, ncu sm__warps_active) overlap.
+    const bool overlap = RT_OVERLAP_SHADOW && !timing && !stats;
+    if (overlap) {
+        if (!ctx->side_stream) {
+            RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        RT_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        RT_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    }
     if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.plane, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
     else k_trace_persistent<0><<<pgrid<0>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.plane, TraceSink{ws.secHitA, ws.secRec, nullptr, nullptr}, ctx->status, ws.counters + 4, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
-    if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
-    else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, TraceSink{nullptr, nullptr, ws.vis0, nullptr}, ctx->status, ws.counters + 5, 0, 0xFF);
+    {
+        cudaStream_t s0 = overlap ? ctx->side_stream : st;
+        if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, s0>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
+        else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, s0>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, TraceSink{nullptr, nullptr, ws.vis0, nullptr}, ctx->status, ws.counters + 5, 0, 0xFF);
+        if (overlap) RT_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    }
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
     k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
     else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
+    if (overlap) RT_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;
     RT_LAUNCH_CHECK();
