@@ -200,10 +200,8 @@ __device__ __forceinline__ uint32_t ref_of(uint32_t key, uint32_t r0, uint32_t r
 // hits near-to-far with a 5-exchange network on integer keys, return the nearest and push the others farthest
 // first.  WITH_T: also record each pushed node's entry distance so that it can be dropped at pop time.
 #ifndef RT_SHADOW_UNSORTED
-#define RT_SHADOW_UNSORTED 1  // any-hit rays take the children in slot order: no sorting network (A/B: shadow rays 3.44 -> 4.55 Grays/s on C2)
-#endif
-#ifndef RT_CLOSEST_PARTIAL
-#define RT_CLOSEST_PARTIAL 0  // closest-hit rays: nearest child first, the other hits pushed in slot order instead of fully sorted
+#define RT_SHADOW_UNSORTED 1  // any-hit rays take the children in slot order: no sorting network (A/B: shadow rays 3.44 -> 4.55 Grays/s on C2;
+                              // reverse slot order, area-ordered slots and "nearest first, rest unsorted" for closest hits all measured worse)
 #endif
 template <bool WITH_T, bool SORTED = true>
 __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint32_t ref, const RayPre &cur, float tCur, uint32_t *stack,
@@ -229,8 +227,7 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
         const bool v[4] = {b0, b1, b2 && r2 != RT_WIDE4_EMPTY, b3 && r3 != RT_WIDE4_EMPTY};
         const uint32_t r[4] = {r0, r1, r2, r3};
 #pragma unroll
-        for (int kk = 3; kk >= 0; --kk) {
-            const int k = RT_SHADOW_UNSORTED == 2 ? 3 - kk : kk;
+        for (int k = 3; k >= 0; --k) {
             if (v[k]) {
                 if (first != RT_SENTINEL) {
                     if (sp < RT_STACK_SIZE) stack[sp++] = first;
@@ -246,22 +243,6 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
     // NaN (a zero direction passes every box, in the reference too), hence the explicit check
     uint32_t k0 = hit_key(b0, t0, 0), k1 = hit_key(b1, t1, 1), k2 = hit_key(b2 && r2 != RT_WIDE4_EMPTY, t2, 2),
              k3 = hit_key(b3 && r3 != RT_WIDE4_EMPTY, t3, 3);
-#if RT_CLOSEST_PARTIAL
-    if (!WITH_T) {
-        const uint32_t kmin = min(min(k0, k1), min(k2, k3));
-        if (kmin == 0xffffffffu) return RT_SENTINEL;
-        const uint32_t ks[4] = {k0, k1, k2, k3};
-        const uint32_t rs[4] = {r0, r1, r2, r3};
-#pragma unroll
-        for (int k = 3; k >= 0; --k) {
-            if (ks[k] != 0xffffffffu && ks[k] != kmin) {
-                if (sp < RT_STACK_SIZE) stack[sp++] = rs[k];
-                else atomicOr(status, 1u);
-            }
-        }
-        return ref_of(kmin, r0, r1, r2, r3);
-    }
-#endif
     key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
     if (k0 == 0xffffffffu) return RT_SENTINEL;
     if (k1 != 0xffffffffu) {  // push the other hits, farthest first
