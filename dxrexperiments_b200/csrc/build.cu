@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
         if (threadIdx.x == 0) s_qn[cur] = 0;
         __syncthreads();
     }
+    __syncthreads();  // every warp has read the exit condition before warp 0 starts rewriting the queue counters
     if (threadIdx.x < 32) {
         for (;; cur ^= 1) {
             const uint32_t q = s_qn[cur];
