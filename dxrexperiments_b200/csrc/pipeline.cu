@@ -114,6 +114,9 @@ __device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, un
     }
 }
 
+#ifndef RT_DISPATCH_BANDS
+#define RT_DISPATCH_BANDS 1
+#endif
 #ifndef RT_OVERLAP_SHADOW
 #define RT_OVERLAP_SHADOW 1
 #endif
@@ -567,7 +570,8 @@ __global__ void k_scale(float *buf, uint64_t n, float s) {
 }
 
 // ------------------------------------------------------------------------------------------------ host
-int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws) {
+// `part` of `parts`: the dispatch may run as several independent pixel bands, each with its own workspace of P pixels.
+int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws, uint32_t part = 0, uint32_t parts = 1) {
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) {
         uint64_t r = o;
@@ -578,17 +582,18 @@ int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws) {
                    oS1 = take(16 * P), oS2 = take(16 * P), oS3 = take(4 * P), oSQ0 = take(32 * 4 * P), oV0 = take(4 * P),
                    oSec = take(32 * 2 * P), oSecH = take(16 * 2 * P), oSecR = take(4 * 2 * P), oSecS = take(4 * 2 * P),
                    oT0 = take(16 * 2 * P), oT1 = take(16 * 2 * P), oT2 = take(16 * 2 * P), oSQ1 = take(32 * 4 * P), oV1 = take(4 * P);
-    if (ctx->ws.bytes < o) {
+    const uint64_t one = align_up(o, 256);
+    if (ctx->ws.bytes < one * parts) {
         if (ctx->ws.base) {
-            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));  // every dispatch joins its helper streams into ctx->stream
             RT_CUDA(cudaFree(ctx->ws.base));
             ctx->ws.base = nullptr;
             ctx->ws.bytes = 0;
         }
-        RT_CUDA(cudaMalloc(&ctx->ws.base, o));
-        ctx->ws.bytes = o;
+        RT_CUDA(cudaMalloc(&ctx->ws.base, one * parts));
+        ctx->ws.bytes = one * parts;
     }
-    uint8_t *b = static_cast<uint8_t *>(ctx->ws.base);
+    uint8_t *b = static_cast<uint8_t *>(ctx->ws.base) + one * part;
     ws.plane = uint32_t(P);
     ws.hitA = (float4 *)(b + oHitA), ws.hitRec = (uint32_t *)(b + oHitRec), ws.counters = (uint32_t *)(b + oCnt);
     ws.slotInfo = (uint4 *)(b + oSlot), ws.S0 = (float4 *)(b + oS0), ws.S1 = (float4 *)(b + oS1), ws.S2 = (float4 *)(b + oS2);
@@ -625,6 +630,9 @@ int upload_records(rt_program *prog) {
 
 extern "C" {
 
+static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, const WS &ws, cudaStream_t st, cudaStream_t side,
+                         cudaEvent_t ev_fork, cudaEvent_t ev_join);
+
 int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t x1,
                             uint32_t y1) {
     RT_REQUIRE(ctx && prog && prog->ctx == ctx, "context/program");
@@ -646,19 +654,70 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     L.jitterScale = realtime ? 10.0f : 30.0f;  // S/ProgressiveRaytracing.hlsl:26, S/RealtimeRaytracing.hlsl:34
     L.realtime = realtime ? 1u : 0u;
     L.shadowsPerHit = (!realtime && L.f.options.showAmbientOcclusionOnly) ? 4u : 2u;
-    const uint64_t P = uint64_t(L.rw) * L.rh;
-    WS ws;
-    int rc = ensure_workspace(ctx, P, ws);
+    int rc = upload_records(prog);
     if (rc) return rc;
-    rc = upload_records(prog);
-    if (rc) return rc;
-
-    cudaStream_t st = ctx->stream;
     const bool timing = ctx->timing;
     if (timing && !ctx->ev_ready) {
         for (auto &e : ctx->ev) RT_CUDA(cudaEventCreate(&e));
         ctx->ev_ready = true;
     }
+    // Two pixel bands, each a complete wavefront pipeline on its own stream (forked from and joined back into the
+    // context's stream, so the call stays stream-ordered for the caller): whenever one band's kernel runs out of rays —
+    // persistent kernels end with 8-20 % of their warps idle, k_primary leaves ~30 % of its warp slots unused — blocks of
+    // the other band's kernels move in.  Bands touch disjoint pixels, so the image is bit-identical to the one-band run.
+    // Instrumented and stage-timed dispatches, and small regions, run as one band.
+    const bool banded = RT_DISPATCH_BANDS && !timing && !ctx->collect_stats && L.rh >= 128 && uint64_t(L.rw) * L.rh >= (1u << 18);
+    if (banded) {
+        if (!ctx->band_stream) {
+            RT_CUDA(cudaStreamCreateWithFlags(&ctx->band_stream, cudaStreamNonBlocking));
+            RT_CUDA(cudaStreamCreateWithFlags(&ctx->band_side_stream, cudaStreamNonBlocking));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_band_fork, cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_band_join, cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
+        }
+        const uint32_t h0 = ((L.rh / 2 + 3) / 4) * 4;  // band boundary on a tile row
+        const uint64_t Pmax = uint64_t(L.rw) * std::max(h0, L.rh - h0);
+        Launch La = L, Lb = L;
+        La.rh = h0;
+        Lb.y0 = L.y0 + h0, Lb.rh = L.rh - h0;
+        WS wa, wb;
+        rc = ensure_workspace(ctx, Pmax, wa, 0, 2);
+        if (rc) return rc;
+        rc = ensure_workspace(ctx, Pmax, wb, 1, 2);
+        if (rc) return rc;
+        RT_CUDA(cudaEventRecord(ctx->ev_band_fork, ctx->stream));
+        RT_CUDA(cudaStreamWaitEvent(ctx->band_stream, ctx->ev_band_fork, 0));
+        if (!ctx->side_stream) {
+            RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        rc = dispatch_band(ctx, prog, La, wa, ctx->stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join);
+        if (rc) return rc;
+        rc = dispatch_band(ctx, prog, Lb, wb, ctx->band_stream, ctx->band_side_stream, ctx->ev_fork2, ctx->ev_join2);
+        if (rc) return rc;
+        RT_CUDA(cudaEventRecord(ctx->ev_band_join, ctx->band_stream));
+        RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_band_join, 0));
+        return RT_OK;
+    }
+    const uint64_t P = uint64_t(L.rw) * L.rh;
+    WS ws;
+    rc = ensure_workspace(ctx, P, ws);
+    if (rc) return rc;
+    if (!timing && !ctx->collect_stats && !ctx->side_stream) {
+        RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    return dispatch_band(ctx, prog, L, ws, ctx->stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join);
+}
+
+// One band of a dispatch: the seven wavefront stages on `st`, the depth-0 shadow wave on `side`.
+static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, const WS &ws, cudaStream_t st, cudaStream_t side,
+                         cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+    const bool timing = ctx->timing;
+    const uint64_t P = uint64_t(L.rw) * L.rh;
     RT_CUDA(cudaMemsetAsync(ws.counters, 0, 256, st));
     const uint32_t tiles = ((L.rw + 7) / 8) * ((L.rh + 3) / 4);
     const int qgrid = ctx->num_sms * 16;
@@ -675,24 +734,19 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     // k_shade_primary and meet again in k_resolve.  Outside the instrumented / per-stage-timed modes the shadow wave
     // runs on a side stream: its persistent blocks move in as the other kernels' blocks drain, so the tails of the
     // trace kernels (8-20 % of each launch with warps running out of rays, ncu sm__warps_active) overlap.
-    const bool overlap = RT_OVERLAP_SHADOW && !timing && !stats;
+    const bool overlap = RT_OVERLAP_SHADOW && !timing && !stats && side != nullptr;
     if (overlap) {
-        if (!ctx->side_stream) {
-            RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-        }
-        RT_CUDA(cudaEventRecord(ctx->ev_fork, st));
-        RT_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        RT_CUDA(cudaEventRecord(ev_fork, st));
+        RT_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
     }
     if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.plane, ws.secHitA, ws.secRec, nullptr, ctx->status, sSec);
     else k_trace_persistent<0><<<pgrid<0>(ctx), 128, 0, st>>>(ctx->tlas, ws.secQ, ws.counters, 2, ws.plane, TraceSink{ws.secHitA, ws.secRec, nullptr, nullptr}, ctx->status, ws.counters + 4, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[3], st));
     {
-        cudaStream_t s0 = overlap ? ctx->side_stream : st;
+        cudaStream_t s0 = overlap ? side : st;
         if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, s0>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, nullptr, nullptr, ws.vis0, ctx->status, sShadow);
         else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, s0>>>(ctx->tlas, ws.shadowQ0, ws.counters, L.shadowsPerHit, ws.plane, TraceSink{nullptr, nullptr, ws.vis0, nullptr}, ctx->status, ws.counters + 5, 0, 0xFF);
-        if (overlap) RT_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        if (overlap) RT_CUDA(cudaEventRecord(ev_join, side));
     }
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
     k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
@@ -700,7 +754,7 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
     else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
-    if (overlap) RT_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (overlap) RT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;
     RT_LAUNCH_CHECK();
