@@ -51,10 +51,13 @@ int rt_context_destroy(rt_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws.base) cudaFree(ctx->ws.base);
-    for (cudaStream_t q : {ctx->band_stream, ctx->band_side_stream})
-        if (q) cudaStreamDestroy(q);
-    for (cudaEvent_t e : {ctx->ev_band_fork, ctx->ev_band_join, ctx->ev_fork2, ctx->ev_join2})
-        if (e) cudaEventDestroy(e);
+    for (auto &b : ctx->band_streams)
+        for (cudaStream_t q : b)
+            if (q) cudaStreamDestroy(q);
+    for (auto &b : ctx->band_events)
+        for (cudaEvent_t e : b)
+            if (e) cudaEventDestroy(e);
+    if (ctx->ev_band_fork) cudaEventDestroy(ctx->ev_band_fork);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

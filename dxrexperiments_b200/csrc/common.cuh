@@ -43,6 +43,7 @@ void rt_set_error(const char *fmt, ...);
 // ---------------------------------------------------------------------------------------------
 // context
 
+#define RT_MAX_BANDS 8
 struct rt_workspace {  // wavefront queues, grown on demand (pipeline.cu)
     void *base = nullptr;
     uint64_t bytes = 0;
@@ -63,8 +64,10 @@ struct rt_context {
     rt_workspace ws;
     cudaStream_t side_stream = nullptr;  // shadow depth-0 wave of a dispatch, overlapped with the secondary-ray chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaStream_t band_stream = nullptr, band_side_stream = nullptr;  // second pixel band of a dispatch and its shadow wave
-    cudaEvent_t ev_band_fork = nullptr, ev_band_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    // pixel bands 1.. of a dispatch (band 0 runs on `stream` / `side_stream`): {main, shadow-wave} streams, {fork, join, band-join} events
+    cudaStream_t band_streams[RT_MAX_BANDS][2] = {};
+    cudaEvent_t band_events[RT_MAX_BANDS][3] = {};
+    cudaEvent_t ev_band_fork = nullptr;
     uint32_t *status = nullptr;          // device word: bit0 = traversal stack overflow, bit1 = procedural primitives reached by a triangles-only dispatch
     rt_hit_group_programs *hit_programs = nullptr;  // device copy of the table rt_trace_rays_hit_groups was last given
     unsigned long long *ray_counts = nullptr;  // device u64[32]: [0..2] rays traced; [8..12], [16..20], [24..28] rt_trace_stats of the primary / secondary / shadow stages

@@ -115,7 +115,7 @@ __device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, un
 }
 
 #ifndef RT_DISPATCH_BANDS
-#define RT_DISPATCH_BANDS 1
+#define RT_DISPATCH_BANDS 2  // pixel bands per dispatch (1 = off, at most RT_MAX_BANDS)
 #endif
 #ifndef RT_OVERLAP_SHADOW
 #define RT_OVERLAP_SHADOW 1
@@ -661,44 +661,46 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
         for (auto &e : ctx->ev) RT_CUDA(cudaEventCreate(&e));
         ctx->ev_ready = true;
     }
-    // Two pixel bands, each a complete wavefront pipeline on its own stream (forked from and joined back into the
+    // Pixel bands, each a complete wavefront pipeline on its own stream (forked from and joined back into the
     // context's stream, so the call stays stream-ordered for the caller): whenever one band's kernel runs out of rays —
     // persistent kernels end with 8-20 % of their warps idle, k_primary leaves ~30 % of its warp slots unused — blocks of
     // the other band's kernels move in.  Bands touch disjoint pixels, so the image is bit-identical to the one-band run.
     // Instrumented and stage-timed dispatches, and small regions, run as one band.
-    const bool banded = RT_DISPATCH_BANDS && !timing && !ctx->collect_stats && L.rh >= 128 && uint64_t(L.rw) * L.rh >= (1u << 18);
-    if (banded) {
-        if (!ctx->band_stream) {
-            RT_CUDA(cudaStreamCreateWithFlags(&ctx->band_stream, cudaStreamNonBlocking));
-            RT_CUDA(cudaStreamCreateWithFlags(&ctx->band_side_stream, cudaStreamNonBlocking));
-            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_band_fork, cudaEventDisableTiming));
-            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_band_join, cudaEventDisableTiming));
-            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
-            RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
-        }
-        const uint32_t h0 = ((L.rh / 2 + 3) / 4) * 4;  // band boundary on a tile row
-        const uint64_t Pmax = uint64_t(L.rw) * std::max(h0, L.rh - h0);
-        Launch La = L, Lb = L;
-        La.rh = h0;
-        Lb.y0 = L.y0 + h0, Lb.rh = L.rh - h0;
-        WS wa, wb;
-        rc = ensure_workspace(ctx, Pmax, wa, 0, 2);
-        if (rc) return rc;
-        rc = ensure_workspace(ctx, Pmax, wb, 1, 2);
-        if (rc) return rc;
-        RT_CUDA(cudaEventRecord(ctx->ev_band_fork, ctx->stream));
-        RT_CUDA(cudaStreamWaitEvent(ctx->band_stream, ctx->ev_band_fork, 0));
+    const uint32_t bands = (!timing && !ctx->collect_stats && uint64_t(L.rw) * L.rh >= (1u << 18)) ? std::min<uint32_t>(RT_DISPATCH_BANDS, L.rh / 64) : 1u;
+    if (bands > 1) {
         if (!ctx->side_stream) {
             RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
             RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
             RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         }
-        rc = dispatch_band(ctx, prog, La, wa, ctx->stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join);
-        if (rc) return rc;
-        rc = dispatch_band(ctx, prog, Lb, wb, ctx->band_stream, ctx->band_side_stream, ctx->ev_fork2, ctx->ev_join2);
-        if (rc) return rc;
-        RT_CUDA(cudaEventRecord(ctx->ev_band_join, ctx->band_stream));
-        RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_band_join, 0));
+        if (!ctx->ev_band_fork) RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_band_fork, cudaEventDisableTiming));
+        for (uint32_t k = 1; k < bands; ++k) {
+            if (ctx->band_streams[k][0]) continue;
+            for (auto &q : ctx->band_streams[k]) RT_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            for (auto &e : ctx->band_events[k]) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        // band boundaries on tile rows
+        uint32_t y[RT_MAX_BANDS + 1];
+        for (uint32_t k = 0; k <= bands; ++k) y[k] = k == bands ? L.rh : uint32_t((uint64_t(L.rh) * k / bands + 3) / 4 * 4);
+        uint64_t Pmax = 0;
+        for (uint32_t k = 0; k < bands; ++k) Pmax = std::max<uint64_t>(Pmax, uint64_t(L.rw) * (y[k + 1] - y[k]));
+        RT_CUDA(cudaEventRecord(ctx->ev_band_fork, ctx->stream));
+        for (uint32_t k = 0; k < bands; ++k) {
+            Launch Lk = L;
+            Lk.y0 = L.y0 + y[k], Lk.rh = y[k + 1] - y[k];
+            WS wk;
+            rc = ensure_workspace(ctx, Pmax, wk, k, bands);
+            if (rc) return rc;
+            if (k == 0) {
+                rc = dispatch_band(ctx, prog, Lk, wk, ctx->stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join);
+            } else {
+                RT_CUDA(cudaStreamWaitEvent(ctx->band_streams[k][0], ctx->ev_band_fork, 0));
+                rc = dispatch_band(ctx, prog, Lk, wk, ctx->band_streams[k][0], ctx->band_streams[k][1], ctx->band_events[k][0], ctx->band_events[k][1]);
+                if (rc == RT_OK) RT_CUDA(cudaEventRecord(ctx->band_events[k][2], ctx->band_streams[k][0]));
+            }
+            if (rc) return rc;
+        }
+        for (uint32_t k = 1; k < bands; ++k) RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->band_events[k][2], 0));
         return RT_OK;
     }
     const uint64_t P = uint64_t(L.rw) * L.rh;
