@@ -384,20 +384,22 @@ __global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, u
     int d = k.lcp(idx, idx + 1) - k.lcp(idx, idx - 1);
     d = min(max(d, -1), 1);
     int minPrefix = k.lcp(idx, idx - d);
-    long long maxLength = 2;  // 64-bit: idx + maxLength*d must not wrap for large n
+    // 32-bit is enough: n < 2^24 (rt_blas_build), and the search leaves the range — and stops — before maxLength
+    // passes 2^27, so idx +- maxLength never wraps
+    int maxLength = 2;
     while (true) {
-        long long j = (long long)idx + maxLength * d;
-        int p = (j < 0 || j >= n) ? -1 : k.lcp(idx, int(j));
+        const int j = idx + maxLength * d;
+        const int p = k.lcp(idx, j);  // -1 outside [0, n)
         if (!(p > minPrefix)) break;
         maxLength *= 4;
     }
-    long long length = 0;
-    for (long long t = maxLength / 2; t > 0; t /= 2) {
-        long long j = (long long)idx + (length + t) * d;
-        int p = (j < 0 || j >= n) ? -1 : k.lcp(idx, int(j));
+    int length = 0;
+    for (int t = maxLength / 2; t > 0; t /= 2) {
+        const int j = idx + (length + t) * d;
+        const int p = k.lcp(idx, j);
         if (p > minPrefix) length += t;
     }
-    int j = idx + int(length) * d;
+    int j = idx + length * d;
     int first = min(idx, j), last = max(idx, j);
     // FindSplit
     int commonPrefix = k.lcp(first, last);
