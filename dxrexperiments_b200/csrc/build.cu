@@ -952,20 +952,14 @@ __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hie
 
 // BVH2 -> BVH4 for the traversal kernels.  Thread i opens node i's two children and then, twice, the internal slot
 // with the largest surface area (half-extent product sum), reading the child boxes straight from the BVH2 wide nodes.
-// `done` (may be null): done[i] != 0 = node i's 4-wide node was already written by k_fit_local.
-__global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide, uint32_t n_internal, rt_wide4_node *wide4,
-                                                        const uint8_t *done) {
-    __shared__ uint8_t s_done[kThreads];
+__global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide, uint32_t n_internal, rt_wide4_node *wide4) {
     // the block's kThreads x 128-byte nodes leave through shared memory as one contiguous run of 16-byte stores; slot
     // k of thread t sits at t * 8 + (k ^ (t & 7)) so that neither side has bank conflicts
     __shared__ float4 s_out[kThreads * 8];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float4 c[4], h[4];  // {center, ref}, {half, -}
     int cnt = 2;
-    const bool skip = i < n_internal && done != nullptr && done[i] != 0;
-    if (__syncthreads_and(skip || i >= n_internal)) return;  // nothing left to do in this block (the common case after k_fit_local)
-    s_done[threadIdx.x] = skip ? 1 : 0;
-    if (i < n_internal && !skip) {
+    if (i < n_internal) {
     {
         const float4 *w = reinterpret_cast<const float4 *>(wide + i);
         const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
@@ -1016,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads) k_collapse4(const rt_wide_node *wide
     float4 *dst = reinterpret_cast<float4 *>(wide4 + b0);
     for (uint32_t g = threadIdx.x; g < valid; g += kThreads) {
         const uint32_t t = g >> 3, e = g & 7;
-        if (!s_done[t]) dst[g] = s_out[t * 8 + (e ^ (t & 7))];
+        dst[g] = s_out[t * 8 + (e ^ (t & 7))];
     }
 }
 
@@ -1449,7 +1443,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
     }
     ctx->launches++;
     if (n > 1 && !fitted_locally) {  // k_fit_local / k_fit_exits write the 4-wide nodes themselves
-        k_collapse4<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(wide, n - 1, reinterpret_cast<rt_wide4_node *>(result + R.wide4), nullptr);
+        k_collapse4<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(wide, n - 1, reinterpret_cast<rt_wide4_node *>(result + R.wide4));
         ctx->launches++;
     }
     RT_LAUNCH_CHECK();
