@@ -164,3 +164,27 @@ def test_sample_sharded_accumulation_world2_gloo(tmp_path):
                         "--master-port", "29731", str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "MAXREL" in r.stdout
+
+
+def test_python_constants_match_the_c_header():
+    """The ctypes mirror (dxrexperiments_b200/types.py) and include/rt_types.h must not drift apart: every enum value the
+    Python side names is parsed out of the header and compared."""
+    text = open(os.path.join(ROOT, "include", "rt_types.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    header = {}
+    for name, val in re.findall(r"\b(RT_[A-Z0-9_]+)\s*=\s*(0x[0-9A-Fa-f]+|\d+)", text):
+        header[name] = int(val, 0)
+    for name, val in re.findall(r"#define\s+(RT_[A-Z0-9_]+)\s+(0x[0-9A-Fa-f]+|\d+)[uU]?\b", text):
+        header[name] = int(val, 0)
+    from dxrexperiments_b200 import types as T
+    checked = 0
+    for py_name in dir(T):
+        c_name = "RT_" + py_name
+        if c_name in header and isinstance(getattr(T, py_name), int):
+            assert getattr(T, py_name) == header[c_name], (py_name, getattr(T, py_name), header[c_name])
+            checked += 1
+    assert checked >= 30, checked
+    assert T.PROCEDURAL_FLAG == header["RT_NODE_PROCEDURAL_FLAG"] and T.LEAF_FLAG == header["RT_NODE_LEAF_FLAG"]
+    assert T.PRIMITIVE_TYPE_PROCEDURAL == header["RT_PRIMITIVE_TYPE_PROCEDURAL"]
+    import ctypes as C
+    assert C.sizeof(T.GeometryDesc) == 48  # the `type` field took the place of padding: the ABI size did not move
