@@ -470,8 +470,10 @@ def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
                 "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes/ray (48 + 64*n_int + 48*n_leaf over the BVH2 visit counts of the same rays, "
                         "SURVEY 8d) x rays per launch / CUDA-event launch time.  The traversal structure is L1/L2-resident, so "
-                        "DRAM traffic (`traffic`, ncu) is far below the algorithmic bytes and the kernel's real bound is the L1 "
-                        "data pipe (profiles/)"}
+                        "DRAM traffic (`traffic`, ncu) is far below the algorithmic bytes — which is also why frac can exceed 1: "
+                        "those bytes are served by L1/L2, not HBM — and the kernel's real bound is instruction issue at 13-20 of 32 "
+                        "lanes active (profiles/r1_ncu_final.md).  Stage times are measured with the dispatch in its sequential, "
+                        "stage-timed mode; `value` is measured with the stages of two pixel bands overlapped (DESIGN 4.2)"}
     return roofline, stages
 
 
