@@ -1423,7 +1423,9 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
         if (update)
             k_fit<false, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, sp, nullptr, perm, wide, ext, parents);
         else if (RT_FIT_LOCAL) {
-            // exit list in the sort's dead ping-pong buffers: node ids in valsB, subtree sizes (<= kFitBlock) behind the flags
+            // exit list in the sort's dead ping-pong buffers: node ids in valsB, subtree sizes (<= kFitBlock) behind the flags.
+            // keysB holds 4n bytes; flags take n, the sizes 2 x (exit entries <= n) after a 256-byte round-up, and a build of
+            // n <= kFitBlock primitives fits in one block and leaves no entries — so the 3n + 255 bytes used fit for every n
             uint32_t *exit_nodes = reinterpret_cast<uint32_t *>(scratch + L.valsB);
             uint16_t *exit_sizes = reinterpret_cast<uint16_t *>(scratch + L.keysB + align_up(n, 256));
             RT_CUDA(cudaFuncSetAttribute(k_fit_local, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFitLocalDynSmem)));  // per device
