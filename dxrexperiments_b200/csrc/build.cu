@@ -1075,12 +1075,14 @@ __device__ void invert_affine(const float *t, float *o) {
 }
 
 // FL/TopLevelLoadAABBs.hlsli:58-100 fused with FL/CalculateSceneAABBFromBVHs.hlsl:16-40.
-__global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_desc *descs, uint32_t n, rt_aabb_node *boxes,
-                                                             rt_bvh_metadata *md, uint32_t *aabb_enc, rt_ext_header *tlas_ext) {
+// `ptrs` != nullptr: D3D12_ELEMENTS_LAYOUT_ARRAY_OF_POINTERS — element i is *ptrs[i] (FL/TopLevelLoadAABBs.hlsli:38-49).
+__global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_desc *descs, const rt_instance_desc *const *ptrs, uint32_t n,
+                                                             rt_aabb_node *boxes, rt_bvh_metadata *md, uint32_t *aabb_enc,
+                                                             rt_ext_header *tlas_ext) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float smn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, smx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     if (i < n) {
-        rt_instance_desc d = descs[i];
+        rt_instance_desc d = ptrs ? *ptrs[i] : descs[i];
         const uint8_t *blas = reinterpret_cast<const uint8_t *>(uintptr_t(d.blas));
         const rt_aabb_node *root = reinterpret_cast<const rt_aabb_node *>(blas + 16);
         // a TLAS over a BLAS with procedural primitives needs hit groups with intersection programs (rt_trace_rays_hit_groups)
@@ -1541,10 +1543,44 @@ int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geo
     return build_common(ctx, n, false, build_flags, scratch, result, L, R);
 }
 
+static int tlas_build_impl(rt_context *ctx, const rt_instance_desc *descs, const rt_instance_desc *const *ptrs, uint32_t n,
+                           uint32_t build_flags, void *scratch_, uint64_t scratch_bytes, void *result_, uint64_t result_bytes);
+
 int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, uint32_t build_flags, void *scratch_,
                   uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
+    return tlas_build_impl(ctx, descs, nullptr, n, build_flags, scratch_, scratch_bytes, result_, result_bytes);
+}
+
+int rt_tlas_build_ptrs(rt_context *ctx, const rt_instance_desc *const *desc_ptrs, uint32_t n, uint32_t build_flags, void *scratch_,
+                       uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
+    return tlas_build_impl(ctx, nullptr, desc_ptrs, n, build_flags, scratch_, scratch_bytes, result_, result_bytes);
+}
+
+int rt_blas_prebuild_ptrs(rt_context *ctx, const rt_geometry_desc *const *geoms, uint32_t n_geoms, uint32_t flags, rt_prebuild_info *info) {
+    RT_REQUIRE(n_geoms == 0 || geoms != nullptr, "null argument");
+    std::vector<rt_geometry_desc> flat(n_geoms);
+    for (uint32_t g = 0; g < n_geoms; ++g) {
+        RT_REQUIRE(geoms[g] != nullptr, "null geometry descriptor pointer");
+        flat[g] = *geoms[g];  // GetGeometryDesc, ARRAY_OF_POINTERS: FL/Util.h:101-114
+    }
+    return rt_blas_prebuild(ctx, flat.data(), n_geoms, flags, info);
+}
+
+int rt_blas_build_ptrs(rt_context *ctx, const rt_geometry_desc *const *geoms, uint32_t n_geoms, uint32_t build_flags, void *scratch,
+                       uint64_t scratch_bytes, void *result, uint64_t result_bytes) {
+    RT_REQUIRE(n_geoms == 0 || geoms != nullptr, "null argument");
+    std::vector<rt_geometry_desc> flat(n_geoms);
+    for (uint32_t g = 0; g < n_geoms; ++g) {
+        RT_REQUIRE(geoms[g] != nullptr, "null geometry descriptor pointer");
+        flat[g] = *geoms[g];
+    }
+    return rt_blas_build(ctx, flat.data(), n_geoms, build_flags, scratch, scratch_bytes, result, result_bytes);
+}
+
+static int tlas_build_impl(rt_context *ctx, const rt_instance_desc *descs, const rt_instance_desc *const *ptrs, uint32_t n,
+                           uint32_t build_flags, void *scratch_, uint64_t scratch_bytes, void *result_, uint64_t result_bytes) {
     RT_REQUIRE(ctx && result_, "null argument");
-    RT_REQUIRE(n == 0 || (descs && scratch_), "null argument");
+    RT_REQUIRE(n == 0 || ((descs || ptrs) && scratch_), "null argument");
     RT_REQUIRE((uintptr_t(result_) & 63) == 0 && (uintptr_t(scratch_) & 63) == 0, "buffers must be 64-byte aligned");
     RT_REQUIRE(n < (1u << 24), "more than 2^24-1 instances");
     RT_REQUIRE(!performs_update(build_flags) || allows_update(build_flags), "PERFORM_UPDATE without ALLOW_UPDATE");
@@ -1562,7 +1598,7 @@ int rt_tlas_build(rt_context *ctx, const rt_instance_desc *descs, uint32_t n, ui
     if (rc || n == 0) return rc;
     uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
     k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
-    k_load_instances<<<rt_div_up(n, kThreads), kThreads, 0, st>>>(descs, n, reinterpret_cast<rt_aabb_node *>(scratch + L.elems),
+    k_load_instances<<<rt_div_up(n, kThreads), kThreads, 0, st>>>(descs, ptrs, n, reinterpret_cast<rt_aabb_node *>(scratch + L.elems),
                                                                  reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), aabb_enc,
                                                                  reinterpret_cast<rt_ext_header *>(result + R.ext));
     ctx->launches += 2;

@@ -61,6 +61,9 @@ def _load():
         "rt_blas_build": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
         "rt_tlas_prebuild": (i32, [vp, u32, u32, vp]),
         "rt_tlas_build": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
+        "rt_tlas_build_ptrs": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
+        "rt_blas_prebuild_ptrs": (i32, [vp, vp, u32, u32, vp]),
+        "rt_blas_build_ptrs": (i32, [vp, vp, u32, u32, vp, u64, vp, u64]),
         "rt_build_scratch_layout": (i32, [u32, i32, vp]),
         "rt_update_cache_layout": (i32, [u32, i32, C.POINTER(u64), C.POINTER(u64)]),
         "rt_as_copy": (i32, [vp, vp, u64, vp, i32]),
@@ -181,16 +184,24 @@ class Context:
         return Buffer(self, max(host.nbytes, 16)).upload(host)
 
     # ---------------------------------------------------------------- acceleration structures
-    def build_blas(self, geoms, build_flags: int = 0, keep_scratch: bool = False):
+    def build_blas(self, geoms, build_flags: int = 0, keep_scratch: bool = False, array_of_pointers: bool = False):
         """geoms: list of dicts {vertices: Buffer|ptr, vertex_count, stride, indices: Buffer|ptr|None, index_count,
         index_format, transform: Buffer|ptr|None, flags}."""
         descs = _geometry_descs(geoms)
         info = T.PrebuildInfo()
-        check(lib.rt_blas_prebuild(self.handle, descs, len(geoms), build_flags, C.byref(info)))
+        if array_of_pointers:  # D3D12_ELEMENTS_LAYOUT_ARRAY_OF_POINTERS: a host array of pointers to the descriptors
+            pp = (C.c_void_p * len(geoms))(*[C.addressof(descs[i]) for i in range(len(geoms))])
+            check(lib.rt_blas_prebuild_ptrs(self.handle, pp, len(geoms), build_flags, C.byref(info)))
+        else:
+            check(lib.rt_blas_prebuild(self.handle, descs, len(geoms), build_flags, C.byref(info)))
         scratch = self.alloc(info.scratch_bytes)
         result = self.alloc(info.result_bytes)
-        check(lib.rt_blas_build(self.handle, descs, len(geoms), build_flags, scratch.ptr, scratch.nbytes, result.ptr,
-                                result.nbytes))
+        if array_of_pointers:
+            check(lib.rt_blas_build_ptrs(self.handle, pp, len(geoms), build_flags, scratch.ptr, scratch.nbytes, result.ptr,
+                                         result.nbytes))
+        else:
+            check(lib.rt_blas_build(self.handle, descs, len(geoms), build_flags, scratch.ptr, scratch.nbytes, result.ptr,
+                                    result.nbytes))
         n = sum(g["aabb_count"] if "aabbs" in g else
                 (g.get("index_count", 0) if g.get("index_format", 32 if g.get("indices") is not None else 0) else
                  g["vertex_count"]) // 3 for g in geoms)
@@ -247,15 +258,30 @@ class Context:
         return out.download(np.uint64, n)
 
     def build_tlas(self, blases, transforms, ids=None, masks=None, hit_groups=None, flags=None, build_flags: int = 0,
-                   keep_scratch: bool = False):
+                   keep_scratch: bool = False, array_of_pointers: bool = False):
+        """array_of_pointers: D3D12_ELEMENTS_LAYOUT_ARRAY_OF_POINTERS — the descriptors are stored in reverse order with a gap
+        between them and handed over as a device array of device addresses (rt_tlas_build_ptrs)."""
         n = len(blases)
-        dev_descs = self.upload(_instance_descs_bytes(blases, transforms, ids, masks, hit_groups, flags)) if n else None
+        descs = _instance_descs_bytes(blases, transforms, ids, masks, hit_groups, flags)
         info = T.PrebuildInfo()
         check(lib.rt_tlas_prebuild(self.handle, n, build_flags, C.byref(info)))
         scratch = self.alloc(info.scratch_bytes)
         result = self.alloc(info.result_bytes)
-        check(lib.rt_tlas_build(self.handle, dev_descs.ptr if n else None, n, build_flags, scratch.ptr, scratch.nbytes,
-                                result.ptr, result.nbytes))
+        if array_of_pointers and n:
+            stride = 64 + 64  # descriptors scattered: reversed, one 64-byte gap after each
+            scattered = np.zeros(n * stride, np.uint8)
+            for i in range(n):
+                scattered[(n - 1 - i) * stride:(n - 1 - i) * stride + 64] = descs[64 * i:64 * i + 64]
+            dev_descs = self.upload(scattered)
+            ptrs = np.array([dev_descs.ptr + (n - 1 - i) * stride for i in range(n)], np.uint64)
+            dev_ptrs = self.upload(ptrs.view(np.uint8))
+            check(lib.rt_tlas_build_ptrs(self.handle, dev_ptrs.ptr, n, build_flags, scratch.ptr, scratch.nbytes, result.ptr,
+                                         result.nbytes))
+            dev_descs = [dev_descs, dev_ptrs]
+        else:
+            dev_descs = self.upload(descs) if n else None
+            check(lib.rt_tlas_build(self.handle, dev_descs.ptr if n else None, n, build_flags, scratch.ptr, scratch.nbytes,
+                                    result.ptr, result.nbytes))
         acc = Accel(self, result, n, top=True, scratch=scratch if keep_scratch else None, keep=[dev_descs, list(blases)],
                     build_flags=build_flags)
         if not keep_scratch:

@@ -106,6 +106,15 @@ int rt_tlas_prebuild(rt_context *ctx, uint32_t n_instances, uint32_t build_flags
 /* instance_descs: DEVICE array of n rt_instance_desc (ELEMENTS_LAYOUT_ARRAY). */
 int rt_tlas_build(rt_context *ctx, const rt_instance_desc *instance_descs, uint32_t n_instances, uint32_t build_flags,
                   void *scratch, uint64_t scratch_bytes, void *result, uint64_t result_bytes);
+/* The same builds from D3D12_ELEMENTS_LAYOUT_ARRAY_OF_POINTERS inputs (FL/Util.h:101-114 GetGeometryDesc; FL/TopLevelLoadAABBs.hlsli:38-49,
+ * FL/LoadInstancesPass.cpp:55-60; exercised by UT:653, 878-934): `geoms` is a HOST array of host pointers to geometry descriptors;
+ * `desc_ptrs` is a DEVICE array of n device addresses, one per instance descriptor. */
+int rt_blas_prebuild_ptrs(rt_context *ctx, const rt_geometry_desc *const *geoms, uint32_t n_geoms, uint32_t build_flags,
+                          rt_prebuild_info *info);
+int rt_blas_build_ptrs(rt_context *ctx, const rt_geometry_desc *const *geoms, uint32_t n_geoms, uint32_t build_flags, void *scratch,
+                       uint64_t scratch_bytes, void *result, uint64_t result_bytes);
+int rt_tlas_build_ptrs(rt_context *ctx, const rt_instance_desc *const *desc_ptrs, uint32_t n_instances, uint32_t build_flags,
+                       void *scratch, uint64_t scratch_bytes, void *result, uint64_t result_bytes);
 /* Acceleration-structure updates (D3D12_RAYTRACING_ACCELERATION_STRUCTURE_BUILD_FLAG_ALLOW_UPDATE / PERFORM_UPDATE,
  * FL/GpuBVH2Builder.cpp:152-204, FL/ComputeAABBs.hlsli:38-67,160-164, unit tests UT:1054-1475).
  *   - build_flags | RT_BUILD_FLAG_ALLOW_UPDATE: rt_*_prebuild reports 4n + 4(2n-1) more result bytes and the same

@@ -172,3 +172,26 @@ def test_blob_bit_exact_degenerate_distributions(kind, ctx, orc):
     rays = random_rays(20000, seed=9, lo=lo, hi=hi)
     ho, hg = otlas.trace(rays, threads=8), ctx.trace(gtlas, rays)
     np.testing.assert_array_equal(hg["t"], ho["t"])
+
+
+def test_array_of_pointers_layouts(ctx, orc):
+    """D3D12_ELEMENTS_LAYOUT_ARRAY_OF_POINTERS (UT:653 multi-geometry BLAS, UT:878-934 TLAS over 50 instances): the same
+    bytes as the ARRAY layout, whether the descriptors arrive by value or through pointers."""
+    a, b = scenes.icosphere(2), scenes.triangle_soup(700, seed=5, extent=3.0, edge=0.6)
+    geoms = []
+    for m in (a, b):
+        geoms.append(dict(vertices=ctx.upload(m.vertices), vertex_count=m.vertices.shape[0], stride=24, indices=ctx.upload(m.indices),
+                          index_count=m.indices.size, index_format=32))
+    flat = ctx.build_blas(geoms)
+    ptrs = ctx.build_blas(geoms, array_of_pointers=True)
+    ref = orc.Blas([dict(vertices=a.vertices, stride=24, indices=a.indices), dict(vertices=b.vertices, stride=24, indices=b.indices)])
+    np.testing.assert_array_equal(flat.blob(), ref.blob())
+    np.testing.assert_array_equal(ptrs.blob(), ref.blob())
+    n_inst = 50
+    transforms = scenes.random_rigid_transforms(n_inst, seed=10)
+    t_flat = ctx.build_tlas([flat] * n_inst, transforms)
+    t_ptrs = ctx.build_tlas([flat] * n_inst, transforms, array_of_pointers=True)
+    np.testing.assert_array_equal(t_ptrs.blob(), t_flat.blob())
+    from helpers import random_rays
+    rays = random_rays(5000, seed=3, lo=(-120, -120, -120), hi=(120, 120, 120))
+    np.testing.assert_array_equal(ctx.trace(t_ptrs, rays).view(np.uint8), ctx.trace(t_flat, rays).view(np.uint8))
