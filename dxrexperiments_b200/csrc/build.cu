@@ -817,14 +817,17 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
             else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float((b0 + e) | RT_NODE_LEAF_FLAG | (s_proc[e] ? RT_NODE_PROCEDURAL_FLAG : 0u)));
         }
     }
-    // child order of a fitted node: smaller subtree on the left; ties keep the Karras order
+    // Child order of a fitted node: smaller subtree on the left; ties keep the Karras order.  Applied once, in place, to
+    // the shared copy of the hierarchy records, so that the write-out loops below (which visit a node once per 16-byte
+    // store) just read {left, right}.
+    if (threadIdx.x < cntInt && s_arrive[threadIdx.x] == 2) {
+        const uint32_t l = s_hier[3 * threadIdx.x + 1], r = s_hier[3 * threadIdx.x + 2];
+        if (s_size[shared_index(r)] < s_size[shared_index(l)]) s_hier[3 * threadIdx.x + 1] = r, s_hier[3 * threadIdx.x + 2] = l;
+    }
+    __syncthreads();
     auto children = [&](uint32_t e, uint32_t &l, uint32_t &r, uint32_t &li, uint32_t &ri) {
         l = s_hier[3 * e + 1], r = s_hier[3 * e + 2];
         li = shared_index(l), ri = shared_index(r);
-        if (s_size[ri] < s_size[li]) {
-            uint32_t t = l; l = r; r = t;
-            t = li; li = ri; ri = t;
-        }
     };
     {   // internal reference nodes: {center, left}, {halfDim, right}
         float4 *dst = reinterpret_cast<float4 *>(nodes + b0);
