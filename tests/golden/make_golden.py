@@ -34,6 +34,39 @@ def rng_kats():
     return (np.array([[r[0], r[1], r[2]] for r in rows], np.uint64), np.array([r[3] for r in rows], np.float32))
 
 
+def hit_group_scene():
+    """Mixed BLAS (non-opaque triangles + opaque spheres) used by the hit-group golden vectors: (mesh, aabbs, rays)."""
+    from helpers import random_rays
+    mesh = scenes.icosphere(2)
+    rng = np.random.Generator(np.random.PCG64(321))
+    c = rng.uniform(-2.5, 2.5, size=(300, 3))
+    hh = rng.uniform(0.1, 0.45, size=(300, 3))
+    aabbs = np.concatenate([c - hh, c + hh], axis=1).astype(np.float32)
+    rays = random_rays(4096, seed=77, lo=(-4, -4, -4), hi=(4, 4, 4), tmin=1e-4)
+    return mesh, aabbs, rays
+
+
+HIT_GROUP_CASES = [  # (name, programs per record [geometry 0, geometry 1], ray flags)
+    ("sphere", [[T.ANYHIT_NONE, T.INTERSECTION_NONE], [T.ANYHIT_NONE, T.INTERSECTION_SPHERE]], 0),
+    ("cutout_box", [[T.ANYHIT_CUTOUT, T.INTERSECTION_NONE], [T.ANYHIT_ACCEPT, T.INTERSECTION_BOX]], 0),
+    ("ignore_forced", [[T.ANYHIT_IGNORE, T.INTERSECTION_NONE], [T.ANYHIT_IGNORE, T.INTERSECTION_SPHERE]], T.RAY_FLAG_FORCE_NON_OPAQUE),
+    ("first_hit", [[T.ANYHIT_ACCEPT, T.INTERSECTION_NONE], [T.ANYHIT_END_SEARCH, T.INTERSECTION_SPHERE]],
+     T.RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | T.RAY_FLAG_FORCE_NON_OPAQUE),
+]
+
+
+def hit_group_vectors(orc):
+    mesh, aabbs, rays = hit_group_scene()
+    blas = orc.Blas([dict(vertices=mesh.vertices, stride=24, indices=mesh.indices, flags=T.GEOMETRY_FLAG_NONE), dict(aabbs=aabbs)])
+    tlas = orc.Tlas([blas], [scenes.IDENTITY_3X4], hit_groups=[0])
+    out = {"blob": np.asarray(blas.blob()).copy()}
+    for name, progs, flags in HIT_GROUP_CASES:
+        h = tlas.trace_hit_groups(rays, progs, ray_flags=flags, geometry_multiplier=1)
+        out[name + "_prim"], out[name + "_t"], out[name + "_geom"] = h["primitive_index"], h["t"], h["geometry_index"]
+        out[name + "_kind"] = (h["leaf_slot"] >> 24).astype(np.uint8)
+    return out
+
+
 def main():
     seeds, rands = rng_kats()
     # build: a seeded soup with duplicate codes
@@ -64,6 +97,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "cornell48.npz"), prim=hits["primitive_index"], t=hits["t"], bary=hits["bary"],
                         progressive4=acc, direct=direct, spec=spec, denoised=den)
     np.savez_compressed(os.path.join(HERE, "rng.npz"), seeds=seeds, rands=rands)
+    np.savez_compressed(os.path.join(HERE, "hitgroups_mixed.npz"), **hit_group_vectors(oracle))
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
