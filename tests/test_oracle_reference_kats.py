@@ -487,3 +487,23 @@ def test_tlas_update_refits_instances(orc):
     h_upd, h_new = t.trace(rays), fresh.trace(rays)
     for f in ("t", "primitive_index", "instance_index"):
         np.testing.assert_array_equal(h_upd[f], h_new[f])                        # same scene => same closest hits
+
+
+def test_any_hit_visibility_does_not_depend_on_the_visiting_order(orc):
+    """The production any-hit kernel visits the four children of a node in slot order instead of near-to-far
+    (DESIGN 4.2).  That is only legitimate because an ACCEPT_FIRST_HIT search answers "is there ANY accepted hit in
+    (tMin, tMax)": the reference-order search must agree with the existence of a closest hit for every ray, with and
+    without culling flags, on single-level and instanced scenes."""
+    from helpers import bunny_case, random_rays, two_material_case
+    for case in (bunny_case(3), two_material_case()):
+        otlas, _ = case.oracle(orc)
+        rays = random_rays(6000, seed=23, lo=(-8, 0.05, -8), hi=(8, 9, 8), tmin=1e-4)
+        rays["tmax"][::3] = 2.5  # a third of the rays are short, like point-light shadow rays
+        for cull in (0, T.RAY_FLAG_CULL_BACK_FACING_TRIANGLES, T.RAY_FLAG_CULL_FRONT_FACING_TRIANGLES):
+            closest = otlas.trace(rays, cull, threads=4)
+            anyhit = otlas.trace(rays, cull | T.RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH | T.RAY_FLAG_SKIP_CLOSEST_HIT_SHADER, threads=4)
+            np.testing.assert_array_equal(anyhit["primitive_index"] != T.NO_HIT, closest["primitive_index"] != T.NO_HIT)
+            # and what the any-hit search reports is a genuine hit no closer than the closest one
+            hit = anyhit["primitive_index"] != T.NO_HIT
+            assert (anyhit["t"][hit] >= closest["t"][hit]).all()
+            assert (anyhit["t"][hit] < rays["tmax"][hit]).all() and (anyhit["t"][hit] > rays["tmin"][hit]).all()
