@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """Pretty-print bench.py JSON lines (files given on the command line)."""
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` must not end in a traceback
 import json, sys
 for path in sys.argv[1:]:
     try:
