@@ -12,8 +12,15 @@ soup, the second half of BASELINE.json's metric).  `--config C3|C4|C5` measures 
 way (C5: realtime pipeline + denoise, reported as per-frame latency); they are extra lines, not the driver's.
 
 N > 1: the frame shards by SAMPLE INDEX: rank r renders samples r, r+N, ... with frameCount = the global
-sample index, every rank holds a replicated BVH, and one NCCL reduce sums the scaled accumulation buffers onto
-rank 0.  Per-GPU work is fixed (16 spp each), so scaling is "weak"; the reduce is inside the timed region.
+sample index, every rank holds a replicated BVH, and one NCCL reduce (rt_accum_reduce, inside librt_core; each rank's
+weight applied in the reduction) sums the accumulation buffers onto rank 0.  Per-GPU work of the headline is fixed (16 spp
+each), so its scaling is "weak"; the reduce is inside the timed region.
+
+Every run ALSO emits `strong`: ONE fixed C3 frame (3840x2160, 64 spp total) sharded over the N ranks by sample index and by
+interleaved screen strips, timed from "scene in pinned host memory" to "frame in rank 0's pinned host memory" (H2D,
+replicated BLAS+TLAS build, the rank's dispatches, the NCCL reduce, ONE D2H on the root).  time_to_frame_ms at N = 1, 2, 4, 8
+is the north star's strong-scaling number; `target_scene` is the >= 1 Grays/s incoherent-ray target on the 1.31 M-triangle
+scene; `incoherent_mrays_per_s` pulls BASELINE.json's "Mrays/s (incoherent, 1080p)" to the top level.
 """
 import argparse
 import ctypes as C
@@ -52,6 +59,13 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-denoise", action="store_true", help="skip the DenoiseCompositor kernel measurement")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (fixed C3 4K 64-spp frame over N ranks)")
+    ap.add_argument("--strong-spp", type=int, default=64)
+    ap.add_argument("--strong-config", default="C3", choices=["C2", "C3", "C4", "C1M"])
+    ap.add_argument("--strong-strip-groups", type=int, default=None,
+                    help="strip groups of the strong-scaling shard plan (default: sample sharding first, strips when samples run out)")
+    ap.add_argument("--strong-reps", type=int, default=2)
+    ap.add_argument("--no-target-scene", action="store_true", help="skip the 1.31 M-triangle incoherent-ray target measurement")
     return ap.parse_args()
 
 
@@ -154,6 +168,8 @@ def run_reference(args):
     wl = load_workload(args)
     cores = os.cpu_count() or 1
     env = scenes.sky_cube(64)
+    import oracle
+    cflags = oracle.use_native()
     orc, tlas, recs, _keep = oracle_scene(wl)
     jit = scenes.jitter_sequence(wl.setup.seed, 1024, wl.width, wl.height)
     acc = np.zeros((wl.height, wl.width, 4), np.float32)
@@ -170,7 +186,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     rays = counts.primary + counts.secondary + counts.shadow
     mrays = rays / dt / 1e6
-    sample = f"{args.steps} x 1 spp of the {wl.width}x{wl.height} frame ({rays} rays), {cores} threads, row-parallel"
+    sample = (f"{args.steps} x 1 spp of the {wl.width}x{wl.height} frame ({rays} rays), {cores} threads, row-parallel, "
+              f"oracle port compiled {cflags}")
     metric, value, hib = metric_of(wl, mrays, dt / args.steps * 1e3)
     out = {"impl": "reference", "metric": metric, "value": value, "unit": metric, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": hib, "scaling": "weak",
@@ -235,6 +252,9 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    comm = make_comm(rt, ctx, torch, dist, world, rank) if world > 1 else None
+    reduced_t = torch.zeros_like(out_t) if (world > 1 and rank == 0) else None
+
     def step(step_index):
         # rank r renders global samples r, r + world, ...; RNG is a pure function of (pixel, frameCount)
         for s in range(SPP):
@@ -242,9 +262,8 @@ def run_ours(args):
             if dn:  # DenoiseCompositor::dispatch on the two AOVs of this frame
                 rt.check(rt.lib.rt_denoise(ctx.handle, outs[0].data_ptr(), outs[1].data_ptr(), dn["tmp"].data_ptr(), dn["out"].data_ptr(),
                                            W, H, C.byref(dn["params"])))
-        if world > 1:
-            rt.check(rt.lib.rt_scale_buffer(ctx.handle, out_t.data_ptr(), out_t.numel(), 1.0 / world))
-            dist.reduce(out_t, dst=0, op=dist.ReduceOp.SUM)
+        if world > 1:  # the path's one collective, inside the product: weight 1/world applied in the NCCL reduction
+            comm.reduce(out_t.data_ptr(), reduced_t.data_ptr() if rank == 0 else None, out_t.numel(), 1.0 / world, root=0)
 
     for i in range(args.warmup):
         step(i)
@@ -283,7 +302,12 @@ def run_ours(args):
     # ---- e2e: the same step through the C ABI with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank)
+        e2e = measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank, comm)
+
+    # ---- strong scaling: ONE fixed 4K 64-spp C3 frame over the N ranks, host scene -> host frame on the root
+    strong = None
+    if not args.no_strong:
+        strong = measure_strong(args, ctx, rt, torch, dist, stream, world, rank, comm)
 
     # ---- roofline of the dominant kernel (rank 0: a single-GPU kernel property)
     roofline, stages = None, None
@@ -298,6 +322,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_denoise:
         denoise = measure_denoise(args, ctx, rt, torch, stream)
 
+    target = None
+    if rank == 0 and world == 1 and not args.no_target_scene and args.config == "C2":
+        target = measure_target_scene(args, ctx, rt, torch)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = measure_cpu_baseline(args, wl, env, jit)
@@ -310,15 +338,42 @@ def run_ours(args):
                "rays_per_step": {"primary": rays[0] / args.steps, "secondary_incoherent": rays[1] / args.steps,
                                  "shadow": rays[2] / args.steps},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "stages": stages,
+               "incoherent_mrays_per_s": incoherent_summary(wl, stages, target), "strong": strong, "target_scene": target,
                "build": build, "denoise": denoise, "cpu_baseline": cpu_baseline,
-               "parallelism": f"sample-index sharding x{world}, replicated BVH, 1 NCCL reduce/frame" if world > 1 else "single GPU"}
+               "parallelism": f"sample-index sharding x{world}, replicated BVH, 1 NCCL reduce/frame (rt_accum_reduce)" if world > 1 else "single GPU"}
         print(json.dumps(out))
+    if comm:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank):
+def make_comm(rt, ctx, torch, dist, world, rank):
+    """rt_comm over NCCL inside librt_core; torch.distributed only carries rank 0's 128-byte unique id."""
+    def exchange(uid):
+        box = [uid]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return rt.Comm(ctx, world, rank, exchange)
+
+
+def incoherent_summary(wl, stages, target):
+    """BASELINE.json's metric is "Mrays/s (incoherent, 1080p)": the incoherent secondary rays alone (cosine-hemisphere and
+    Phong-lobe bounces, k_trace_persistent<0>), CUDA-event timed around their kernel, for the headline workload and for the
+    north star's 1 M-triangle target scene."""
+    out = {"definition": "incoherent secondary rays traced / CUDA-event time of their traversal kernel (stage-timed dispatches)"}
+    if stages:
+        for k, v in stages.items():
+            if k.startswith("secondary_incoherent"):
+                out[wl.name] = v["mrays_per_s"]
+    if target:
+        out["C1M"] = target["incoherent_mrays_per_s"]
+        out["target_ge_1000_on_1M_triangles"] = bool(target["incoherent_mrays_per_s"] >= 1000.0)
+    return out
+
+
+def measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank, comm=None):
     """Step through the reference-facing C ABI starting from HOST memory: pinned VB/IB/instance descs -> device,
     BLAS + TLAS builds, the step's dispatches (+ denoise for C5), accumulated frame -> pinned host."""
     W, H, SPP = wl.width, wl.height, wl.spp
@@ -366,7 +421,8 @@ def measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank):
         dn_tmp, dn_out = torch.empty_like(outs[0]), torch.empty_like(outs[0])
         result_t = dn_out
     dparams = denoiser_params()
-    img_h = torch.empty(H * W * 4, dtype=torch.float32).pin_memory()
+    img_h = torch.empty(H * W * 4, dtype=torch.float32).pin_memory() if rank == 0 else None  # only the root holds the frame
+    reduced_t = torch.zeros_like(result_t) if (world > 1 and rank == 0) else None
 
     def step(i):
         for (vb_h, ib_h), (vb_d, ib_d) in zip(host, dev):
@@ -387,9 +443,9 @@ def measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank):
                 rt.check(rt.lib.rt_denoise(ctx.handle, outs[0].data_ptr(), outs[1].data_ptr(), dn_tmp.data_ptr(), dn_out.data_ptr(), W, H,
                                            C.byref(dparams)))
         if world > 1:
-            rt.check(rt.lib.rt_scale_buffer(ctx.handle, result_t.data_ptr(), result_t.numel(), 1.0 / world))
-            dist.reduce(result_t, dst=0, op=dist.ReduceOp.SUM)
-        img_h.copy_(result_t, non_blocking=True)
+            comm.reduce(result_t.data_ptr(), reduced_t.data_ptr() if rank == 0 else None, result_t.numel(), 1.0 / world, root=0)
+        if rank == 0:
+            img_h.copy_(reduced_t if world > 1 else result_t, non_blocking=True)
 
     for i in range(max(1, min(args.warmup, 2))):
         step(i)
@@ -412,14 +468,199 @@ def measure_e2e(args, wl, ctx, rt, torch, dist, stream, env, jit, world, rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    assert float(img_h.sum()) > 0.0
+    if rank == 0:
+        assert float(img_h.sum()) > 0.0 and bool(torch.isfinite(img_h).all())
     ms = float(t.item())
     metric, value, _ = metric_of(wl, float(r.item()) / (ms * 1e-3) / 1e6, ms / args.steps)
     h2d = sum(int(a.numel() + b.numel()) for a, b in host) + int(inst_h.numel())
-    return {"value": value, "unit": metric, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(img_h.numel() * 4),
+    return {"value": value, "unit": metric, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(H * W * 16),
             "ms_per_step": ms / args.steps,
             "includes": "pinned H2D of VB/IB/instance descs, BLAS+TLAS build, the step's dispatches"
-                        + (" + denoise" if wl.realtime else "") + ", D2H of the frame"}
+                        + (" + denoise" if wl.realtime else "") + (", rt_accum_reduce onto rank 0" if world > 1 else "")
+                        + ", D2H of the frame (root only)"}
+
+
+def measure_strong(args, ctx, rt, torch, dist, stream, world, rank, comm):
+    """The north star's strong-scaling number: ONE fixed progressive frame (default C3: 3840x2160, 64 spp in total) split
+    across the N ranks by sample index and by interleaved screen strips (sharding.plan), replicated BVH.  Timed region, per
+    rank, on the device: pinned-host scene -> device, BLAS + TLAS build, this rank's dispatches, rt_accum_reduce, and on
+    the root the D2H of the finished frame into pinned memory.  time_to_frame = max over ranks."""
+    from dxrexperiments_b200 import sharding
+    wl = scenes.workload(args.strong_config)
+    W, H, SPP = wl.width, wl.height, args.strong_spp
+    plan = sharding.plan(rank, world, SPP, strip_groups=args.strong_strip_groups, strip_rows=32)
+    env = scenes.sky_cube(64)
+    jit = scenes.jitter_sequence(wl.setup.seed, max(SPP, 1), W, H)
+    n_inst = len(wl.transforms)
+    host, dev, descs, bscr, bres = [], [], [], [], []
+    for m in wl.meshes:
+        vb_h = torch.from_numpy(m.vertices.view(np.uint8).reshape(-1).copy()).pin_memory()
+        ib_h = torch.from_numpy(m.indices.view(np.uint8).reshape(-1).copy()).pin_memory()
+        vb_d, ib_d = torch.empty_like(vb_h, device="cuda"), torch.empty_like(ib_h, device="cuda")
+        host.append((vb_h, ib_h))
+        dev.append((vb_d, ib_d))
+        d = (T.GeometryDesc * 1)()
+        d[0].vertex_buffer, d[0].vertex_count, d[0].vertex_stride_bytes = vb_d.data_ptr(), m.vertices.shape[0], 24
+        d[0].index_buffer, d[0].index_count, d[0].index_format = ib_d.data_ptr(), m.indices.size, 32
+        d[0].flags = T.GEOMETRY_FLAG_OPAQUE
+        info = T.PrebuildInfo()
+        rt.check(rt.lib.rt_blas_prebuild(ctx.handle, d, 1, 0, C.byref(info)))
+        descs.append(d)
+        bscr.append(torch.empty(info.scratch_bytes, dtype=torch.uint8, device="cuda"))
+        bres.append(torch.empty(info.result_bytes, dtype=torch.uint8, device="cuda"))
+    tinfo = T.PrebuildInfo()
+    rt.check(rt.lib.rt_tlas_prebuild(ctx.handle, n_inst, 0, C.byref(tinfo)))
+    tscr = torch.empty(tinfo.scratch_bytes, dtype=torch.uint8, device="cuda")
+    tres = torch.empty(tinfo.result_bytes, dtype=torch.uint8, device="cuda")
+    inst = (T.InstanceDesc * n_inst)()
+    for i, (k, xf) in enumerate(zip(wl.instance_mesh, wl.transforms)):
+        inst[i].transform[:] = np.asarray(xf, np.float32).reshape(12).tolist()
+        inst[i].instance_id_and_mask = (i & 0xFFFFFF) | (0xFF << 24)
+        inst[i].hit_group_and_flags = 2 * i
+        inst[i].blas = bres[k].data_ptr()
+    inst_h = torch.from_numpy(np.frombuffer(bytes(inst), dtype=np.uint8).copy()).pin_memory()
+    inst_d = torch.empty_like(inst_h, device="cuda")
+    env_d = torch.from_numpy(np.ascontiguousarray(env, np.float32).reshape(-1)).cuda()
+    prog = rt.Program(ctx, rt.PROGRESSIVE)
+    for i, k in enumerate(wl.instance_mesh):
+        for ray_type in range(2):
+            rt.check(rt.lib.rt_bindings_set_hit_record(prog.handle, ray_type, i, dev[k][0].data_ptr(), dev[k][1].data_ptr(),
+                                                       C.byref(wl.materials[k])))
+    rt.check(rt.lib.rt_bindings_set_miss_record(prog.handle, 0, env_d.data_ptr(), env.shape[1]))
+    acc = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")  # zero outside this rank's strips, for ever
+    frame_d = torch.zeros_like(acc) if (world > 1 and rank == 0) else None
+    img_h = torch.empty(H * W * 4, dtype=torch.float32).pin_memory() if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def frame_once():
+        ev[0].record(stream)
+        for (vb_h, ib_h), (vb_d, ib_d) in zip(host, dev):
+            vb_d.copy_(vb_h, non_blocking=True)
+            ib_d.copy_(ib_h, non_blocking=True)
+        inst_d.copy_(inst_h, non_blocking=True)
+        for d, sc, rs in zip(descs, bscr, bres):
+            rt.check(rt.lib.rt_blas_build(ctx.handle, d, 1, 0, sc.data_ptr(), sc.numel(), rs.data_ptr(), rs.numel()))
+        rt.check(rt.lib.rt_tlas_build(ctx.handle, inst_d.data_ptr(), n_inst, 0, tscr.data_ptr(), tscr.numel(), tres.data_ptr(), tres.numel()))
+        ev[1].record(stream)
+        rt.check(rt.lib.rt_set_tlas(ctx.handle, tres.data_ptr()))
+        rt.check(rt.lib.rt_set_output(ctx.handle, 0, acc.data_ptr(), 16 * W))
+        for local, smp in enumerate(plan.samples):
+            f = scenes.make_frame(wl.setup, W, H, frame_count=smp, accum_count=local, jitter=jit[smp % len(jit)])
+            rt.check(rt.lib.rt_set_frame_constants(ctx.handle, C.byref(f)))
+            if plan.strip_groups > 1:
+                rt.check(rt.lib.rt_dispatch_rays_interleaved(ctx.handle, prog.handle, W, H, plan.strip_rows, plan.strip_groups, plan.strip_group))
+            else:
+                rt.check(rt.lib.rt_dispatch_rays(ctx.handle, prog.handle, W, H, 3))
+        ev[2].record(stream)
+        if world > 1:
+            comm.reduce(acc.data_ptr(), frame_d.data_ptr() if rank == 0 else None, acc.numel(), plan.weight, root=0)
+        ev[3].record(stream)
+        if rank == 0:
+            img_h.copy_(frame_d if world > 1 else acc, non_blocking=True)
+        ev[4].record(stream)
+
+    frame_once()  # warm-up (also grows the wavefront workspace)
+    torch.cuda.synchronize()
+    ctx.status()
+    ctx.ray_counts(reset=True)
+    times, parts = [], []
+    for _ in range(max(1, args.strong_reps)):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        frame_once()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[4])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
+    rc = ctx.ray_counts(reset=True)
+    r = torch.tensor([float(rc.primary + rc.secondary + rc.shadow)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    assert bool(torch.isfinite(img_h).all()) and float(img_h.sum()) > 0.0
+    best = int(np.argmin(times))
+    ms = float(np.median(times))
+    rays_per_frame = float(r.item()) / len(times)
+    h2d = sum(int(a.numel() + b.numel()) for a, b in host) + int(inst_h.numel())
+    return {"metric": "time to frame, ms (fixed frame, strong scaling; lower is better)", "time_to_frame_ms": ms, "all_ms": times,
+            "n_gpus": world, "workload": f"{wl.description.split(' progressive')[0]}: ONE frame of {SPP} spp in total, split over {world} rank(s)",
+            "width": W, "height": H, "spp_total": SPP, "triangles": wl.num_triangles,
+            "shard_plan": {"strip_groups": plan.strip_groups, "sample_groups": plan.sample_groups, "strip_rows": plan.strip_rows,
+                           "samples_on_rank0": len(plan.samples)},
+            "root_breakdown_ms": dict(zip(["h2d_and_build", "dispatches", "nccl_reduce", "d2h_root"], parts[best])),
+            "mrays_per_s": rays_per_frame / (ms * 1e-3) / 1e6, "rays_per_frame": rays_per_frame,
+            "h2d_bytes_per_rank": h2d, "reduce_bytes_per_rank": int(H * W * 16) if world > 1 else 0, "d2h_bytes_root": int(H * W * 16),
+            "includes": "pinned H2D of VB/IB/instance descs + BLAS/TLAS build on every rank, the rank's dispatches, "
+                        "rt_accum_reduce (NCCL, weighted) onto rank 0, one D2H of the frame on rank 0"}
+
+
+def measure_target_scene(args, ctx, rt, torch):
+    """North-star target: >= 1 Grays/s of incoherent secondary rays on a ~1 M-triangle scene at 1080p.  C1M = displaced
+    icosphere, 1 310 722 triangles in one flat BLAS (traversal section ~440 MB, several times the L2).  Reported: the
+    incoherent stage alone (CUDA events around k_trace_persistent<0>), its algorithmic bytes per launch from the
+    instrumented pass, the whole-frame rate, and the measured DRAM traffic of the same kernel (ncu, profiles/traffic.json)."""
+    wl = scenes.workload("C1M")
+    W, H, SPP = wl.width, wl.height, 2
+    env = scenes.sky_cube(64)
+    jit = scenes.jitter_sequence(wl.setup.seed, 16, W, H)
+    out = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+    r = rt.Renderer(ctx, wl.meshes, wl.transforms, wl.materials, env, rt.PROGRESSIVE, W, H, outputs=[TorchBuffer(out)],
+                    instance_mesh=wl.instance_mesh)
+
+    def frames(n0, n):
+        for s in range(n0, n0 + n):
+            r.dispatch(scenes.make_frame(wl.setup, W, H, frame_count=s, accum_count=s, jitter=jit[s % len(jit)]))
+
+    frames(0, 2)  # warm-up
+    ctx.enable_trace_stats(True)
+    ctx.trace_stats(reset=True)
+    frames(0, SPP)
+    st = ctx.trace_stats(reset=True)
+    ctx.enable_trace_stats(False)
+    ctx.enable_stage_timing(True)
+    ctx.stage_timing(reset=True)
+    reps = 3
+    for _ in range(reps):
+        frames(0, SPP)
+    tp, ts, tsh = ctx.stage_timing(reset=True)
+    ctx.enable_stage_timing(False)
+    # whole frames, overlapped dispatch
+    ctx.ray_counts(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        frames(0, SPP)
+    e1.record()
+    torch.cuda.synchronize()
+    rc = ctx.ray_counts(reset=True)
+    ms = e0.elapsed_time(e1)
+    sec = st[1]
+    n_launch = reps * SPP
+    ms_launch = ts / n_launch
+    bytes_launch = (48.0 * sec.rays + 64.0 * sec.internal_visits + 48.0 * sec.leaf_visits) / SPP
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    gbs = bytes_launch / (ms_launch * 1e-3) / 1e9
+    traffic = load_ncu_traffic("C1M secondary_incoherent (k_trace_persistent<0>)")
+    roof = {"bound": "hbm", "kernel": "k_trace_persistent<0> (closest hit, incoherent secondary rays)", "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
+            "dram_frac": (traffic / (ms_launch * 1e-3) / 1e9 / peak) if traffic else None,
+            "note": "achieved = algorithmic bytes (48 + 64 n_int + 48 n_leaf per ray over the BVH2 visit counts of the same rays) / "
+                    "CUDA-event launch time; traffic = dram bytes per launch of the same kernel from the committed ncu capture; "
+                    "dram_frac = traffic / time / peak is the share of the HBM roof the kernel really uses"}
+    return {"workload": wl.description, "triangles": wl.num_triangles, "width": W, "height": H,
+            "incoherent_mrays_per_s": sec.rays / SPP / (ms_launch * 1e-3) / 1e6,
+            "incoherent_rays_per_launch": sec.rays / SPP, "ms_per_launch": ms_launch,
+            "n_int_per_ray": sec.internal_visits / max(sec.rays, 1), "n_leaf_per_ray": sec.leaf_visits / max(sec.rays, 1),
+            "primary_mrays_per_s": st[0].rays / SPP / (tp / n_launch * 1e-3) / 1e6,
+            "shadow_mrays_per_s": st[2].rays / SPP / (tsh / n_launch * 1e-3) / 1e6,
+            "all_rays_mrays_per_s": (rc.primary + rc.secondary + rc.shadow) / (ms * 1e-3) / 1e6, "ms_per_frame": ms / n_launch,
+            "roofline": roof}
 
 
 def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
@@ -465,15 +706,32 @@ def measure_roofline(args, ctx, renderer, setup, jit, world, rank):
     dom_i = max(range(3), key=lambda i: times[i])
     d = stages[names[dom_i]]
     traffic = load_ncu_traffic(names[dom_i]) if args.config == "C2" else None
+    dram_frac = (traffic / (d["ms_per_launch"] * 1e-3) / 1e9 / peak) if traffic and d["ms_per_launch"] else None
+    # The bound that binds on an L2-resident scene is instruction issue, not HBM: thread-instructions per second against
+    # SMs x 4 schedulers x 32 lanes x SM clock.  Instruction counts come from the committed ncu capture of the same kernel
+    # (they are a property of the rays and the tree, not of the run); the time is measured live.
+    issue = None
+    ncu = load_ncu_counters(names[dom_i]) if args.config == "C2" else None
+    if ncu and d["ms_per_launch"]:
+        sm_hz = 1.965e9
+        peak_tinst = 148 * 4 * 32 * sm_hz / 1e12
+        ach = ncu["warp_instructions"] * ncu["lanes_per_instruction"] / (d["ms_per_launch"] * 1e-3) / 1e12
+        issue = {"bound": "issue", "kernel": names[dom_i], "achieved": ach, "peak": peak_tinst, "unit": "T thread-instructions/s",
+                 "frac": ach / peak_tinst, "warp_instructions_per_launch": ncu["warp_instructions"],
+                 "lanes_per_instruction": ncu["lanes_per_instruction"], "source": ncu.get("source"),
+                 "note": "frac = (issue-slot utilisation) x (lanes active / 32): what separates the kernel from a perfectly "
+                         "converged, always-issuing SIMT machine"}
     roofline = {"bound": "hbm", "kernel": names[dom_i], "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["achieved_gbs"] / peak if d["achieved_gbs"] else None, "traffic": traffic,
+                "frac": d["achieved_gbs"] / peak if d["achieved_gbs"] else None, "traffic": traffic, "dram_frac": dram_frac,
+                "binds": False, "issue": issue,
                 "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes/ray (48 + 64*n_int + 48*n_leaf over the BVH2 visit counts of the same rays, "
-                        "SURVEY 8d) x rays per launch / CUDA-event launch time.  The traversal structure is L1/L2-resident, so "
-                        "DRAM traffic (`traffic`, ncu) is far below the algorithmic bytes — which is also why frac can exceed 1: "
-                        "those bytes are served by L1/L2, not HBM — and the kernel's real bound is instruction issue at 13-20 of 32 "
-                        "lanes active (profiles/r1_ncu_final.md).  Stage times are measured with the dispatch in its sequential, "
-                        "stage-timed mode; `value` is measured with the stages of two pixel bands overlapped (DESIGN 4.2)"}
+                        "SURVEY 8d) x rays per launch / CUDA-event launch time, as the contract defines it.  On this workload the "
+                        "HBM roof does NOT bind (`binds`: false): the traversal structure is L1/L2-resident, measured DRAM traffic "
+                        "(`traffic`, ncu) is a few per cent of the algorithmic bytes (`dram_frac` of the HBM peak), which is also why "
+                        "frac can exceed 1.  The binding roof is instruction issue (`issue`); the HBM-relevant measurement is "
+                        "`target_scene.roofline` (1.31 M triangles, structure several times the L2).  Stage times are measured with the "
+                        "dispatch in its sequential, stage-timed mode; `value` with the stages of two pixel bands overlapped (DESIGN 4.2)"}
     return roofline, stages
 
 
@@ -483,6 +741,21 @@ def load_ncu_traffic(stage_key):
     if os.path.exists(p):
         try:
             return json.load(open(p)).get("dram_bytes_per_launch", {}).get(stage_key)
+        except Exception:
+            return None
+    return None
+
+
+def load_ncu_counters(stage_key):
+    """warp instructions / lanes per instruction of a trace stage from the committed ncu capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            c = j.get("issue_counters", {}).get(stage_key)
+            if c:
+                c = dict(c, source=j.get("source"))
+            return c
         except Exception:
             return None
     return None
@@ -574,22 +847,37 @@ def measure_denoise(args, ctx, rt, torch, stream):
 
 
 def measure_cpu_baseline(args, wl, env, jit):
+    """the oracle port compiled -O3 -march=native on this host, all cores, median of >= 3
+    repetitions, build and trace timed separately (Mtri/s and Mrays/s defined as for the GPU)."""
+    import oracle
+    cflags = oracle.use_native()
     cores = os.cpu_count() or 1
-    orc, tlas, recs, _keep = oracle_scene(wl)
+    # build: BLAS (+ TLAS) of the workload's meshes, single-threaded (the restated builder is sequential)
+    build_times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        orc, tlas, recs, _keep = oracle_scene(wl)
+        build_times.append(time.perf_counter() - t0)
+    build_s = float(np.median(build_times))
     acc = np.zeros((wl.height, wl.width, 4), np.float32)
-    counts = T.RayCounts()
-    t0 = time.perf_counter()
-    n = 0
-    while True:
+    vals, rays_total, t_start = [], 0, time.perf_counter()
+    for n in range(5):
+        counts = T.RayCounts()
+        t0 = time.perf_counter()
         oracle_frame(orc, tlas, recs, env, wl, frame_for(wl.setup, args, jit, n, 0), acc, cores, counts)
-        n += 1
-        if time.perf_counter() - t0 > 10.0 or n >= 4:
+        dt = time.perf_counter() - t0
+        rays = counts.primary + counts.secondary + counts.shadow
+        rays_total += rays
+        vals.append(metric_of(wl, rays / dt / 1e6, dt * 1e3)[1])
+        if len(vals) >= 3 and time.perf_counter() - t_start > 20.0:
             break
-    dt = time.perf_counter() - t0
-    rays = counts.primary + counts.secondary + counts.shadow
-    metric, value, _ = metric_of(wl, rays / dt / 1e6, dt / n * 1e3)
-    return {"value": value, "unit": metric, "cores": cores, "kind": "port",
-            "sample": f"{n} x 1 spp of the {wl.width}x{wl.height} frame ({rays} rays) in {dt:.1f} s, row-parallel over {cores} threads"}
+    metric = metric_of(wl, 0.0, 0.0)[0]
+    return {"value": float(np.median(vals)), "unit": metric, "cores": cores, "kind": "port",
+            "sample": f"median of {len(vals)} x 1 spp of the {wl.width}x{wl.height} frame ({rays_total // len(vals)} rays each) in "
+                      f"{time.perf_counter() - t_start:.1f} s, row-parallel over {cores} threads, compiled {cflags}",
+            "all_values": vals,
+            "build": {"metric": "LBVH build Mtri/s (CPU, 1 thread, default flags = 1 treelet pass)", "value": wl.num_triangles / build_s / 1e6,
+                      "triangles": wl.num_triangles, "ms": build_s * 1e3, "cores": 1, "repetitions": 3}}
 
 
 def main():

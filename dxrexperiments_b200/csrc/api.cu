@@ -97,6 +97,22 @@ int rt_get_status(rt_context *ctx) {
         RT_CUDA(cudaMemcpyAsync(ctx->status, &cleared, 4, cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    if (s & 8u) {
+        const uint32_t cleared = s & ~14u;
+        RT_CUDA(cudaMemcpyAsync(ctx->status, &cleared, 4, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        rt_set_error("a ray hit an instance whose hit-group record index lies beyond the bound records "
+                     "(InstanceContributionToHitGroupIndex + ray type >= records set with rt_bindings_set_hit_record)");
+        return RT_ERR_INVALID_ARG;
+    }
+    if (s & 4u) {
+        const uint32_t cleared = s & ~6u;
+        RT_CUDA(cudaMemcpyAsync(ctx->status, &cleared, 4, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        rt_set_error("a top-level build was given an instance whose BLAS address is null or does not hold a finished bottom-level "
+                     "build of this library; such instances were made inactive");
+        return RT_ERR_INVALID_ARG;
+    }
     if (s & 1u) {
         rt_set_error("traversal stack overflow: a ray needed more than 64 stack entries");
         return RT_ERR_OVERFLOW;
@@ -127,16 +143,19 @@ int rt_free(rt_context *ctx, void *dev) {
 }
 int rt_memset(rt_context *ctx, void *dev, int value, uint64_t bytes) {
     RT_REQUIRE(ctx && (dev || bytes == 0), "null argument");
+    RT_CUDA(cudaSetDevice(ctx->device));
     RT_CUDA(cudaMemsetAsync(dev, value, bytes, ctx->stream));
     return RT_OK;
 }
 int rt_upload(rt_context *ctx, void *dev, const void *host, uint64_t bytes) {
     RT_REQUIRE(ctx && (bytes == 0 || (dev && host)), "null argument");
+    RT_CUDA(cudaSetDevice(ctx->device));
     if (bytes) RT_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return RT_OK;
 }
 int rt_download(rt_context *ctx, void *host, const void *dev, uint64_t bytes) {
     RT_REQUIRE(ctx && (bytes == 0 || (dev && host)), "null argument");
+    RT_CUDA(cudaSetDevice(ctx->device));
     if (bytes) RT_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     return RT_OK;

@@ -1079,23 +1079,41 @@ __device__ void invert_affine(const float *t, float *o) {
 
 // FL/TopLevelLoadAABBs.hlsli:58-100 fused with FL/CalculateSceneAABBFromBVHs.hlsl:16-40.
 // `ptrs` != nullptr: D3D12_ELEMENTS_LAYOUT_ARRAY_OF_POINTERS — element i is *ptrs[i] (FL/TopLevelLoadAABBs.hlsli:38-49).
+__device__ __forceinline__ bool blas_is_valid(const uint8_t *blas) {
+    if (blas == nullptr || (uintptr_t(blas) & 63) != 0) return false;
+    const rt_bvh_offsets *bo = reinterpret_cast<const rt_bvh_offsets *>(blas);
+    if (bo->offsetToBoxes != 16 || bo->totalSize < 48 || bo->totalSize > (1ull << 33)) return false;
+    const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(bo->totalSize, 64));
+    return be->magic == RT_EXT_MAGIC && be->top_level == 0;
+}
+
 __global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_desc *descs, const rt_instance_desc *const *ptrs, uint32_t n,
                                                              rt_aabb_node *boxes, rt_bvh_metadata *md, uint32_t *aabb_enc,
-                                                             rt_ext_header *tlas_ext) {
+                                                             rt_ext_header *tlas_ext, uint32_t *status) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float smn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, smx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     if (i < n) {
         rt_instance_desc d = ptrs ? *ptrs[i] : descs[i];
         const uint8_t *blas = reinterpret_cast<const uint8_t *>(uintptr_t(d.blas));
+        // A null BLAS address, or one that does not point at a finished rt_core bottom-level build, makes the instance
+        // inactive (empty box, mask 0) and raises status bit 2 (rt_get_status -> RT_ERR_INVALID_ARG) instead of faulting.
+        const bool valid = blas_is_valid(blas);
+        if (!valid) {
+            atomicOr(status, 4u);
+            d.instance_id_and_mask &= 0x00ffffffu;
+            d.blas = 0;
+        }
         const rt_aabb_node *root = reinterpret_cast<const rt_aabb_node *>(blas + 16);
         // a TLAS over a BLAS with procedural primitives needs hit groups with intersection programs (rt_trace_rays_hit_groups)
-        const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(reinterpret_cast<const rt_bvh_offsets *>(blas)->totalSize, 64));
-        if (be->has_procedural) atomicOr(&tlas_ext->has_procedural, 1u);
+        if (valid) {
+            const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(reinterpret_cast<const rt_bvh_offsets *>(blas)->totalSize, 64));
+            if (be->has_procedural) atomicOr(&tlas_ext->has_procedural, 1u);
+        }
         float bmn[3], bmx[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {  // BoundingBoxToAABB
-            bmn[k] = root->center[k] - root->halfDim[k];
-            bmx[k] = root->center[k] + root->halfDim[k];
+            bmn[k] = valid ? root->center[k] - root->halfDim[k] : FLT_MAX;
+            bmx[k] = valid ? root->center[k] + root->halfDim[k] : -FLT_MAX;
         }
         // TransformAABB: FL/RayTracingHelper.hlsli:340-366
         float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -1106,6 +1124,10 @@ __global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_d
             mx[0] = fmaxf(mx[0], v.x), mx[1] = fmaxf(mx[1], v.y), mx[2] = fmaxf(mx[2], v.z);
         }
         Box b = aabb_to_box(mn, mx);
+        if (!valid) {  // an empty box: the union with it leaves every ancestor unchanged and no ray passes its slab test
+#pragma unroll
+            for (int k = 0; k < 3; ++k) b.c[k] = 0.0f, b.h[k] = -FLT_MAX;
+        }
         rt_aabb_node nb;
 #pragma unroll
         for (int k = 0; k < 3; ++k) nb.center[k] = b.c[k], nb.halfDim[k] = b.h[k];
@@ -1128,10 +1150,12 @@ __global__ void __launch_bounds__(kThreads) k_load_instances(const rt_instance_d
         uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(md) + size_t(i) * 116);
 #pragma unroll
         for (int k = 0; k < 29; ++k) dst[k] = w[k];
+        if (valid) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {  // scene AABB from the re-derived corners of the stored box
-            smn[k] = b.c[k] - b.h[k];
-            smx[k] = b.c[k] + b.h[k];
+            for (int k = 0; k < 3; ++k) {  // scene AABB from the re-derived corners of the stored box
+                smn[k] = b.c[k] - b.h[k];
+                smx[k] = b.c[k] + b.h[k];
+            }
         }
     }
     block_reduce_aabb(smn, smx, aabb_enc);
@@ -1162,12 +1186,17 @@ __global__ void __launch_bounds__(kThreads) k_rearrange_instances(const rt_bvh_m
     pi.hit_group_and_flags = (w[13] & ~RT_PACKED_INSTANCE_IDENTITY) | (ident ? RT_PACKED_INSTANCE_IDENTITY : 0u);
     pi.instance_index = w[28];
     const uint8_t *blas = reinterpret_cast<const uint8_t *>(uintptr_t(uint64_t(w[14]) | (uint64_t(w[15]) << 32)));
-    const rt_bvh_offsets *bo = reinterpret_cast<const rt_bvh_offsets *>(blas);
-    const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(bo->totalSize, 64));
-    pi.blas_root_ref = be->root_ref;
-    pi.blas_wide = reinterpret_cast<const rt_wide_node *>(blas + be->off_wide);
-    pi.blas_tris = reinterpret_cast<const rt_packed_tri *>(blas + be->off_leaf);
-    pi.blas_wide4 = reinterpret_cast<const rt_wide4_node *>(blas + be->off_wide4);
+    if (blas != nullptr) {
+        const rt_bvh_offsets *bo = reinterpret_cast<const rt_bvh_offsets *>(blas);
+        const rt_ext_header *be = reinterpret_cast<const rt_ext_header *>(blas + align_up(bo->totalSize, 64));
+        pi.blas_root_ref = be->root_ref;
+        pi.blas_wide = reinterpret_cast<const rt_wide_node *>(blas + be->off_wide);
+        pi.blas_tris = reinterpret_cast<const rt_packed_tri *>(blas + be->off_leaf);
+        pi.blas_wide4 = reinterpret_cast<const rt_wide4_node *>(blas + be->off_wide4);
+    } else {  // inactive instance (k_load_instances cleared its mask and address)
+        pi.blas_root_ref = RT_NODE_LEAF_FLAG;
+        pi.blas_wide = nullptr, pi.blas_tris = nullptr, pi.blas_wide4 = nullptr;
+    }
     pi._pad = 0;
     packed[dst] = pi;
 }
@@ -1176,9 +1205,11 @@ __global__ void __launch_bounds__(kThreads) k_rearrange_instances(const rt_bvh_m
 struct SortPlan {
     uint32_t blocks, tiles_per_block;
 };
+constexpr uint32_t kSortHistRows = 148 * 8;  // rows of kRadix counters in the scratch buffer (a public prebuild size: device independent)
 SortPlan plan_sort(uint32_t n, int num_sms) {
     uint32_t tiles = (n + kSortTile - 1) / kSortTile;
-    uint32_t max_blocks = uint32_t(num_sms) * 4;
+    // the scratch layout (make_layout, sized without a context) reserves kSortHistRows histogram rows: blocks + the row totals
+    uint32_t max_blocks = std::min<uint32_t>(uint32_t(num_sms) * 4, kSortHistRows - 1);
     SortPlan p;
     p.blocks = std::max(1u, std::min(tiles, max_blocks));
     p.tiles_per_block = (tiles + p.blocks - 1) / p.blocks;
@@ -1207,7 +1238,7 @@ Layout make_layout(uint32_t n, bool top) {
     L.valsC = take(4 * nn);
     L.hier = take(12 * (2 * nn - 1));
     L.counters = take(4 * nn);
-    L.hist = take(4ull * kRadix * 148 * 8);
+    L.hist = take(4ull * kRadix * kSortHistRows);
     L.elems = take((top ? 32 : 48) * nn);  // BLAS: rt_packed_tri records in load order; TLAS: instance boxes
     L.meta = take((top ? 116 : 0) * nn);
     // treelet pass (bottom level only): one 24-byte box per node, the base-treelet list (FL/GpuBVH2Builder.cpp:376-408)
@@ -1601,9 +1632,11 @@ static int tlas_build_impl(rt_context *ctx, const rt_instance_desc *descs, const
     if (rc || n == 0) return rc;
     uint32_t *aabb_enc = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc);
     k_init_aabb<<<1, 32, 0, st>>>(aabb_enc);
+    if (performs_update(build_flags))  // the flag is re-derived from the instances of THIS update (only ever OR-ed below)
+        RT_CUDA(cudaMemsetAsync(result + R.ext + offsetof(rt_ext_header, has_procedural), 0, 4, st));
     k_load_instances<<<rt_div_up(n, kThreads), kThreads, 0, st>>>(descs, ptrs, n, reinterpret_cast<rt_aabb_node *>(scratch + L.elems),
                                                                  reinterpret_cast<rt_bvh_metadata *>(scratch + L.meta), aabb_enc,
-                                                                 reinterpret_cast<rt_ext_header *>(result + R.ext));
+                                                                 reinterpret_cast<rt_ext_header *>(result + R.ext), ctx->status);
     ctx->launches += 2;
     RT_LAUNCH_CHECK();
     return build_common(ctx, n, true, build_flags, scratch, result, L, R);

@@ -74,6 +74,8 @@ struct rt_context {
     // stage timing (optional)
     bool timing = false;
     bool collect_stats = false;  // instrumented trace kernels (rt_enable_trace_stats)
+    bool capture = false;        // rt_enable_debug_capture: dispatches run as one band and keep their stage products
+    uint64_t dbg_pixels = 0;     // pixels of the last captured dispatch (its workspace layout)
     cudaEvent_t ev[8] = {};
     bool ev_ready = false;
     double t_primary = 0, t_secondary = 0, t_shadow = 0;

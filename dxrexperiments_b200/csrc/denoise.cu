@@ -215,12 +215,9 @@ extern "C" int rt_denoise(rt_context *ctx, const float *direct, const float *ind
         idx = idx < 0 ? 0 : (idx > KERNEL_TAPS ? KERNEL_TAPS : idx);
         A.wts[i + MAX_EXTENT] = idx < 2 ? 1.0f : (idx < 3 ? 0.9f : (idx < 4 ? 0.75f : (idx < 5 ? 0.6f : (idx < 6 ? 0.5f : 0.0f))));
     }
-    static bool smem_opt_in = false;
-    if (!smem_opt_in) {
-        RT_CUDA(cudaFuncSetAttribute(k_denoise<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H_SMEM)));
-        RT_CUDA(cudaFuncSetAttribute(k_denoise<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(V_SMEM)));
-        smem_opt_in = true;
-    }
+    // the opt-in is a per-device attribute of the function: set it on every call (a process may hold contexts on several GPUs)
+    RT_CUDA(cudaFuncSetAttribute(k_denoise<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H_SMEM)));
+    RT_CUDA(cudaFuncSetAttribute(k_denoise<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(V_SMEM)));
     A.input = reinterpret_cast<const float4 *>(indirect_specular);
     A.out = reinterpret_cast<float4 *>(tmp);
     k_denoise<0><<<dim3(rt_div_up(width, H_TW), rt_div_up(height, H_TH)), kThreadsDn, H_SMEM, ctx->stream>>>(A);

@@ -38,7 +38,9 @@ constexpr int kBlock = 128;
 struct Launch {
     rt_per_frame_constants f;
     uint32_t width, height;  // full launch dimensions
-    uint32_t x0, y0, rw, rh; // pixel rectangle handled by this dispatch
+    uint32_t x0, y0, rw, rh; // pixel rectangle handled by this dispatch (rh counts the dispatch's own rows: "virtual" rows)
+    uint32_t v0;             // first virtual row of this band of the dispatch
+    uint32_t stripShift, stripGroups, stripGroup;  // strip-interleaved dispatch (stripGroups > 1): virtual row -> image row, see image_row()
     float jitterScale;
     uint32_t realtime;
     uint32_t shadowsPerHit;  // 2, or 4 in the ambient-occlusion debug view
@@ -71,6 +73,15 @@ enum : uint32_t {
     SLOT_UNIFORM = 16u,
     SLOT_AO = 32u,
 };
+
+// Image row of row `r` of a band.  A plain (region) dispatch covers rows y0 .. y0+rh-1.  A strip-interleaved dispatch
+// (rt_dispatch_rays_interleaved: screen-tile sharding across GPUs) covers the strips of 2^stripShift rows whose index is
+// congruent to stripGroup modulo stripGroups, packed into consecutive virtual rows.
+__device__ __forceinline__ uint32_t image_row(const Launch &L, uint32_t r) {
+    const uint32_t v = L.v0 + r;
+    if (L.stripGroups <= 1) return L.y0 + v;
+    return (((v >> L.stripShift) * L.stripGroups + L.stripGroup) << L.stripShift) + (v & ((1u << L.stripShift) - 1u));
+}
 
 __device__ __forceinline__ void store_ray(rt_ray *q, f3 o, float tmin, f3 d, float tmax) {
     float4 *p = reinterpret_cast<float4 *>(q);
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(kBlock, RT_PRIMARY_MIN_BLOCKS) k_primary(const
     const bool inside = lx < L.rw && ly < L.rh;
     TraceCtr ctr{0, 0, 0, 0};
     if (inside) {
-        const uint32_t x = L.x0 + lx, y = L.y0 + ly;
+        const uint32_t x = L.x0 + lx, y = image_row(L, ly);
         f3 o, d;
         primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
         TraceAccel A = resolve_tlas(tlas, status);
@@ -198,7 +209,7 @@ __device__ __forceinline__ void write_pixel(const Launch &L, float *out, uint64_
 __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
                                                           uint32_t n_recs, const float *env, uint32_t envSize, float *out0,
                                                           uint64_t pitch0, float *out1, uint64_t pitch1,
-                                                          unsigned long long *rayCounts) {
+                                                          unsigned long long *rayCounts, uint32_t *status) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t P = L.rw * L.rh;
     const bool inRange = p < P;
@@ -207,7 +218,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
     uint32_t x = 0, y = 0;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
     if (inRange) {
-        x = L.x0 + p % L.rw, y = L.y0 + p / L.rw;
+        x = L.x0 + p % L.rw, y = image_row(L, p / L.rw);
         primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
         hA = ws.hitA[p];
         isHit = __float_as_uint(hA.w) != RT_NO_HIT;
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
     uint32_t nShadow = 0, nSecondary = 0;
     if (isHit) {
         uint32_t rec = ws.hitRec[p];
-        if (rec >= n_recs) rec = 0;
+        if (rec >= n_recs) rec = 0, atomicOr(status, 8u);  // a hit on an instance without a bound record: rt_get_status -> RT_ERR_INVALID_ARG
         const rt_hit_record_dev &R = recs[rec];
         const uint32_t prim = __float_as_uint(hA.w);
         const f3 N = normalize3(interpolate_normal(R, prim, hA.y, hA.z));
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const 
 // term kept literally, so a zero pdf produces the same NaN as the shader).
 __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
                                                             uint32_t n_recs, const float *env, uint32_t envSize,
-                                                            unsigned long long *rayCounts) {
+                                                            unsigned long long *rayCounts, uint32_t *status) {
     const uint32_t cnt = ws.counters[0], n = cnt * 2;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t lr = base + threadIdx.x;
@@ -373,12 +384,12 @@ __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constan
                 } else {
                     kind = 2;
                     rec = ws.secRec[r];
-                    if (rec >= n_recs) rec = 0;
+                    if (rec >= n_recs) rec = 0, atomicOr(status, 8u);
                     const rt_hit_record_dev &R = recs[rec];
                     const f3 N = normalize3(interpolate_normal(R, __float_as_uint(hA.w), hA.y, hA.z));
                     pos = o + hA.x * d;
                     const uint32_t pix = ws.slotInfo[hitSlot].x;
-                    const uint32_t x = L.x0 + pix % L.rw, y = L.y0 + pix / L.rw;
+                    const uint32_t x = L.x0 + pix % L.rw, y = image_row(L, pix / L.rw);
                     uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
                     le = eval_lights(L.f, pos, N);
                     if (!L.realtime && L.f.options.debug == 2) {
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Laun
     const uint32_t n = ws.counters[0];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const uint4 info = ws.slotInfo[s];
-        const uint32_t x = L.x0 + info.x % L.rw, y = L.y0 + info.x / L.rw;
+        const uint32_t x = L.x0 + info.x % L.rw, y = image_row(L, info.x / L.rw);
         const rt_material_params &m = recs[info.y].mat;
         const uint32_t flags = info.z;
         f3 color;
@@ -618,6 +629,11 @@ int pgrid(rt_context *ctx) {
 int upload_records(rt_program *prog) {
     if (!prog->dirty) return RT_OK;
     rt_context *ctx = prog->ctx;
+    // RtBindings holds one record per (instance, ray type) (libs/DXRFramework/RtBindings.cpp:131-164): a hole inside the
+    // bound range would be shaded through null vertex / index buffers
+    for (uint32_t i = 0; i < prog->n_recs; ++i)
+        RT_REQUIRE(prog->host_recs[i].vb != nullptr && prog->host_recs[i].ib != nullptr,
+                   "unbound hit record inside the bound range (every instance needs a record for every ray type)");
     if (prog->n_recs) {
         RT_CUDA(cudaMemcpyAsync(prog->dev_recs, prog->host_recs, sizeof(rt_hit_record_dev) * prog->n_recs, cudaMemcpyHostToDevice, ctx->stream));
         // host_recs is pageable: the copy is staged before the call returns, so later edits are safe
@@ -633,14 +649,15 @@ extern "C" {
 static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, const WS &ws, cudaStream_t st, cudaStream_t side,
                          cudaEvent_t ev_fork, cudaEvent_t ev_join);
 
-int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t x1,
-                            uint32_t y1) {
+static int dispatch_impl(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t x1,
+                         uint32_t y1, uint32_t stripShift, uint32_t stripGroups, uint32_t stripGroup) {
     RT_REQUIRE(ctx && prog && prog->ctx == ctx, "context/program");
     RT_REQUIRE(ctx->tlas != nullptr, "no TLAS bound (rt_set_tlas)");
     RT_REQUIRE(ctx->output[0] != nullptr, "no output bound to slot 0 (rt_set_output)");
     RT_REQUIRE(prog->kind != RT_PROGRAM_REALTIME || ctx->output[1] != nullptr, "realtime program needs output slot 1");
     RT_REQUIRE(x0 < x1 && y0 < y1 && x1 <= width && y1 <= height, "pixel rectangle");
     RT_REQUIRE(ctx->pitch[0] >= uint64_t(width) * 16, "output pitch");
+    RT_REQUIRE(prog->kind != RT_PROGRAM_REALTIME || ctx->pitch[1] >= uint64_t(width) * 16, "output pitch of slot 1");
     RT_REQUIRE(prog->n_recs > 0, "no hit records bound (rt_bindings_set_hit_record)");
     RT_CUDA(cudaSetDevice(ctx->device));
     const bool realtime = prog->kind == RT_PROGRAM_REALTIME;
@@ -651,6 +668,7 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     L.f = ctx->frame;
     L.width = width, L.height = height;
     L.x0 = x0, L.y0 = y0, L.rw = x1 - x0, L.rh = y1 - y0;
+    L.v0 = 0, L.stripShift = stripShift, L.stripGroups = stripGroups, L.stripGroup = stripGroup;
     L.jitterScale = realtime ? 10.0f : 30.0f;  // S/ProgressiveRaytracing.hlsl:26, S/RealtimeRaytracing.hlsl:34
     L.realtime = realtime ? 1u : 0u;
     L.shadowsPerHit = (!realtime && L.f.options.showAmbientOcclusionOnly) ? 4u : 2u;
@@ -666,7 +684,7 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     // persistent kernels end with 8-20 % of their warps idle, k_primary leaves ~30 % of its warp slots unused — blocks of
     // the other band's kernels move in.  Bands touch disjoint pixels, so the image is bit-identical to the one-band run.
     // Instrumented and stage-timed dispatches, and small regions, run as one band.
-    const uint32_t bands = (!timing && !ctx->collect_stats && uint64_t(L.rw) * L.rh >= (1u << 18)) ? std::min<uint32_t>(RT_DISPATCH_BANDS, L.rh / 64) : 1u;
+    const uint32_t bands = (!timing && !ctx->collect_stats && !ctx->capture && uint64_t(L.rw) * L.rh >= (1u << 18)) ? std::min<uint32_t>(RT_DISPATCH_BANDS, L.rh / 64) : 1u;
     if (bands > 1) {
         if (!ctx->side_stream) {
             RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
@@ -687,7 +705,7 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
         RT_CUDA(cudaEventRecord(ctx->ev_band_fork, ctx->stream));
         for (uint32_t k = 0; k < bands; ++k) {
             Launch Lk = L;
-            Lk.y0 = L.y0 + y[k], Lk.rh = y[k + 1] - y[k];
+            Lk.v0 = y[k], Lk.rh = y[k + 1] - y[k];
             WS wk;
             rc = ensure_workspace(ctx, Pmax, wk, k, bands);
             if (rc) return rc;
@@ -707,6 +725,7 @@ int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, u
     WS ws;
     rc = ensure_workspace(ctx, P, ws);
     if (rc) return rc;
+    if (ctx->capture) ctx->dbg_pixels = P;
     if (!timing && !ctx->collect_stats && !ctx->side_stream) {
         RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
         RT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -730,7 +749,7 @@ static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, con
     else k_primary<false><<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status, sPrim);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[1], st));
     k_shade_primary<<<rt_div_up(P, kBlock), kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
-                                                             ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts);
+                                                             ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts, ctx->status);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
     // The depth-0 shadow wave and the secondary-ray chain (trace -> shade -> depth-1 shadow wave) both depend only on
     // k_shade_primary and meet again in k_resolve.  Outside the instrumented / per-stage-timed modes the shadow wave
@@ -751,7 +770,7 @@ static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, con
         if (overlap) RT_CUDA(cudaEventRecord(ev_join, side));
     }
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[4], st));
-    k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts);
+    k_shade_secondary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->ray_counts, ctx->status);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[5], st));
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
     else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
@@ -773,6 +792,26 @@ static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, con
         ctx->t_shadow += ms;
     }
     return RT_OK;
+}
+
+int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t x1,
+                            uint32_t y1) {
+    return dispatch_impl(ctx, prog, width, height, x0, y0, x1, y1, 0, 1, 0);
+}
+
+int rt_dispatch_rays_interleaved(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t strip_rows, uint32_t groups,
+                                 uint32_t group) {
+    RT_REQUIRE(groups >= 1 && group < groups, "strip group");
+    RT_REQUIRE(strip_rows >= 4 && (strip_rows & (strip_rows - 1)) == 0, "strip_rows must be a power of two >= 4");
+    if (groups == 1) return dispatch_impl(ctx, prog, width, height, 0, 0, width, height, 0, 1, 0);
+    uint32_t shift = 0;
+    while ((1u << shift) < strip_rows) ++shift;
+    // rows of this group: whole strips group, group + groups, ... plus the part of the last strip inside the image
+    const uint32_t strips = (height + strip_rows - 1) / strip_rows;
+    uint32_t rows = 0;
+    for (uint32_t k = group; k < strips; k += groups) rows += std::min(strip_rows, height - k * strip_rows);
+    if (rows == 0) return RT_OK;  // more groups than strips: nothing to render for this one
+    return dispatch_impl(ctx, prog, width, height, 0, 0, width, rows, shift, groups, group);
 }
 
 int rt_dispatch_rays(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t /*depth*/) {
@@ -855,6 +894,59 @@ int rt_generate_primary_rays(rt_context *ctx, const rt_per_frame_constants *fram
     k_primary_rays<<<rt_div_up(uint64_t(width) * height, kBlock), kBlock, 0, ctx->stream>>>(L, rays);
     ctx->launches++;
     RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
+// ---- parity instrumentation: the stage products of the last captured dispatch (SURVEY.md 8b "rt_trace_primary_ids")
+int rt_enable_debug_capture(rt_context *ctx, int enable) {
+    RT_REQUIRE(ctx != nullptr, "ctx");
+    ctx->capture = enable != 0;
+    if (!enable) ctx->dbg_pixels = 0;
+    return RT_OK;
+}
+
+int rt_debug_counts(rt_context *ctx, uint32_t *pixels, uint32_t *hit_slots, uint32_t *shadow1_pairs) {
+    RT_REQUIRE(ctx && ctx->dbg_pixels > 0, "no captured dispatch (rt_enable_debug_capture, then dispatch)");
+    RT_CUDA(cudaSetDevice(ctx->device));
+    WS ws;
+    int rc = ensure_workspace(ctx, ctx->dbg_pixels, ws);
+    if (rc) return rc;
+    uint32_t c[2] = {0, 0};
+    RT_CUDA(cudaMemcpyAsync(c, ws.counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pixels) *pixels = uint32_t(ctx->dbg_pixels);
+    if (hit_slots) *hit_slots = c[0];
+    if (shadow1_pairs) *shadow1_pairs = c[1];
+    return RT_OK;
+}
+
+int rt_debug_download(rt_context *ctx, int array, uint32_t plane, void *host, uint64_t host_bytes) {
+    RT_REQUIRE(ctx && host, "null argument");
+    uint32_t P = 0, slots = 0, pairs = 0;
+    int rc = rt_debug_counts(ctx, &P, &slots, &pairs);
+    if (rc) return rc;
+    WS ws;
+    rc = ensure_workspace(ctx, P, ws);
+    if (rc) return rc;
+    const uint8_t *src = nullptr;
+    uint64_t elem = 0, count = 0, max_plane = 1;
+    switch (array) {
+        case RT_DEBUG_PRIMARY_HITS: src = (const uint8_t *)ws.hitA, elem = 16, count = P; break;
+        case RT_DEBUG_PRIMARY_RECORDS: src = (const uint8_t *)ws.hitRec, elem = 4, count = P; break;
+        case RT_DEBUG_SLOT_INFO: src = (const uint8_t *)ws.slotInfo, elem = 16, count = slots; break;
+        case RT_DEBUG_SECONDARY_RAYS: src = (const uint8_t *)(ws.secQ + size_t(plane) * ws.plane), elem = 32, count = slots, max_plane = 2; break;
+        case RT_DEBUG_SECONDARY_HITS: src = (const uint8_t *)(ws.secHitA + size_t(plane) * ws.plane), elem = 16, count = slots, max_plane = 2; break;
+        case RT_DEBUG_SECONDARY_RECORDS: src = (const uint8_t *)(ws.secRec + size_t(plane) * ws.plane), elem = 4, count = slots, max_plane = 2; break;
+        case RT_DEBUG_SHADOW0_RAYS: src = (const uint8_t *)(ws.shadowQ0 + size_t(plane) * ws.plane), elem = 32, count = slots, max_plane = 4; break;
+        case RT_DEBUG_SHADOW0_VISIBILITY: src = ws.vis0 + size_t(plane) * ws.plane, elem = 1, count = slots, max_plane = 4; break;
+        case RT_DEBUG_SHADOW1_RAYS: src = (const uint8_t *)(ws.shadowQ1 + size_t(plane) * 2 * ws.plane), elem = 32, count = pairs, max_plane = 2; break;
+        case RT_DEBUG_SHADOW1_VISIBILITY: src = ws.vis1 + size_t(plane) * 2 * ws.plane, elem = 1, count = pairs, max_plane = 2; break;
+        default: RT_REQUIRE(false, "unknown debug array");
+    }
+    RT_REQUIRE(plane < max_plane, "plane");
+    RT_REQUIRE(host_bytes >= elem * count, "host buffer too small (rt_debug_counts gives the element counts)");
+    if (count) RT_CUDA(cudaMemcpyAsync(host, src, elem * count, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
 

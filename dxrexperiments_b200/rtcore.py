@@ -90,6 +90,15 @@ def _load():
         "rt_trace_rays_hit_groups": (i32, [vp, vp, vp, u64, u32, u32, u32, u32, vp, u32, vp]),
         "rt_generate_primary_rays": (i32, [vp, vp, u32, u32, C.c_float, vp]),
         "rt_scale_buffer": (i32, [vp, vp, u64, C.c_float]),
+        "rt_dispatch_rays_interleaved": (i32, [vp, vp, u32, u32, u32, u32, u32]),
+        "rt_enable_debug_capture": (i32, [vp, i32]),
+        "rt_debug_counts": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "rt_debug_download": (i32, [vp, i32, u32, vp, u64]),
+        "rt_comm_get_unique_id": (i32, [vp]),
+        "rt_comm_create": (i32, [vp, vp, i32, i32, pp]),
+        "rt_comm_destroy": (i32, [vp]),
+        "rt_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "rt_accum_reduce": (i32, [vp, vp, vp, vp, u64, C.c_float, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -342,6 +351,32 @@ class Context:
         check(lib.rt_get_ray_counts(self.handle, C.byref(c), 1 if reset else 0))
         return c
 
+    # ---------------------------------------------------------------- parity instrumentation
+    DEBUG_ARRAYS = {"primary_hits": (0, "pixels", np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])),
+                    "primary_records": (1, "pixels", np.dtype("<u4")),
+                    "slot_info": (2, "slots", np.dtype([("pixel", "<u4"), ("record", "<u4"), ("flags", "<u4"), ("pad", "<u4")])),
+                    "secondary_rays": (3, "slots", T.RAY_DTYPE),
+                    "secondary_hits": (4, "slots", np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])),
+                    "secondary_records": (5, "slots", np.dtype("<u4")),
+                    "shadow0_rays": (6, "slots", T.RAY_DTYPE), "shadow0_visibility": (7, "slots", np.dtype("u1")),
+                    "shadow1_rays": (8, "pairs", T.RAY_DTYPE), "shadow1_visibility": (9, "pairs", np.dtype("u1"))}
+
+    def enable_debug_capture(self, on=True):
+        check(lib.rt_enable_debug_capture(self.handle, 1 if on else 0))
+
+    def debug_counts(self):
+        p, s, q = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib.rt_debug_counts(self.handle, C.byref(p), C.byref(s), C.byref(q)))
+        return {"pixels": p.value, "slots": s.value, "pairs": q.value}
+
+    def debug_array(self, name: str, plane: int = 0) -> np.ndarray:
+        """A stage product of the last captured dispatch (rt_debug_download)."""
+        code, which, dtype = self.DEBUG_ARRAYS[name]
+        n = self.debug_counts()[which]
+        out = np.zeros(max(n, 1), dtype=dtype)
+        check(lib.rt_debug_download(self.handle, code, plane, out.ctypes.data, out.nbytes))
+        return out[:n]
+
     def enable_trace_stats(self, on=True):
         check(lib.rt_enable_trace_stats(self.handle, 1 if on else 0))
 
@@ -501,6 +536,59 @@ class Program:
 PROGRESSIVE, REALTIME = 0, 1
 
 
+class Comm:
+    """rt_comm: the NCCL communicator behind rt_accum_reduce (one process per GPU).
+
+    ``exchange(id_bytes_or_None) -> id_bytes`` is the side channel that carries rank 0's 128-byte unique id to every
+    rank: rank 0 calls it with the bytes, the others with None (torch.distributed broadcast, a shared file, MPI ...)."""
+
+    def __init__(self, ctx: Context, world: int, rank: int, exchange):
+        self.ctx, self.world, self.rank = ctx, world, rank
+        uid = None
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            check(lib.rt_comm_get_unique_id(buf))
+            uid = bytes(buf)
+        uid = exchange(uid)
+        assert len(uid) == 128
+        h = C.c_void_p()
+        check(lib.rt_comm_create(ctx.handle, (C.c_uint8 * 128).from_buffer_copy(uid), world, rank, C.byref(h)))
+        self.handle = h.value
+
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        check(lib.rt_comm_info(self.handle, None, None, C.byref(v)))
+        return v.value
+
+    def reduce(self, send_ptr, recv_ptr, count: int, weight: float, root: int = 0):
+        check(lib.rt_accum_reduce(self.ctx.handle, self.handle, send_ptr, recv_ptr, count, weight, root))
+
+    def close(self):
+        if self.handle:
+            lib.rt_comm_destroy(self.handle)
+            self.handle = None
+
+
+def file_exchange(path: str, timeout_s: float = 120.0):
+    """Unique-id side channel over a shared file (no torch.distributed needed): rank 0 writes, the others poll."""
+    import time
+
+    def exchange(uid):
+        if uid is not None:
+            tmp = path + ".tmp"
+            with open(tmp, "wb") as f:
+                f.write(uid)
+            os.replace(tmp, path)
+            return uid
+        t0 = time.time()
+        while time.time() - t0 < timeout_s:
+            if os.path.exists(path) and os.path.getsize(path) == 128:
+                return open(path, "rb").read()
+            time.sleep(0.01)
+        raise TimeoutError(f"no NCCL unique id at {path}")
+    return exchange
+
+
 class Renderer:
     """Convenience host for tests/bench: one scene (instances of meshes), one program, fp32 outputs on the device."""
 
@@ -525,13 +613,16 @@ class Renderer:
         self.out = list(outputs) if outputs is not None else [ctx.alloc(16 * width * height).zero() for _ in range(n_out)]
         assert len(self.out) == n_out
 
-    def dispatch(self, frame: T.PerFrameConstants, region=None):
+    def dispatch(self, frame: T.PerFrameConstants, region=None, strips=None):
+        """region: (x0, y0, x1, y1) pixel rectangle; strips: (strip_rows, groups, group) strip-interleaved shard."""
         # global root arguments are (re)bound per dispatch, as render() does (ProgressiveRaytracingPipeline.cpp:236-242)
         for slot, o in enumerate(self.out):
             check(lib.rt_set_output(self.ctx.handle, slot, o.ptr, 16 * self.width))
         check(lib.rt_set_tlas(self.ctx.handle, self.tlas.result.ptr))
         check(lib.rt_set_frame_constants(self.ctx.handle, C.byref(frame)))
-        if region is None:
+        if strips is not None:
+            check(lib.rt_dispatch_rays_interleaved(self.ctx.handle, self.program.handle, self.width, self.height, *strips))
+        elif region is None:
             check(lib.rt_dispatch_rays(self.ctx.handle, self.program.handle, self.width, self.height, 3))
         else:
             x0, y0, x1, y1 = region

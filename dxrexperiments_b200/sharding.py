@@ -6,10 +6,58 @@ random numbers are a pure function of (pixel, frameCount), so rank r rendering g
 would have rendered; only the order of the fp32 summation differs.
 
 Each rank keeps the reference's running mean over ITS samples (RayGen: ProgressiveRaytracing.hlsl:36-38).
-To combine, a rank scales its buffer by ``n_rank / n_total`` (``rt_scale_buffer``) and one sum-reduce
-(NCCL on GPUs, gloo in the CPU tests) adds the buffers onto the root.
+To combine, one weighted sum-reduce adds the buffers onto the root: ``rt_accum_reduce`` (NCCL, the weight
+``n_rank / n_total`` applied inside the reduction) on GPUs, gloo in the CPU tests.
+
+:func:`plan` combines both axes: ``world = strip_groups x sample_groups``.  Rank ``r`` belongs to strip group
+``r % strip_groups`` (it renders every ``strip_groups``-th horizontal strip, ``rt_dispatch_rays_interleaved``, a balanced
+split of sky and geometry) and to sample group ``r // strip_groups`` (it renders that group's round-robin share of the
+samples).  Its buffer is zero outside its strips, so the same reduce assembles the frame.
 """
+from dataclasses import dataclass
 from typing import List, Tuple
+
+
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    strip_groups: int
+    strip_group: int
+    sample_groups: int
+    sample_group: int
+    samples: List[int]   # global sample indices (= frameCount values) this rank renders
+    weight: float        # this rank's weight in the reduce: len(samples) / total_samples
+    strip_rows: int
+
+    def rows(self, height: int) -> List[int]:
+        """Image rows this rank renders."""
+        return [y for y in range(height) if (y // self.strip_rows) % self.strip_groups == self.strip_group]
+
+
+def default_strip_groups(world: int, total_samples: int) -> int:
+    """Shard by sample index as far as the samples go (identical work on every rank), by strips beyond that."""
+    g = 1
+    while world // g > max(total_samples, 1) or world % g:
+        g += 1
+    return g
+
+
+def plan(rank: int, world: int, total_samples: int, strip_groups: int = None, strip_rows: int = 32) -> ShardPlan:
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    if total_samples <= 0:
+        raise ValueError("total_samples must be positive")
+    if strip_groups is None:
+        strip_groups = default_strip_groups(world, total_samples)
+    if strip_groups < 1 or world % strip_groups:
+        raise ValueError("world must be a multiple of strip_groups")
+    if strip_rows < 4 or strip_rows & (strip_rows - 1):
+        raise ValueError("strip_rows must be a power of two >= 4")
+    sample_groups = world // strip_groups
+    sg, tg = rank // strip_groups, rank % strip_groups
+    samples = list(range(sg, total_samples, sample_groups))
+    return ShardPlan(rank, world, strip_groups, tg, sample_groups, sg, samples, len(samples) / float(total_samples), strip_rows)
 
 
 def samples_for_rank(rank: int, world: int, total_samples: int) -> List[int]:

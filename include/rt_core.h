@@ -185,6 +185,12 @@ int rt_dispatch_rays(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t
  * sharding across GPUs.  Pixels outside the rectangle are not touched. */
 int rt_dispatch_rays_region(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t x0,
                             uint32_t y0, uint32_t x1, uint32_t y1);
+/* Same, restricted to every `groups`-th horizontal strip of `strip_rows` image rows (a power of two >= 4), starting
+ * with strip `group`: screen-tile sharding of one frame across GPUs with a balanced load (SURVEY.md 8e ii; the
+ * reference is single-GPU, libs/DXRFramework/RtContext.cpp:23).  One dispatch covers all of the group's strips, so
+ * the kernels stay as large as a contiguous region of the same area.  Pixels of other groups are not touched. */
+int rt_dispatch_rays_interleaved(rt_context *ctx, rt_program *prog, uint32_t width, uint32_t height, uint32_t strip_rows,
+                                 uint32_t groups, uint32_t group);
 /* Rays traced by all dispatches since the last reset (synchronises). */
 int rt_get_ray_counts(rt_context *ctx, rt_ray_counts *counts, int reset);
 /* Instrumented traversal: while enabled, dispatches run trace kernels that count node visits and triangle tests
@@ -197,6 +203,29 @@ int rt_get_trace_stats(rt_context *ctx, rt_trace_stats *primary, rt_trace_stats 
  * accumulated milliseconds: primary closest-hit, incoherent secondary closest-hit, shadow any-hit. */
 int rt_enable_stage_timing(rt_context *ctx, int enable);
 int rt_get_stage_timing(rt_context *ctx, double *primary_ms, double *secondary_ms, double *shadow_ms, int reset);
+
+/* Parity instrumentation (test infrastructure of the boundary, never on a timed path): while capture is enabled a
+ * dispatch runs as ONE pixel band (the same kernels, bit-identical results) and its stage products stay readable:
+ * the camera rays' hits written by the ray-generation kernel (the north star's "primary-ray hit triangle IDs"),
+ * the compacted secondary / shadow ray queues and what the queue traversal kernels answered.  Queues are planar:
+ * `plane` selects the ray kind (secondary: 0 indirect diffuse, 1 Phong lobe; shadow: 0 directional, 1 point light,
+ * 2-3 ambient-occlusion debug view).  There is no reference counterpart (the Fallback Layer keeps this state in
+ * registers of its uber shader, FL/TraverseShader.hlsli:21-73); the oracle re-traces the downloaded rays. */
+typedef enum rt_debug_array {
+    RT_DEBUG_PRIMARY_HITS = 0,       /* pixels x {float t, u, v; uint32 PrimitiveIndex (0xFFFFFFFF = miss)}, pixel order of the dispatch */
+    RT_DEBUG_PRIMARY_RECORDS = 1,    /* pixels x uint32 hit-group record index (InstanceContribution + ray type) */
+    RT_DEBUG_SLOT_INFO = 2,          /* hit_slots x {uint32 pixel, record, flags, 0} */
+    RT_DEBUG_SECONDARY_RAYS = 3,     /* hit_slots x rt_ray per plane; tmax < 0 marks an inactive slot */
+    RT_DEBUG_SECONDARY_HITS = 4,     /* hit_slots x {t, u, v, PrimitiveIndex} per plane */
+    RT_DEBUG_SECONDARY_RECORDS = 5,  /* hit_slots x uint32 per plane */
+    RT_DEBUG_SHADOW0_RAYS = 6,       /* hit_slots x rt_ray per plane (depth-0 shadow rays) */
+    RT_DEBUG_SHADOW0_VISIBILITY = 7, /* hit_slots x uint8 per plane: 1 = unoccluded */
+    RT_DEBUG_SHADOW1_RAYS = 8,       /* shadow1_pairs x rt_ray per plane (shadow rays of the secondary hits) */
+    RT_DEBUG_SHADOW1_VISIBILITY = 9  /* shadow1_pairs x uint8 per plane */
+} rt_debug_array;
+int rt_enable_debug_capture(rt_context *ctx, int enable);
+int rt_debug_counts(rt_context *ctx, uint32_t *pixels, uint32_t *hit_slots, uint32_t *shadow1_pairs); /* synchronises */
+int rt_debug_download(rt_context *ctx, int array, uint32_t plane, void *host, uint64_t host_bytes);   /* synchronises */
 
 /* DenoiseCompositor::dispatch (src/DenoiseCompositor.cpp:109-148): pass H (joint = direct, input =
  * indirect specular -> tmp) then pass V (-> out, + direct, exposure, Reinhard, gamma).  RGBA fp32, tightly packed. */
@@ -231,6 +260,27 @@ int rt_generate_primary_rays(rt_context *ctx, const rt_per_frame_constants *fram
 /* buf[i] *= scale  (i < count floats): turns a rank's running mean into its share of the global mean
  * before the NCCL sum of the accumulation buffers. */
 int rt_scale_buffer(rt_context *ctx, float *buf, uint64_t count, float scale);
+
+
+/* ---- multi-GPU accumulation: one process per GPU, replicated acceleration structures, the frame split
+ * by sample index (frameCount = global sample index) and / or by screen strips (rt_dispatch_rays_interleaved), and ONE
+ * NCCL reduce per output frame.  New work of this library: the reference has no multi-GPU path (NodeMask is always 0,
+ * libs/DXRFramework/RtContext.cpp:23, FL/GpuBVH2Builder.cpp:17).  libnccl.so.2 is bound at run time on first use
+ * (RT_NCCL_LIB overrides the name); without it these calls return RT_ERR_UNSUPPORTED and everything else works.
+ *   rank 0: rt_comm_get_unique_id -> hand the 128 bytes to every rank over any side channel (file, MPI, a
+ *   torch.distributed broadcast) -> all ranks: rt_comm_create (collective) -> per frame: rt_accum_reduce. */
+#define RT_COMM_ID_BYTES 128
+typedef struct rt_comm rt_comm;
+int rt_comm_get_unique_id(uint8_t *id /* RT_COMM_ID_BYTES */);
+int rt_comm_create(rt_context *ctx, const uint8_t *id, int world_size, int rank, rt_comm **out);
+int rt_comm_destroy(rt_comm *comm);
+int rt_comm_info(const rt_comm *comm, int *world_size, int *rank, int *nccl_version);
+/* recv[i] = sum over ranks r of weight_r * send_r[i], i < count floats, on rank `root` (root = -1: on every rank).
+ * `weight` is this rank's share of the frame's samples (its spp / total spp for running-mean accumulation buffers,
+ * 1 for sums); it is applied inside the reduction, not by a separate pass.  Stream-ordered on the context's stream;
+ * recv may equal send (in place) and is ignored on non-root ranks.  Strip-sharded ranks pass full-frame buffers that
+ * are zero outside their strips. */
+int rt_accum_reduce(rt_context *ctx, rt_comm *comm, const float *send, float *recv, uint64_t count, float weight, int root);
 
 #ifdef __cplusplus
 }

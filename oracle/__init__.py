@@ -24,13 +24,29 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+def use_native() -> str:
+    """CPU-baseline build of the same sources: -O3 -march=native, compiled ON THE MACHINE THAT RUNS IT (oracle/_native/
+    is git- and gpurun-ignored, so a library built for another CPU never travels).  Must be called before the first
+    lib() call; falls back to the portable -O2 library if the compile fails.  Returns the flags in use."""
+    global _SO
+    if _lib is not None:  # already loaded: report what is in use
+        return "-O3 -march=native -ffp-contract=off" if _SO.endswith("liboracle_native.so") else "-O2 -ffp-contract=off"
+    try:
+        subprocess.run(["make", "-C", _DIR, "-s", "native"], check=True, capture_output=True, timeout=600)
+        _SO = os.path.join(_DIR, "_native", "liboracle_native.so")
+        return "-O3 -march=native -ffp-contract=off"
+    except Exception:
+        return "-O2 -ffp-contract=off (native build failed)"
+
+
 _lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if _SO.endswith("liboracle.so"):
+            build()
         L = C.CDLL(_SO)
         vp, u32, u64, i32, f32p = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_float)
         L.orc_scene_aabb.argtypes = [vp, u32, vp]

@@ -123,6 +123,25 @@ def test_sharding_plans():
     assert (cover == 1).all()
     with pytest.raises(ValueError):
         sharding.samples_for_rank(4, 4, 10)
+    # strip x sample plans: every (row, sample) is rendered exactly once, the weights of a row's owners add up to 1
+    for world, spp, groups in [(1, 5, None), (2, 8, 1), (2, 8, 2), (4, 6, 2), (8, 64, None), (8, 64, 2), (8, 2, None), (6, 3, 3)]:
+        h = 77
+        hits = np.zeros((h, spp), int)
+        wsum = np.zeros(h)
+        for r in range(world):
+            pl = sharding.plan(r, world, spp, strip_groups=groups, strip_rows=8)
+            assert pl.strip_groups * pl.sample_groups == world
+            rows = pl.rows(h)
+            for smp in pl.samples:
+                hits[rows, smp] += 1
+            wsum[rows] += pl.weight
+        assert (hits == 1).all(), (world, spp, groups)
+        np.testing.assert_allclose(wsum, 1.0, rtol=1e-12)
+    assert sharding.default_strip_groups(8, 64) == 1 and sharding.default_strip_groups(8, 2) == 4 and sharding.default_strip_groups(8, 1) == 8
+    with pytest.raises(ValueError):
+        sharding.plan(0, 4, 8, strip_groups=3)
+    with pytest.raises(ValueError):
+        sharding.plan(0, 4, 8, strip_groups=2, strip_rows=12)
 
 
 WORKER = r'''
@@ -139,9 +158,12 @@ case = cornell_case(); tlas, recs = case.oracle(oracle)
 w = h = 24; total = 6
 jit = scenes.jitter_sequence(9, total, w, h)
 acc = np.zeros((h, w, 4), np.float32)
-for local, s in enumerate(sharding.samples_for_rank(rank, world, total)):
+plan = sharding.plan(rank, world, total, strip_groups=int(os.environ["STRIP_GROUPS"]), strip_rows=4)
+for local, s in enumerate(plan.samples):
     oracle.render_progressive(tlas, recs, case.env, scenes.make_frame(case.setup, w, h, s, local, jitter=jit[s]), w, h, acc)
-t = torch.from_numpy(acc * np.float32(sharding.combine_scale(rank, world, total)))
+mine = np.zeros(h, bool); mine[plan.rows(h)] = True
+acc[~mine] = 0  # a strip-interleaved dispatch leaves the other groups' rows untouched (zero)
+t = torch.from_numpy(acc * np.float32(plan.weight))
 dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
 if rank == 0:
     ref = np.zeros((h, w, 4), np.float32)
@@ -154,12 +176,13 @@ dist.destroy_process_group()
 '''
 
 
-def test_sample_sharded_accumulation_world2_gloo(tmp_path):
-    """N > 1 host logic on CPU: two gloo ranks render interleaved samples (the oracle stands in for the renderer),
-    scale by their share and sum-reduce; rank 0 must hold the single-process 6-spp frame."""
+@pytest.mark.parametrize("strip_groups", [1, 2])
+def test_sample_sharded_accumulation_world2_gloo(tmp_path, strip_groups):
+    """N > 1 host logic on CPU: two gloo ranks render their shard of the samples / strips (the oracle stands in for the
+    renderer), weight by their share and sum-reduce; rank 0 must hold the single-process 6-spp frame."""
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", OMP_NUM_THREADS="1", STRIP_GROUPS=str(strip_groups))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29731", str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

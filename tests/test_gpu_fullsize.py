@@ -53,6 +53,11 @@ def test_c2_1080p_frame_hit_ids_and_sample_shards(ctx, rt, orc):
     assert _ids_agree(hg, ho) >= HIT_ID_MIN
     hit = (hg["primitive_index"] == ho["primitive_index"]) & (ho["primitive_index"] != T.NO_HIT)
     np.testing.assert_array_equal(hg["t"][hit], ho["t"][hit])
+    # criterion 2 for the kernels a dispatch really runs (k_primary, k_trace_persistent<0>/<1>) on all 2 073 600 pixels
+    from test_gpu_stage_parity import check_stages
+    rr = _renderer(rt, ctx, wl, env)
+    traced, shadows = check_stages(ctx, orc, otlas, rr, frame0, W, H, threads=16)
+    assert traced > 1_000_000 and shadows > 1_000_000
     # criterion 3: 2 spp of the 1080p frame against the oracle
     acc = np.zeros((H, W, 4), np.float32)
     for s in range(2):
