@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <fstream>
 #include <map>
+#include <chrono>
 #include <sstream>
+#include <thread>
 #include <tuple>
 
 #include "RtBindings.h"
@@ -35,7 +37,43 @@ void RtBuffer::clear() { ThrowIfFailed(rt_memset(mCtx, mPtr, 0, mBytes), "rt_mem
 
 RtContext::SharedPtr RtContext::create(int deviceOrdinal) { return SharedPtr(new RtContext(deviceOrdinal)); }
 RtContext::RtContext(int deviceOrdinal) { ThrowIfFailed(rt_context_create(deviceOrdinal, &mCtx), "rt_context_create"); }
-RtContext::~RtContext() { rt_context_destroy(mCtx); }
+RtContext::~RtContext() {
+    rt_comm_destroy(mComm);
+    rt_context_destroy(mCtx);
+}
+
+void RtContext::joinCommunicator(int worldSize, int rank, const std::string &idFile) {
+    ThrowIfFalse(mComm == nullptr, "joinCommunicator: already joined");
+    ThrowIfFalse(worldSize >= 1 && rank >= 0 && rank < worldSize && !idFile.empty(), "joinCommunicator: world / rank / id file");
+    uint8_t id[RT_COMM_ID_BYTES];
+    if (rank == 0) {
+        ThrowIfFailed(rt_comm_get_unique_id(id), "rt_comm_get_unique_id");
+        const std::string tmp = idFile + ".tmp";
+        {
+            std::ofstream f(tmp, std::ios::binary);
+            f.write(reinterpret_cast<const char *>(id), sizeof(id));
+            ThrowIfFalse(bool(f), "joinCommunicator: cannot write the id file");
+        }
+        ThrowIfFalse(std::rename(tmp.c_str(), idFile.c_str()) == 0, "joinCommunicator: cannot publish the id file");
+    } else {
+        bool got = false;
+        for (int tries = 0; tries < 12000 && !got; ++tries) {  // up to two minutes
+            std::ifstream f(idFile, std::ios::binary);
+            if (f && f.read(reinterpret_cast<char *>(id), sizeof(id)) && f.gcount() == std::streamsize(sizeof(id))) got = true;
+            else std::this_thread::sleep_for(std::chrono::milliseconds(10));
+        }
+        ThrowIfFalse(got, "joinCommunicator: no NCCL unique id appeared in the id file");
+    }
+    ThrowIfFailed(rt_comm_create(mCtx, id, worldSize, rank, &mComm), "rt_comm_create");
+    mWorld = worldSize, mRank = rank;
+}
+
+void RtContext::reduceAccumulation(const RtBuffer::SharedPtr &send, const RtBuffer::SharedPtr &recv, uint64_t floats, float weight, int root) {
+    ThrowIfFalse(mComm != nullptr, "reduceAccumulation: joinCommunicator first");
+    ThrowIfFalse(send && send->size() >= floats * 4 && (!recv || recv->size() >= floats * 4), "reduceAccumulation: buffer sizes");
+    ThrowIfFailed(rt_accum_reduce(mCtx, mComm, static_cast<const float *>(send->ptr()), recv ? static_cast<float *>(recv->ptr()) : nullptr, floats,
+                                  weight, root), "rt_accum_reduce");
+}
 
 RtBuffer::SharedPtr RtContext::createBuffer(uint64_t bytes) { return RtBuffer::SharedPtr(new RtBuffer(mCtx, bytes)); }
 RtBuffer::SharedPtr RtContext::createBuffer(const void *initialData, uint64_t bytes) {
@@ -50,6 +88,30 @@ uint64_t RtContext::launchCount() const { return rt_launch_count(mCtx); }
 void RtContext::raytrace(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height, uint32_t depth) {
     ThrowIfFalse(bindings && state && state->getProgram(), "raytrace: bindings/state without a program");
     ThrowIfFailed(rt_dispatch_rays(mCtx, state->getProgram()->getNative(), width, height, depth), "rt_dispatch_rays");
+}
+
+void RtContext::raytraceStrips(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height,
+                               uint32_t stripRows, uint32_t groups, uint32_t group) {
+    ThrowIfFalse(bindings && state && state->getProgram(), "raytraceStrips: bindings/state without a program");
+    ThrowIfFailed(rt_dispatch_rays_interleaved(mCtx, state->getProgram()->getNative(), width, height, stripRows, groups, group),
+                  "rt_dispatch_rays_interleaved");
+}
+
+void RtContext::traceRays(std::shared_ptr<RtProgram> program, std::shared_ptr<RtScene> scene, const rt_ray *rays, uint64_t n, uint32_t rayFlags,
+                          uint32_t instanceMask, uint32_t rayContribution, uint32_t geometryMultiplier, rt_hit *hits) {
+    ThrowIfFalse(program && scene && scene->getTlasWrappedPtr(), "traceRays: program / built scene");
+    ThrowIfFalse(n == 0 || (rays && hits), "traceRays: null ray or hit array");
+    // one table entry per shader-table hit record: [instance][ray type], as RtBindings lays them out (RtBindings.cpp:131-164)
+    const uint32_t groups = program->getHitProgramCount();
+    std::vector<rt_hit_group_programs> table(size_t(scene->getNumInstances()) * groups);
+    for (size_t r = 0; r < table.size(); ++r) table[r] = program->getHitGroupPrograms(uint32_t(r % groups));
+    auto dRays = createBuffer(rays, std::max<uint64_t>(n * sizeof(rt_ray), 32));
+    auto dHits = createBuffer(std::max<uint64_t>(n * sizeof(rt_hit), 32));
+    ThrowIfFailed(rt_trace_rays_hit_groups(mCtx, scene->getTlasWrappedPtr(), static_cast<const rt_ray *>(dRays->ptr()), n, rayFlags, instanceMask,
+                                           rayContribution, geometryMultiplier, table.data(), uint32_t(table.size()),
+                                           static_cast<rt_hit *>(dHits->ptr())), "rt_trace_rays_hit_groups");
+    if (n) dHits->download(hits, n * sizeof(rt_hit));
+    checkDeviceStatus();
 }
 
 // ============================================================================================ RtModel
@@ -163,17 +225,34 @@ RtModel::RtModel(RtContext::SharedPtr context, std::vector<Vertex> vertices, std
 
 RtModel::~RtModel() = default;
 
+RtModel::SharedPtr RtModel::createProcedural(RtContext::SharedPtr context, const std::vector<float> &aabbs, bool opaque) {
+    ThrowIfFalse(!aabbs.empty() && aabbs.size() % 6 == 0, "createProcedural: 6 floats {min, max} per AABB");
+    // the AABB buffer takes the place of the vertex buffer (stride 24 = D3D12_RAYTRACING_AABB); there is no index buffer,
+    // but closest-hit records still bind one, so a one-element placeholder keeps the record complete
+    std::vector<Vertex> boxes(aabbs.size() / 6);
+    std::memcpy(boxes.data(), aabbs.data(), aabbs.size() * sizeof(float));
+    SharedPtr m(new RtModel(context, std::move(boxes), {}));
+    m->mProcedural = true;
+    m->mOpaque = opaque;
+    m->mNumTriangles = m->mNumVertices;  // primitives
+    return m;
+}
+
 void RtModel::build(RtContext::SharedPtr context) {
     // blasGenerator.AddVertexBuffer(VB, 0, nVerts, sizeof(Vertex), IB, 0, nTris*3, R32_UINT, nullptr, 0), opaque, no update
     rt_geometry_desc g{};
     g.vertex_buffer = mVertexBuffer->ptr();
     g.vertex_count = mNumVertices;
     g.vertex_stride_bytes = sizeof(Vertex);
-    g.index_buffer = mIndexBuffer->ptr();
-    g.index_count = mNumTriangles * 3;
-    g.index_format = 32;
+    if (mProcedural) {
+        g.type = RT_GEOMETRY_TYPE_PROCEDURAL_AABBS;
+    } else {
+        g.index_buffer = mIndexBuffer->ptr();
+        g.index_count = mNumTriangles * 3;
+        g.index_format = 32;
+    }
     g.transform3x4 = nullptr;
-    g.flags = RT_GEOMETRY_FLAG_OPAQUE;
+    g.flags = mOpaque ? RT_GEOMETRY_FLAG_OPAQUE : RT_GEOMETRY_FLAG_NONE;
     rt_prebuild_info info{};
     ThrowIfFailed(rt_blas_prebuild(context->getNative(), &g, 1, RT_BUILD_FLAG_NONE, &info), "rt_blas_prebuild");
     auto scratch = context->createBuffer(info.scratch_bytes);
@@ -215,8 +294,33 @@ const uint8_t kProgressiveRaytracingLibrary[] = "rt_core:ProgressiveRaytracing";
 const UINT kProgressiveRaytracingLibrarySize = sizeof(kProgressiveRaytracingLibrary);
 const uint8_t kRealtimeRaytracingLibrary[] = "rt_core:RealtimeRaytracing";
 const UINT kRealtimeRaytracingLibrarySize = sizeof(kRealtimeRaytracingLibrary);
+const uint8_t kHitGroupProgramsLibrary[] = "rt_core:HitGroupPrograms";
+const UINT kHitGroupProgramsLibrarySize = sizeof(kHitGroupProgramsLibrary);
 
 static const char *kLibraryExports[] = {"RayGen", "PrimaryClosestHit", "PrimaryMiss", "ShadowClosestHit", "ShadowAnyHit", "ShadowMiss"};
+// exports of kHitGroupProgramsLibrary and the program ids they stand for (include/rt_types.h)
+static const struct {
+    const char *name;
+    RtShader::Type type;
+    uint32_t id;
+} kHitGroupExports[] = {{"AnyHitAccept", RtShader::Type::AnyHit, RT_ANYHIT_ACCEPT},          {"AnyHitIgnore", RtShader::Type::AnyHit, RT_ANYHIT_IGNORE},
+                        {"AnyHitEndSearch", RtShader::Type::AnyHit, RT_ANYHIT_END_SEARCH},   {"AnyHitCutout", RtShader::Type::AnyHit, RT_ANYHIT_CUTOUT},
+                        {"IntersectBox", RtShader::Type::Intersection, RT_INTERSECTION_BOX}, {"IntersectSphere", RtShader::Type::Intersection, RT_INTERSECTION_SPHERE},
+                        {"ProceduralClosestHit", RtShader::Type::ClosestHit, 0}};
+
+static uint32_t anyHitId(const std::string &name) {
+    if (name.empty()) return RT_ANYHIT_NONE;
+    if (name == "ShadowAnyHit") return RT_ANYHIT_ACCEPT;  // the application's no-op any-hit shader (ProgressiveRaytracing.hlsl:172-176)
+    for (const auto &e : kHitGroupExports)
+        if (e.type == RtShader::Type::AnyHit && name == e.name) return e.id;
+    throw std::logic_error("'" + name + "' is not an any-hit shader");
+}
+static uint32_t intersectionId(const std::string &name) {
+    if (name.empty()) return RT_INTERSECTION_NONE;
+    for (const auto &e : kHitGroupExports)
+        if (e.type == RtShader::Type::Intersection && name == e.name) return e.id;
+    throw std::logic_error("'" + name + "' is not an intersection shader");
+}
 
 UINT RootSignatureGenerator::argumentBytes() const {
     UINT off = 0;
@@ -237,14 +341,20 @@ static std::string narrow(const std::wstring &w) { return std::string(w.begin(),
 RtProgram::Desc &RtProgram::Desc::addShaderLibrary(const uint8_t *bytecode, UINT bytecodeSize, const std::vector<std::wstring> &symbolExports) {
     ThrowIfFalse(bytecode != nullptr, "addShaderLibrary: null library");
     const std::string token(reinterpret_cast<const char *>(bytecode), strnlen(reinterpret_cast<const char *>(bytecode), bytecodeSize));
+    bool hitGroupLibrary = false;
     if (token == reinterpret_cast<const char *>(kProgressiveRaytracingLibrary)) mLibrary = RT_PROGRAM_PROGRESSIVE;
     else if (token == reinterpret_cast<const char *>(kRealtimeRaytracingLibrary)) mLibrary = RT_PROGRAM_REALTIME;
+    else if (token == reinterpret_cast<const char *>(kHitGroupProgramsLibrary)) hitGroupLibrary = true;
     else throw std::logic_error("addShaderLibrary: unknown shader library (shaders are compiled into librt_core.so; pass "
-                                "kProgressiveRaytracingLibrary or kRealtimeRaytracingLibrary)");
+                                "kProgressiveRaytracingLibrary, kRealtimeRaytracingLibrary or kHitGroupProgramsLibrary)");
     for (const auto &w : symbolExports) {
         std::string e = narrow(w);
         bool known = false;
-        for (const char *k : kLibraryExports) known |= (e == k);
+        if (hitGroupLibrary) {
+            for (const auto &k : kHitGroupExports) known |= (e == k.name);
+        } else {
+            for (const char *k : kLibraryExports) known |= (e == k);
+        }
         if (!known) throw std::logic_error("addShaderLibrary: the library does not export '" + e + "'");
         mExports.push_back(e);
     }
@@ -271,7 +381,9 @@ RtProgram::Desc &RtProgram::Desc::addMiss(uint32_t missIndex, const std::string 
 RtProgram::Desc &RtProgram::Desc::addHitGroup(uint32_t hitIndex, const std::string &closestHit, const std::string &anyHit, const std::string &intersection) {
     requireExport(mExports, closestHit);
     requireExport(mExports, anyHit);
-    ThrowIfFalse(intersection.empty(), "intersection shaders (procedural geometry) are not part of these libraries");
+    requireExport(mExports, intersection);
+    (void)anyHitId(anyHit), (void)intersectionId(intersection);  // the names must be shaders of the right kind
+    ThrowIfFalse(hitIndex < 8, "addHitGroup: at most 8 hit groups");
     if (hitIndex >= mHit.size()) mHit.resize(hitIndex + 1);
     mHit[hitIndex] = {intersection, anyHit, closestHit};
     return *this;
@@ -286,7 +398,10 @@ RtProgram::SharedPtr RtProgram::create(RtContext::SharedPtr context, const Desc 
 RtProgram::RtProgram(RtContext::SharedPtr context, const Desc &desc) : mDesc(desc), mContext(context) {
     ThrowIfFalse(desc.mLibrary >= 0, "RtProgram: no shader library");
     ThrowIfFalse(desc.mRayGen == "RayGen", "RtProgram: the ray generation shader must be 'RayGen'");
-    ThrowIfFalse(desc.mHit.size() == 2 && desc.mMiss.size() == 2, "RtProgram: the libraries define 2 hit groups and 2 miss shaders");
+    // ray types 0 and 1 are the pipelines' own (primary, shadow); further hit groups (procedural geometry, other any-hit
+    // behaviour) are reached through RtContext::traceRays
+    ThrowIfFalse(desc.mHit.size() >= 2 && desc.mHit.size() <= 8 && desc.mMiss.size() == 2,
+                 "RtProgram: the pipeline libraries define hit groups 0 (primary) and 1 (shadow) and 2 miss shaders");
     ThrowIfFalse(desc.mHit[0].closestHit == "PrimaryClosestHit" && desc.mMiss[0] == "PrimaryMiss" && desc.mHit[1].closestHit == "ShadowClosestHit" &&
                      desc.mMiss[1] == "ShadowMiss",
                  "RtProgram: ray type 0 must be the primary hit group/miss, ray type 1 the shadow one");
@@ -296,6 +411,7 @@ RtProgram::RtProgram(RtContext::SharedPtr context, const Desc &desc) : mDesc(des
         HitGroup g;
         g.mClosestHit = std::make_shared<RtShader>(RtShader::Type::ClosestHit, desc.mHit[i].closestHit);
         if (!desc.mHit[i].anyHit.empty()) g.mAnyHit = std::make_shared<RtShader>(RtShader::Type::AnyHit, desc.mHit[i].anyHit);
+        if (!desc.mHit[i].intersection.empty()) g.mIntersection = std::make_shared<RtShader>(RtShader::Type::Intersection, desc.mHit[i].intersection);
         g.mExportName = "HitGroup" + std::to_string(i);
         mHitPrograms.push_back(g);
     }
@@ -304,6 +420,14 @@ RtProgram::RtProgram(RtContext::SharedPtr context, const Desc &desc) : mDesc(des
 }
 
 RtProgram::~RtProgram() { rt_program_destroy(mProgram); }
+
+rt_hit_group_programs RtProgram::getHitGroupPrograms(uint32_t rayIndex) const {
+    const HitGroup &g = mHitPrograms.at(rayIndex);
+    rt_hit_group_programs p{};
+    p.any_hit = anyHitId(g.mAnyHit ? g.mAnyHit->getEntryPoint() : std::string());
+    p.intersection = intersectionId(g.mIntersection ? g.mIntersection->getEntryPoint() : std::string());
+    return p;
+}
 
 // ============================================================================================ RtParams / RtBindings
 void RtParams::write(const void *src, UINT size, UINT alignment) {

@@ -10,6 +10,8 @@ namespace DXRFramework {
 
 class RtBindings;
 class RtState;
+class RtProgram;
+class RtScene;
 
 // A device allocation (the ComPtr<ID3D12Resource> of the reference); freed with the last reference.
 class RtBuffer {
@@ -48,6 +50,26 @@ public:
     void raytrace(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height,
                   uint32_t depth);
 
+    // Strip-interleaved dispatch: the rows of every `groups`-th strip of `stripRows` image rows, starting with strip
+    // `group` (screen-tile sharding of one frame across GPUs; rt_dispatch_rays_interleaved).
+    void raytraceStrips(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height,
+                        uint32_t stripRows, uint32_t groups, uint32_t group);
+
+    // TraceRay() with the program's hit groups honoured in full — any-hit and intersection shaders, procedural
+    // primitives, every ray flag (FL/TraverseFunction.hlsli:520-799) — for `n` caller-supplied rays (host arrays).
+    // Record of a candidate = rayContribution + geometryIndex * geometryMultiplier + InstanceContributionToHitGroupIndex
+    // (= instance * hitGroupCount, RtScene.cpp:29); its hit group = record % hitGroupCount.
+    void traceRays(std::shared_ptr<RtProgram> program, std::shared_ptr<RtScene> scene, const rt_ray *rays, uint64_t n, uint32_t rayFlags,
+                   uint32_t instanceMask, uint32_t rayContribution, uint32_t geometryMultiplier, rt_hit *hits);
+
+    // Multi-GPU accumulation (one process per GPU): joins the NCCL communicator of `worldSize` ranks.  `idFile` is the
+    // side channel for rank 0's unique id (rank 0 writes it, the others wait for it).  reduceAccumulation sums
+    // weight_r * buffer_r over the ranks onto `root` (rt_accum_reduce); `recv` may be null on the other ranks.
+    void joinCommunicator(int worldSize, int rank, const std::string &idFile);
+    void reduceAccumulation(const RtBuffer::SharedPtr &send, const RtBuffer::SharedPtr &recv, uint64_t floats, float weight, int root = 0);
+    int worldSize() const { return mWorld; }
+    int rank() const { return mRank; }
+
     // CreateBuffer / AllocateUploadBuffer (Helpers/DirectXRaytracingHelper.h)
     RtBuffer::SharedPtr createBuffer(uint64_t bytes);
     RtBuffer::SharedPtr createBuffer(const void *initialData, uint64_t bytes);
@@ -64,6 +86,8 @@ public:
 private:
     explicit RtContext(int deviceOrdinal);
     rt_context *mCtx = nullptr;
+    rt_comm *mComm = nullptr;
+    int mWorld = 1, mRank = 0;
 };
 
 }  // namespace DXRFramework

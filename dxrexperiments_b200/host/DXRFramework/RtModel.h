@@ -25,7 +25,11 @@ public:
     static SharedPtr create(RtContext::SharedPtr context, const std::string &filePath);
     // Procedural meshes (all BASELINE configs are synthetic).
     static SharedPtr create(RtContext::SharedPtr context, const std::vector<Vertex> &vertices, const std::vector<uint32_t> &indices);
+    // Procedural-primitive model (D3D12_RAYTRACING_GEOMETRY_TYPE_PROCEDURAL_PRIMITIVE_AABBS, FL/LoadProceduralGeometry.hlsl):
+    // 6 floats {min xyz, max xyz} per primitive; hit through an intersection shader of the hit group (RtContext::traceRays).
+    static SharedPtr createProcedural(RtContext::SharedPtr context, const std::vector<float> &aabbs, bool opaque = true);
     ~RtModel();
+    bool isProcedural() const { return mProcedural; }
 
     RtBuffer::SharedPtr getVertexBuffer() const { return mVertexBuffer; }
     RtBuffer::SharedPtr getIndexBuffer() const { return mIndexBuffer; }
@@ -37,6 +41,10 @@ public:
 
     // Parses an OBJ file into the interleaved layout; returns false if the file cannot be read.
     static bool loadObj(const std::string &path, std::vector<Vertex> &vertices, std::vector<uint32_t> &indices);
+    // The reference's loader (RtModel.cpp:26-58): Assimp import with Triangulate | GenSmoothNormals | FlipUVs |
+    // JoinIdenticalVertices | PreTransformVertices, all meshes merged with a per-mesh vertex offset.  Defined in
+    // RtModelAssimp.cpp, compiled when RT_HAVE_ASSIMP is set (make ASSIMP_INCLUDE=... ASSIMP_LIB=...).
+    static bool loadWithAssimp(const std::string &path, std::vector<Vertex> &vertices, std::vector<uint32_t> &indices);
 
 private:
     friend class RtScene;
@@ -44,6 +52,7 @@ private:
     void build(RtContext::SharedPtr context);  // RtModel.cpp:86-118
 
     bool mHasIndexBuffer = false;
+    bool mProcedural = false, mOpaque = true;
     UINT mNumVertices = 0;
     UINT mNumTriangles = 0;
     RtBuffer::SharedPtr mVertexBuffer, mIndexBuffer, mBlasBuffer;

@@ -16,6 +16,12 @@ extern const uint8_t kProgressiveRaytracingLibrary[];  // "rt_core:ProgressiveRa
 extern const UINT kProgressiveRaytracingLibrarySize;
 extern const uint8_t kRealtimeRaytracingLibrary[];      // "rt_core:RealtimeRaytracing"
 extern const UINT kRealtimeRaytracingLibrarySize;
+// The compiled-in any-hit and intersection programs of rt_trace_rays_hit_groups (include/rt_types.h RT_ANYHIT_*,
+// RT_INTERSECTION_*), exported as AnyHitAccept, AnyHitIgnore, AnyHitEndSearch, AnyHitCutout, IntersectBox,
+// IntersectSphere and the closest-hit stand-in ProceduralClosestHit.  Added NEXT TO a pipeline library, it lets
+// addHitGroup(idx, closestHit, anyHit, intersection) (libs/DXRFramework/RtProgram.h:51) name them.
+extern const uint8_t kHitGroupProgramsLibrary[];        // "rt_core:HitGroupPrograms"
+extern const UINT kHitGroupProgramsLibrarySize;
 
 enum class RootParameterType { SRV, UAV, CBV, Constants32Bit, DescriptorTable };
 
@@ -96,6 +102,10 @@ public:
     HitGroup getHitProgram(uint32_t rayIndex) const { return mHitPrograms.at(rayIndex); }
     uint32_t getMissProgramCount() const { return (uint32_t)mMissPrograms.size(); }
     RtShader::SharedPtr getMissProgram(uint32_t rayIndex) const { return mMissPrograms.at(rayIndex); }
+
+    // The any-hit / intersection program ids of hit group `rayIndex` (RT_ANYHIT_* / RT_INTERSECTION_*): what
+    // GetAnyHitAndIntersectionStateId resolves from the hit-group record in the reference (FL/TraverseFunction.hlsli:651-660).
+    rt_hit_group_programs getHitGroupPrograms(uint32_t rayIndex) const;
 
     rt_program *getNative() const { return mProgram; }
     rt_program_kind getKind() const { return mKind; }

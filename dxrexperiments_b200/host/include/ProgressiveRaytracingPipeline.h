@@ -22,6 +22,13 @@ public:
     void setJitterSeed(uint32_t seed) override { mRng = std::mt19937(seed); }
     const PerFrameConstants &getFrameConstants() const override { return mConstantBuffer; }
 
+    // Multi-GPU sharding of a frame (the reference is single-GPU).  setStripShard: render() covers only
+    // every `groups`-th strip of `stripRows` image rows, starting with strip `group` (RtContext::raytraceStrips).
+    // skipFrame: consume the jitter of a sample another rank renders, so that every rank draws the SAME jitter for
+    // sample s as a single GPU would (update() takes its jitter from a sequential generator, :191-193).
+    void setStripShard(UINT stripRows, UINT groups, UINT group) { mStripRows = stripRows, mStripGroups = groups, mStripGroup = group; }
+    void skipFrame() { (void)mRngDist(mRng), (void)mRngDist(mRng); }
+
     // Environment: a procedural sky by default; loadEnvironmentDDS replaces it with an R16G16B16A16F / R32G32B32A32F
     // cube map file such as the reference's assets/textures/CathedralRadiance.dds.
     bool loadEnvironmentDDS(const std::string &path);
@@ -49,6 +56,7 @@ protected:
     PerFrameConstants mConstantBuffer{};
     DXRFramework::RtTexture::SharedPtr mEnvCube;
     bool mActive = true;
+    UINT mStripRows = 32, mStripGroups = 1, mStripGroup = 0;
     std::mt19937 mRng;
     std::uniform_real_distribution<float> mRngDist;
 };

@@ -157,7 +157,8 @@ void RaytracingPipelineBase::render(UINT /*frameIndex*/, UINT width, UINT height
         ThrowIfFailed(rt_set_output(ctx, i, static_cast<float *>(mOutputResource.at(i)->ptr()), uint64_t(width) * 16), "rt_set_output");
     ThrowIfFailed(rt_set_tlas(ctx, mRtScene->getTlasWrappedPtr()), "rt_set_tlas");
 
-    mRtContext->raytrace(mRtBindings, mRtState, width, height, 3);
+    if (mStripGroups > 1) mRtContext->raytraceStrips(mRtBindings, mRtState, width, height, mStripRows, mStripGroups, mStripGroup);
+    else mRtContext->raytrace(mRtBindings, mRtState, width, height, 3);
     for (auto &o : mOutputResource) mRtContext->insertUAVBarrier(o);
 }
 

@@ -4,6 +4,9 @@
 //
 //   dxr_headless --model scene.obj --pipeline progressive --spp 16 --width 1920 --height 1080 --out frame.pfm
 //   dxr_headless --scene cornell --pipeline realtime --out direct.pfm --out2 spec.pfm --denoise composite.pfm
+//   dxr_headless ... --exr frame.exr [--exr-half]        OpenEXR output (fp32, or HALF = the reference's R16G16B16A16_FLOAT)
+// Multi-GPU (one process per GPU, replicated scene; the frame's samples and strips are sharded, one NCCL reduce at the end):
+//   for r in 0 1; do dxr_headless ... --spp 64 --world 2 --rank $r --comm-file /tmp/id [--strip-groups 2] --out frame.pfm & done
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -66,7 +69,8 @@ struct Args {
 static int usage() {
     std::puts("dxr_headless [--model file.obj | --scene cornell|triangle] [--pipeline progressive|realtime] [--width W] [--height H]\n"
               "             [--spp N] [--seed S] [--no-jitter] [--eye x y z] [--at x y z] [--light-pos x y z] [--env-dds file | --env-raw file size]\n"
-              "             [--out file.pfm] [--out2 file.pfm] [--denoise file.pfm] [--dump-frames file.bin] [--device N]");
+              "             [--out file.pfm] [--out2 file.pfm] [--denoise file.pfm] [--exr file.exr [--exr-half]] [--dump-frames file.bin] [--device N]\n"
+              "             [--world N --rank R --comm-file path [--strip-groups G] [--strip-rows 32]]   (one process per GPU)");
     return 0;
 }
 
@@ -83,8 +87,22 @@ int main(int argc, char **argv) {
     if (a.has("help")) return usage();
     const UINT width = UINT(a.num("width", 1920)), height = UINT(a.num("height", 1080)), spp = UINT(a.num("spp", 1));
     const std::string pipelineName = a.str("pipeline", "progressive");
+    const int world = int(a.num("world", 1)), rank = int(a.num("rank", 0));
     try {
-        auto context = RtContext::create(int(a.num("device", 0)));
+        if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("--world / --rank");
+        auto context = RtContext::create(int(a.num("device", rank)));
+        // shard plan (dxrexperiments_b200/sharding.py): rank = sampleGroup * stripGroups + stripGroup
+        UINT stripGroups = UINT(a.num("strip-groups", 0));
+        if (stripGroups == 0) {  // samples first, strips when the samples run out
+            stripGroups = 1;
+            while (UINT(world) / stripGroups > std::max<UINT>(spp, 1) || UINT(world) % stripGroups) ++stripGroups;
+        }
+        if (UINT(world) % stripGroups) throw std::runtime_error("--world must be a multiple of --strip-groups");
+        const UINT sampleGroups = UINT(world) / stripGroups, sampleGroup = UINT(rank) / stripGroups, stripGroup = UINT(rank) % stripGroups;
+        if (world > 1) {
+            if (!a.has("comm-file")) throw std::runtime_error("--world > 1 needs --comm-file (the side channel for the NCCL unique id)");
+            context->joinCommunicator(world, rank, a.str("comm-file", ""));
+        }
 
         // ---- scene (DXRExperimentsApp::InitRaytracing, src/DXRExperimentsApp.cpp:78-138)
         auto scene = RtScene::create();
@@ -138,6 +156,7 @@ int main(int argc, char **argv) {
         }
         pipeline->loadResources(3);
         pipeline->createOutputResource(DXGI_FORMAT_R16G16B16A16_FLOAT, width, height);
+        if (stripGroups > 1) pipeline->setStripShard(UINT(a.num("strip-rows", 32)), stripGroups, stripGroup);
 
         auto t0 = std::chrono::steady_clock::now();
         pipeline->buildAccelerationStructures();
@@ -147,7 +166,13 @@ int main(int argc, char **argv) {
         // ---- frames (OnUpdate / OnRender)
         std::ofstream frames;
         if (a.has("dump-frames")) frames.open(a.str("dump-frames", ""), std::ios::binary);
+        UINT mySamples = 0;
         for (UINT f = 0; f < spp; ++f) {
+            if (f % sampleGroups != sampleGroup) {  // another sample group's frame: keep the jitter sequence in step
+                pipeline->skipFrame();
+                continue;
+            }
+            ++mySamples;
             pipeline->update(0.0f, f, (f + 2) % 3, f % 3, width, height);
             if (a.has("no-jitter")) {
                 auto &fc = const_cast<PerFrameConstants &>(pipeline->getFrameConstants());
@@ -156,23 +181,38 @@ int main(int argc, char **argv) {
             if (frames) frames.write(reinterpret_cast<const char *>(&pipeline->getFrameConstants()), sizeof(PerFrameConstants));
             pipeline->render(f % 3, width, height);
         }
+        // ---- the path's one collective: every output is summed onto rank 0, weighted by the rank's share of the samples
+        std::vector<RtBuffer::SharedPtr> finalOut;
+        for (int i = 0; i < pipeline->getNumOutputs(); ++i) finalOut.push_back(pipeline->getOutputResource(i));
+        if (world > 1) {
+            const uint64_t floats = uint64_t(width) * height * 4;
+            for (size_t i = 0; i < finalOut.size(); ++i) {
+                RtBuffer::SharedPtr recv = rank == 0 ? context->createBuffer(floats * 4) : nullptr;
+                context->reduceAccumulation(finalOut[i], recv, floats, float(mySamples) / float(spp), 0);
+                if (rank == 0) finalOut[i] = recv;
+            }
+        }
         context->waitForGpu();
         context->checkDeviceStatus();
         auto t2 = std::chrono::steady_clock::now();
 
         std::vector<float> img(size_t(width) * height * 4);
         auto save = [&](RtBuffer::SharedPtr buf, const std::string &path) {
+            if (rank != 0) return;  // only the root holds the frame
             buf->download(img.data(), img.size() * sizeof(float));
-            if (!ImageIO::writePFM(path, img.data(), width, height)) throw std::runtime_error("cannot write " + path);
+            const bool exr = path.size() > 4 && path.substr(path.size() - 4) == ".exr";
+            const bool ok = exr ? ImageIO::writeEXR(path, img.data(), width, height, a.has("exr-half")) : ImageIO::writePFM(path, img.data(), width, height);
+            if (!ok) throw std::runtime_error("cannot write " + path);
         };
-        if (a.has("out")) save(pipeline->getOutputResource(0), a.str("out", ""));
-        if (a.has("out2") && pipeline->getNumOutputs() > 1) save(pipeline->getOutputResource(1), a.str("out2", ""));
-        if (a.has("denoise")) {
+        if (a.has("out")) save(finalOut[0], a.str("out", ""));
+        if (a.has("exr")) save(finalOut[0], a.str("exr", ""));
+        if (a.has("out2") && finalOut.size() > 1) save(finalOut[1], a.str("out2", ""));
+        if (a.has("denoise") && rank == 0) {
             if (pipeline->getNumOutputs() < 2) throw std::runtime_error("--denoise needs --pipeline realtime");
             auto denoiser = DenoiseCompositor::create(context);
             denoiser->loadResources(3, false);
             denoiser->createOutputResource(DXGI_FORMAT_R16G16B16A16_FLOAT, width, height);
-            denoiser->dispatch({pipeline->getOutputSrvHandle(0), pipeline->getOutputSrvHandle(1)}, 0, width, height);
+            denoiser->dispatch({finalOut[0]->gpuHandle(), finalOut[1]->gpuHandle()}, 0, width, height);
             context->waitForGpu();
             save(denoiser->getOutputResource(), a.str("denoise", ""));
         }
@@ -181,9 +221,10 @@ int main(int argc, char **argv) {
         const double buildMs = std::chrono::duration<double, std::milli>(t1 - t0).count(), renderMs = std::chrono::duration<double, std::milli>(t2 - t1).count();
         const double rays = double(rc.primary + rc.secondary + rc.shadow);
         std::printf("{\"pipeline\": \"%s\", \"triangles\": %u, \"width\": %u, \"height\": %u, \"frames\": %u, \"build_ms\": %.3f, \"render_ms\": %.3f, "
-                    "\"rays\": %.0f, \"mrays_per_s\": %.1f, \"kernel_launches\": %llu, \"core\": \"%s\"}\n",
+                    "\"rays\": %.0f, \"mrays_per_s\": %.1f, \"kernel_launches\": %llu, \"world\": %d, \"rank\": %d, \"strip_groups\": %u, "
+                    "\"samples_on_rank\": %u, \"core\": \"%s\"}\n",
                     pipeline->getName(), model->getNumTriangles(), width, height, spp, buildMs, renderMs, rays, rays / (renderMs * 1e3),
-                    (unsigned long long)context->launchCount(), rt_version());
+                    (unsigned long long)context->launchCount(), world, rank, stripGroups, mySamples, rt_version());
     } catch (const std::exception &e) {
         std::fprintf(stderr, "dxr_headless: %s\n", e.what());
         return 1;

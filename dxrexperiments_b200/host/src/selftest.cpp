@@ -5,6 +5,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <string>
+#include <vector>
 
 #include "../DXRFramework/RtBindings.h"
 #include "../include/Camera.h"
@@ -142,9 +145,71 @@ static int testProgramDesc() {
     return 0;
 }
 
+static int testExr(const std::string &dir) {
+    const uint32_t w = 7, h = 4;
+    std::vector<float> img(w * h * 4);
+    for (size_t i = 0; i < img.size(); ++i) img[i] = float(i) * 0.37f - 5.0f;
+    img[5] = 1e-8f, img[9] = 65520.0f, img[13] = 3.14159274f;
+    CHECK(ImageIO::writeEXR(dir + "/t.exr", img.data(), w, h, false));
+    std::vector<float> back;
+    uint32_t bw = 0, bh = 0;
+    CHECK(ImageIO::readEXR(dir + "/t.exr", back, bw, bh));
+    CHECK(bw == w && bh == h && back.size() == img.size());
+    CHECK(std::memcmp(back.data(), img.data(), img.size() * 4) == 0);  // fp32 files keep the accumulation buffer exactly
+    // file anatomy: magic, version 2, attribute block ends before the offset table of h entries, then h chunks of 8 + w*16 bytes
+    std::ifstream f(dir + "/t.exr", std::ios::binary);
+    std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    uint32_t magic;
+    std::memcpy(&magic, raw.data(), 4);
+    CHECK(magic == 20000630u && raw[4] == 2 && std::string(raw.data() + 8) == "channels");
+    CHECK(ImageIO::writeEXR(dir + "/h.exr", img.data(), w, h, true));
+    CHECK(ImageIO::readEXR(dir + "/h.exr", back, bw, bh));
+    for (size_t i = 0; i < img.size(); ++i) CHECK(back[i] == ImageIO::halfToFloat(ImageIO::floatToHalf(img[i])));
+    // round-to-nearest-even half conversion: exact values, ties, overflow, subnormals
+    CHECK(ImageIO::floatToHalf(1.0f) == 0x3C00 && ImageIO::floatToHalf(-2.0f) == 0xC000 && ImageIO::floatToHalf(65504.0f) == 0x7BFF);
+    CHECK(ImageIO::floatToHalf(65520.0f) == 0x7C00 && ImageIO::floatToHalf(1e-8f) == 0x0000 && ImageIO::floatToHalf(5.9604644775390625e-08f) == 0x0001);
+    CHECK(ImageIO::floatToHalf(1.0f + 1.0f / 2048.0f) == 0x3C00 && ImageIO::floatToHalf(1.0f + 3.0f / 2048.0f) == 0x3C02);  // ties to even
+    for (uint32_t hbits = 0; hbits < 0x7C00; hbits += 7) CHECK(ImageIO::floatToHalf(ImageIO::halfToFloat(uint16_t(hbits))) == hbits);
+    CHECK(!ImageIO::readEXR(dir + "/t.pfm", back, bw, bh));
+    return 0;
+}
+
+static int testHitGroupDesc() {
+    // RtProgram::Desc::addHitGroup(idx, closestHit, anyHit, intersection) with the compiled-in hit-group programs
+    RtProgram::Desc d;
+    d.addShaderLibrary(kProgressiveRaytracingLibrary, kProgressiveRaytracingLibrarySize,
+                       {L"RayGen", L"PrimaryClosestHit", L"PrimaryMiss", L"ShadowClosestHit", L"ShadowAnyHit", L"ShadowMiss"});
+    d.addShaderLibrary(kHitGroupProgramsLibrary, kHitGroupProgramsLibrarySize, {L"AnyHitIgnore", L"AnyHitCutout", L"IntersectSphere", L"ProceduralClosestHit"});
+    d.setRayGen("RayGen").addMiss(0, "PrimaryMiss").addMiss(1, "ShadowMiss");
+    d.addHitGroup(0, "PrimaryClosestHit", "").addHitGroup(1, "ShadowClosestHit", "ShadowAnyHit");
+    d.addHitGroup(2, "ProceduralClosestHit", "AnyHitCutout", "IntersectSphere");
+    bool threw = false;
+    try {
+        d.addHitGroup(3, "ProceduralClosestHit", "", "IntersectBox");  // not among the exports listed above
+    } catch (const std::logic_error &) {
+        threw = true;
+    }
+    CHECK(threw);
+    threw = false;
+    try {
+        d.addHitGroup(3, "ProceduralClosestHit", "IntersectSphere", "");  // an intersection shader is not an any-hit shader
+    } catch (const std::logic_error &) {
+        threw = true;
+    }
+    CHECK(threw);
+    threw = false;
+    try {
+        RtProgram::Desc().addShaderLibrary(kHitGroupProgramsLibrary, kHitGroupProgramsLibrarySize, {L"RayGen"});
+    } catch (const std::logic_error &) {
+        threw = true;
+    }
+    CHECK(threw);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     const std::string dir = argc > 1 ? argv[1] : "/tmp";
-    if (testObj(dir) || testPfmAndHalf(dir) || testDds(dir) || testBindingsLayout() || testProgramDesc()) return 1;
+    if (testObj(dir) || testPfmAndHalf(dir) || testDds(dir) || testBindingsLayout() || testProgramDesc() || testExr(dir) || testHitGroupDesc()) return 1;
     std::puts("host selftest OK");
     return 0;
 }
