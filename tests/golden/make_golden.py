@@ -98,6 +98,17 @@ def main():
                         progressive4=acc, direct=direct, spec=spec, denoised=den)
     np.savez_compressed(os.path.join(HERE, "rng.npz"), seeds=seeds, rands=rands)
     np.savez_compressed(os.path.join(HERE, "hitgroups_mixed.npz"), **hit_group_vectors(oracle))
+    # a 192 x 128 crop of the reference's own mock denoiser inputs (src/DenoiseCompositor.cpp:52-60 loads
+    # assets/textures/{DirectLighting,IndirectSpecular}.PNG, 1922 x 1126, 8-bit) around the busiest region: a fixture that
+    # travels to the GPU box, where /root/reference does not exist.  tests/test_independent_answers.py checks the crop
+    # against the full files whenever they are present.
+    tex = "/root/reference/assets/textures"
+    if os.path.exists(os.path.join(tex, "DirectLighting.PNG")):
+        from PIL import Image
+        y0, x0, hh, ww = 128, 832, 128, 192
+        d = np.asarray(Image.open(os.path.join(tex, "DirectLighting.PNG")).convert("RGBA"))[y0:y0 + hh, x0:x0 + ww]
+        sp = np.asarray(Image.open(os.path.join(tex, "IndirectSpecular.PNG")).convert("RGBA"))[y0:y0 + hh, x0:x0 + ww]
+        np.savez_compressed(os.path.join(HERE, "denoise_mock_crop.npz"), direct_u8=d, spec_u8=sp, origin=np.array([y0, x0]))
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
