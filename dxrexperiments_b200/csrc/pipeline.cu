@@ -206,19 +206,42 @@ __device__ __forceinline__ void write_pixel(const Launch &L, float *out, uint64_
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-__global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
-                                                          uint32_t n_recs, const float *env, uint32_t envSize, float *out0,
-                                                          uint64_t pitch0, float *out1, uint64_t pitch1,
-                                                          unsigned long long *rayCounts, uint32_t *status) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t P = L.rw * L.rh;
-    const bool inRange = p < P;
+// Coherence binning (north star: "rays compacted and sorted ... between bounces"): a block shades one 16x16 pixel tile
+// and hands out the tile's hit slots bin by bin, the bin being {hit-group record (material / instance), direction octant of
+// the indirect-diffuse ray}.  The hits of a tile lie close together in space, so after the binning 32 consecutive slots —
+// one warp of the queue kernels, for every ray kind of those slots — hold rays that start near each other, on the same
+// material, and head into the same octant: they walk the same part of the tree.  The sort is a counting sort in shared
+// memory inside the shading kernel (one global atomic per block); no pass over the queues, no extra launch.
+// The reference has no counterpart: the Fallback Layer traces in fixed 8x8 pixel groups and never reorders rays
+// (FL/UberShaderRayTracingProgram.cpp:268-272).
+#ifndef RT_COHERENCE_BINS
+#define RT_COHERENCE_BINS 1  // 0: slots in pixel order within the tile (A/B measurements)
+#endif
+constexpr int kShadeTile = 16;                     // pixels per tile edge
+constexpr int kShadeThreads = kShadeTile * kShadeTile;
+constexpr int kBins = 32;                          // 4 record classes x 8 octants
+
+__device__ __forceinline__ uint32_t octant_of(f3 d) {
+    return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+}
+
+__global__ void __launch_bounds__(kShadeThreads) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+                                                                 uint32_t n_recs, const float *env, uint32_t envSize, float *out0,
+                                                                 uint64_t pitch0, float *out1, uint64_t pitch1,
+                                                                 unsigned long long *rayCounts, uint32_t *status) {
+    __shared__ uint32_t s_count[kBins], s_offset[kBins], s_base;
+    const uint32_t tilesX = (L.rw + kShadeTile - 1) / kShadeTile;
+    const uint32_t lx = (blockIdx.x % tilesX) * kShadeTile + (threadIdx.x % kShadeTile);
+    const uint32_t ly = (blockIdx.x / tilesX) * kShadeTile + (threadIdx.x / kShadeTile);
+    const uint32_t p = ly * L.rw + lx;
+    const bool inRange = lx < L.rw && ly < L.rh;
+    if (threadIdx.x < kBins) s_count[threadIdx.x] = 0;
     bool isHit = false;
     float4 hA = make_float4(0, 0, 0, 0);
     uint32_t x = 0, y = 0;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
     if (inRange) {
-        x = L.x0 + p % L.rw, y = image_row(L, p / L.rw);
+        x = L.x0 + lx, y = image_row(L, ly);
         primary_ray(L.f, L.width, L.height, x, y, L.jitterScale, o, d);
         hA = ws.hitA[p];
         isHit = __float_as_uint(hA.w) != RT_NO_HIT;
@@ -232,17 +255,21 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
             }
         }
     }
-    const uint32_t slot = warp_alloc(isHit, &ws.counters[0]);
-    uint32_t nShadow = 0, nSecondary = 0;
+    // ---- shade first (everything stays in registers), allocate the slot afterwards: the bin needs the sampled direction
+    uint32_t nShadow = 0, nSecondary = 0, rec = 0, flags = 0, bin = 0;
+    f3 pos = mk3(0, 0, 0);
+    float4 s0 = make_float4(0, 0, 0, 0), s1 = s0, s2 = s0;
+    float s3 = 0.0f;
+    float shTmax[4] = {-1.0f, -1.0f, -1.0f, -1.0f}, shTmin = RT_RAY_EPSILON, secTmax[2] = {-1.0f, -1.0f};
+    f3 shDir[4] = {mk3(0, 0, 1), mk3(0, 0, 1), mk3(0, 0, 1), mk3(0, 0, 1)}, secDir[2] = {mk3(0, 0, 1), mk3(0, 0, 1)};
     if (isHit) {
-        uint32_t rec = ws.hitRec[p];
+        rec = ws.hitRec[p];
         if (rec >= n_recs) rec = 0, atomicOr(status, 8u);  // a hit on an instance without a bound record: rt_get_status -> RT_ERR_INVALID_ARG
         const rt_hit_record_dev &R = recs[rec];
         const uint32_t prim = __float_as_uint(hA.w);
         const f3 N = normalize3(interpolate_normal(R, prim, hA.y, hA.z));
-        const f3 pos = o + hA.x * d;  // HitWorldPosition
+        pos = o + hA.x * d;  // HitWorldPosition
         const rt_debug_options &opt = L.f.options;
-        uint32_t flags = 0;
         if (!L.realtime && opt.showAmbientOcclusionOnly) {
             // evaluateAO: S/RaytracingCommon.hlsli:98-124 — 4 shadow rays, tMax 10
             flags = SLOT_AO;
@@ -250,21 +277,21 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
             float nol[4], pdf[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                f3 dir;
                 if (opt.cosineHemisphereSampling) {
-                    dir = cos_hemisphere(seed, N);
-                    nol[i] = saturatef(dot3(N, dir));
+                    shDir[i] = cos_hemisphere(seed, N);
+                    nol[i] = saturatef(dot3(N, shDir[i]));
                     pdf[i] = nol[i] / RT_M_PI;
                 } else {
-                    dir = uniform_hemisphere(seed, N);
-                    nol[i] = saturatef(dot3(N, dir));
+                    shDir[i] = uniform_hemisphere(seed, N);
+                    nol[i] = saturatef(dot3(N, shDir[i]));
                     pdf[i] = 1.0f / (2.0f * RT_M_PI);
                 }
-                store_ray(&ws.shadowQ0[size_t(i) * ws.plane + slot], pos, RT_RAY_EPSILON, dir, 10.0f);
+                shTmax[i] = 10.0f;
             }
             nShadow = 4;
-            ws.S0[slot] = make_float4(nol[0], nol[1], nol[2], nol[3]);
-            ws.S1[slot] = make_float4(pdf[0], pdf[1], pdf[2], pdf[3]);
+            s0 = make_float4(nol[0], nol[1], nol[2], nol[3]);
+            s1 = make_float4(pdf[0], pdf[1], pdf[2], pdf[3]);
+            bin = octant_of(shDir[0]);
         } else {
             uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
             LightEval le = eval_lights(L.f, pos, N);
@@ -273,42 +300,90 @@ __global__ void __launch_bounds__(kBlock) k_shade_primary(const __grid_constant_
                 if (next_rand(seed) < 0.5f) usePoint = false, flags |= SLOT_DEBUG2_DIR;
                 else useDir = false, flags |= SLOT_DEBUG2_POINT;
             }
-            store_ray(&ws.shadowQ0[slot], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
-            store_ray(&ws.shadowQ0[size_t(ws.plane) + slot], pos, RT_RAY_EPSILON, le.pointL, usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f);
-            for (uint32_t k = 2; k < L.shadowsPerHit; ++k) store_ray(&ws.shadowQ0[size_t(k) * ws.plane + slot], pos, 0.0f, le.dirL, -1.0f);
+            shDir[0] = le.dirL, shTmax[0] = useDir ? RT_RAY_MAX_T : -1.0f;
+            shDir[1] = le.pointL, shTmax[1] = usePoint ? le.pointDist - RT_RAY_EPSILON : -1.0f;
+            shDir[2] = shDir[3] = le.dirL;  // unused planes of the AO layout: inactive
             nShadow = (useDir ? 1 : 0) + (usePoint ? 1 : 0);
             // indirect diffuse: S/ProgressiveRaytracing.hlsl:57-78,107-110
             float uniformNoL = 0.0f;
-            bool hasDiffuse = !L.realtime && !opt.noIndirectDiffuse;
-            f3 dDir = mk3(0, 0, 1);
+            const bool hasDiffuse = !L.realtime && !opt.noIndirectDiffuse;
             if (hasDiffuse) {
-                if (opt.cosineHemisphereSampling) dDir = cos_hemisphere(seed, N);
+                if (opt.cosineHemisphereSampling) secDir[0] = cos_hemisphere(seed, N);
                 else {
-                    dDir = uniform_hemisphere(seed, N);
-                    uniformNoL = saturatef(dot3(N, dDir));
+                    secDir[0] = uniform_hemisphere(seed, N);
+                    uniformNoL = saturatef(dot3(N, secDir[0]));
                     flags |= SLOT_UNIFORM;
                 }
                 flags |= SLOT_HAS_DIFFUSE;
+                secTmax[0] = RT_RAY_MAX_T;
             }
-            store_ray(&ws.secQ[slot], pos, RT_RAY_EPSILON, dDir, hasDiffuse ? RT_RAY_MAX_T : -1.0f);
             // indirect specular: S/ProgressiveRaytracing.hlsl:114-131
-            f3 fres = mk3(0, 0, 0), sDir = mk3(0, 0, 1);
+            f3 fres = mk3(0, 0, 0);
             float pdf = 1.0f, brdf = 0.0f;
             const bool hasSpec = (R.mat.type == 1 || R.mat.type == 2) && R.mat.reflectivity > 0.001f;
             if (hasSpec) {
                 float exponent = expf((1.0f - R.mat.roughness) * 12.0f);
                 f3 mirror = reflect3(d, N);
-                sDir = phong_lobe(seed, mirror, exponent, pdf, brdf);
+                secDir[1] = phong_lobe(seed, mirror, exponent, pdf, brdf);
                 fres = fresnel_schlick(d, N, mk3(R.mat.specular[0], R.mat.specular[1], R.mat.specular[2]));
                 flags |= SLOT_HAS_SPEC;
+                secTmax[1] = RT_RAY_MAX_T;
             }
-            store_ray(&ws.secQ[size_t(ws.plane) + slot], pos, RT_RAY_EPSILON, sDir, hasSpec ? RT_RAY_MAX_T : -1.0f);
             nSecondary = (hasDiffuse ? 1 : 0) + (hasSpec ? 1 : 0);
-            ws.S0[slot] = make_float4(le.dirPre.x, le.dirPre.y, le.dirPre.z, le.falloff);
-            ws.S1[slot] = make_float4(le.pointPre.x, le.pointPre.y, le.pointPre.z, pdf);
-            ws.S2[slot] = make_float4(fres.x, fres.y, fres.z, brdf);
-            ws.S3[slot] = uniformNoL;
+            s0 = make_float4(le.dirPre.x, le.dirPre.y, le.dirPre.z, le.falloff);
+            s1 = make_float4(le.pointPre.x, le.pointPre.y, le.pointPre.z, pdf);
+            s2 = make_float4(fres.x, fres.y, fres.z, brdf);
+            s3 = uniformNoL;
+            bin = octant_of(hasDiffuse ? secDir[0] : secDir[1]);
         }
+        bin |= ((rec >> 1) & 3u) << 3;  // records come in pairs per instance (ray types): the instance / material class
+    }
+    // ---- slot allocation: counting sort of the tile's hits by bin
+    const int lane = threadIdx.x & 31;
+    uint32_t slot = 0xffffffffu;
+#if RT_COHERENCE_BINS
+    __syncthreads();  // s_count cleared
+    uint32_t inWarp = 0, warpBase = 0;
+    {
+        const unsigned hitMask = __ballot_sync(0xffffffffu, isHit);
+        if (isHit) {
+            const unsigned same = __match_any_sync(hitMask, bin);
+            inWarp = __popc(same & ((1u << lane) - 1u));
+            const int leader = __ffs(same) - 1;
+            if (lane == leader) warpBase = atomicAdd(&s_count[bin], uint32_t(__popc(same)));
+            warpBase = __shfl_sync(same, warpBase, leader);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of the 32 bin counts, one global allocation for the tile
+        const uint32_t c = s_count[lane];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += v;
+        }
+        s_offset[lane] = incl - c;
+        if (lane == 31 && incl) s_base = atomicAdd(&ws.counters[0], incl);
+    }
+    __syncthreads();
+    if (isHit) slot = s_base + s_offset[bin] + warpBase + inWarp;
+#else
+    slot = warp_alloc(isHit, &ws.counters[0]);
+#endif
+    if (isHit) {
+        const size_t pl = ws.plane;
+        for (uint32_t k = 0; k < L.shadowsPerHit; ++k)
+            store_ray(&ws.shadowQ0[size_t(k) * pl + slot], pos, (flags & SLOT_AO) || k < 2 ? shTmin : 0.0f, shDir[k], shTmax[k]);
+        // (in the AO debug view both secondary rays are inactive: tmax < 0)
+        store_ray(&ws.secQ[slot], pos, RT_RAY_EPSILON, secDir[0], secTmax[0]);
+        store_ray(&ws.secQ[pl + slot], pos, RT_RAY_EPSILON, secDir[1], secTmax[1]);
+        if (!(flags & SLOT_AO)) {
+            ws.S2[slot] = s2;
+            ws.S3[slot] = s3;
+        }
+        ws.S0[slot] = s0;
+        ws.S1[slot] = s1;
         ws.slotInfo[slot] = make_uint4(p, rec, flags, 0);
     }
     warp_count_add(&rayCounts[0], inRange ? 1u : 0u);
@@ -738,7 +813,6 @@ static int dispatch_impl(rt_context *ctx, rt_program *prog, uint32_t width, uint
 static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, const WS &ws, cudaStream_t st, cudaStream_t side,
                          cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     const bool timing = ctx->timing;
-    const uint64_t P = uint64_t(L.rw) * L.rh;
     RT_CUDA(cudaMemsetAsync(ws.counters, 0, 256, st));
     const uint32_t tiles = ((L.rw + 7) / 8) * ((L.rh + 3) / 4);
     const int qgrid = ctx->num_sms * 16;
@@ -748,7 +822,8 @@ static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, con
     if (stats) k_primary<true><<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status, sPrim);
     else k_primary<false><<<rt_div_up(tiles, kBlock / 32), kBlock, 0, st>>>(L, ctx->tlas, ws, ctx->status, sPrim);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[1], st));
-    k_shade_primary<<<rt_div_up(P, kBlock), kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
+    const uint32_t shadeTiles = ((L.rw + kShadeTile - 1) / kShadeTile) * ((L.rh + kShadeTile - 1) / kShadeTile);
+    k_shade_primary<<<shadeTiles, kShadeThreads, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size,
                                                              ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1], ctx->ray_counts, ctx->status);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[2], st));
     // The depth-0 shadow wave and the secondary-ray chain (trace -> shade -> depth-1 shadow wave) both depend only on

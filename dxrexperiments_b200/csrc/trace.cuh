@@ -203,9 +203,18 @@ __device__ __forceinline__ uint32_t ref_of(uint32_t key, uint32_t r0, uint32_t r
 #define RT_SHADOW_UNSORTED 1  // any-hit rays take the children in slot order: no sorting network (A/B: shadow rays 3.44 -> 4.55 Grays/s on C2;
                               // reverse slot order, area-ordered slots and "nearest first, rest unsorted" for closest hits all measured worse)
 #endif
-template <bool WITH_T, bool SORTED = true>
-__device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint32_t ref, const RayPre &cur, float tCur, uint32_t *stack,
-                                               uint32_t *stackT, int &sp, uint32_t *status) {
+// The traversal stack is a policy type S with  bool room(sp, n)  and  void push(sp, ref, key):
+//   LocalStack  — 64 entries (+ entry distances) in local memory: the one-thread-one-ray loops (k_primary)
+//   the persistent kernels' stack keeps its first entries in shared memory (trace_persistent.cuh).
+struct LocalStack {
+    uint32_t ref[RT_STACK_SIZE], key[RT_STACK_SIZE];
+    __device__ __forceinline__ bool room(int sp, int n) const { return sp + n <= RT_STACK_SIZE; }
+    __device__ __forceinline__ void push(int &sp, uint32_t r, uint32_t k) { ref[sp] = r, key[sp] = k, ++sp; }
+};
+
+template <bool WITH_T, bool SORTED = true, class S>
+__device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint32_t ref, const RayPre &cur, float tCur, S &stk, int &sp,
+                                               uint32_t *status) {
     const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
 #if RT_LDG256
     float4 c0, h0, c1, h1, c2, h2, c3, h3;
@@ -230,7 +239,7 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
         for (int k = 3; k >= 0; --k) {
             if (v[k]) {
                 if (first != RT_SENTINEL) {
-                    if (sp < RT_STACK_SIZE) stack[sp++] = first;
+                    if (stk.room(sp, 1)) stk.push(sp, first, 0u);
                     else atomicOr(status, 1u);
                 }
                 first = r[k];
@@ -246,22 +255,12 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
     key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
     if (k0 == 0xffffffffu) return RT_SENTINEL;
     if (k1 != 0xffffffffu) {  // push the other hits, farthest first
-        if (sp + 3 > RT_STACK_SIZE) {
+        if (!stk.room(sp, 3)) {
             atomicOr(status, 1u);
         } else {
-            if (k3 != 0xffffffffu) {
-                stack[sp] = ref_of(k3, r0, r1, r2, r3);
-                if (WITH_T) stackT[sp] = k3;
-                sp++;
-            }
-            if (k2 != 0xffffffffu) {
-                stack[sp] = ref_of(k2, r0, r1, r2, r3);
-                if (WITH_T) stackT[sp] = k2;
-                sp++;
-            }
-            stack[sp] = ref_of(k1, r0, r1, r2, r3);
-            if (WITH_T) stackT[sp] = k1;
-            sp++;
+            if (k3 != 0xffffffffu) stk.push(sp, ref_of(k3, r0, r1, r2, r3), k3);
+            if (k2 != 0xffffffffu) stk.push(sp, ref_of(k2, r0, r1, r2, r3), k2);
+            stk.push(sp, ref_of(k1, r0, r1, r2, r3), k1);
         }
     }
     return ref_of(k0, r0, r1, r2, r3);
@@ -278,7 +277,7 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
     hit.u = hit.v = 0.0f;
     hit.inst_index = hit.geom_index = hit.inst_id = hit.leaf_slot = hit.record = 0;
     if (A.count == 0) return false;
-    uint32_t stack[RT_STACK_SIZE], stackT[RT_STACK_SIZE];
+    LocalStack stk;
     int sp = 0, blasBase = -1;
     float tCur = tmax;
     RayPre cur;
@@ -349,7 +348,7 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
                 }
             }
         } else {
-            ref = wide4_step<true>(nodes, ref, cur, tCur, stack, stackT, sp, status);
+            ref = wide4_step<true>(nodes, ref, cur, tCur, stk, sp, status);
         }
         if (ref == RT_SENTINEL) {
             bool done = false;
@@ -365,8 +364,8 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
                     blasBase = -1;
                 }
                 --sp;
-                if ((stackT[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
-                ref = stack[sp];
+                if ((stk.key[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
+                ref = stk.ref[sp];
                 break;
             }
             if (done) break;

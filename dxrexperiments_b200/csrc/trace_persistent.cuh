@@ -11,7 +11,6 @@
 //   * an internal step reads ONE 128-byte rt_wide4_node (eight 16-byte loads) and tests four boxes, i.e. two BVH2
 //     levels per dependent memory round trip — the kernel was latency-bound on the chain of node fetches
 //     (profiles/r1_ncu_trace_persistent.md); hits are ordered near-to-far with a 5-exchange network on integer keys;
-//   * pushed nodes carry their entry distance and are dropped at pop time once a closer hit is committed;
 //   * the ray constants are only recomputed when the instance transform actually changes them.
 // MODE 0: closest hit, ray flags 0 (secondary rays of the pipelines)  -> compact hit records
 // MODE 1: any hit (shadow rays: ACCEPT_FIRST_HIT | SKIP_CLOSEST_HIT)   -> visibility bytes
@@ -45,16 +44,38 @@ struct TraceSink {  // where results go; only the members of the kernel's MODE a
 #ifndef RT_PERSIST_MIN_BLOCKS
 #define RT_PERSIST_MIN_BLOCKS 8
 #endif
-#ifndef RT_POP_CULL
-#define RT_POP_CULL 0  // 1: keep each pushed node's entry distance and drop it at pop time behind a committed hit.  With the
-                       // treelet-optimised tree the second stack costs more than the skipped visits save (A/B: -6 % on secondary rays)
-#endif
 #ifndef RT_PERSIST_WIDE4
 #define RT_PERSIST_WIDE4 1  // 1: traverse the 4-wide nodes (rt_wide4_node); 0: the BVH2 wide nodes (A/B measurements)
 #endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 0  // > 0: the first RT_SMEM_STACK entries of every lane's stack in shared memory ([entry][thread], conflict free),
+                         // deeper ones in local memory.  Measured (profiles/r2_trace_ab.md): 8 entries in shared memory cost 6-9 % on
+                         // C2 / C1M — the kernel is issue-bound and the extra select between the two homes costs more than the
+                         // cheaper access saves; local memory is L1-resident on-chip SRAM already, so the default keeps the stack there
+#endif
+constexpr int kPersistThreads = 128;
+
+// Stack policy of wide4_step (trace.cuh) for the persistent lanes.
+struct PersistStack {
+#if RT_SMEM_STACK > 0
+    uint32_t *sm;  // &s_stack[0][threadIdx.x]
+    uint32_t lm[RT_STACK_SIZE - RT_SMEM_STACK];
+    __device__ __forceinline__ void push(int &sp, uint32_t r, uint32_t) {
+        if (sp < RT_SMEM_STACK) sm[sp * kPersistThreads] = r;
+        else lm[sp - RT_SMEM_STACK] = r;
+        ++sp;
+    }
+    __device__ __forceinline__ uint32_t at(int sp) const { return sp < RT_SMEM_STACK ? sm[sp * kPersistThreads] : lm[sp - RT_SMEM_STACK]; }
+#else
+    uint32_t lm[RT_STACK_SIZE];
+    __device__ __forceinline__ void push(int &sp, uint32_t r, uint32_t) { lm[sp++] = r; }
+    __device__ __forceinline__ uint32_t at(int sp) const { return lm[sp]; }
+#endif
+    __device__ __forceinline__ bool room(int sp, int n) const { return sp + n <= RT_STACK_SIZE; }
+};
 
 template <int MODE>
-__global__ void __launch_bounds__(128, RT_PERSIST_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPersistThreads, RT_PERSIST_MIN_BLOCKS)
 k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, uint32_t mult, uint32_t plane, TraceSink sink,
                    uint32_t *status, uint32_t *nextRay, uint32_t userFlags, uint32_t userMask) {
     constexpr bool GENERAL = MODE == 2;
@@ -72,9 +93,10 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
     const uint32_t instMask = GENERAL ? userMask : 0xFFu;  // InstanceInclusionMask is 0xFF for every ray of the pipelines
     constexpr uint32_t rayContribution = MODE == 1 ? 1u : 0u;  // shadow rays use hit group 1 (S/RaytracingCommon.hlsli:94)
 
-    uint32_t stack[RT_STACK_SIZE];
-#if RT_PERSIST_WIDE4
-    uint32_t stackT[(MODE == 1 || !RT_POP_CULL) ? 1 : RT_STACK_SIZE];  // entry distance of each pushed node (culled at pop)
+    PersistStack stk;
+#if RT_SMEM_STACK > 0
+    __shared__ uint32_t s_stack[RT_SMEM_STACK][kPersistThreads];
+    stk.sm = &s_stack[0][threadIdx.x];
 #endif
     // per-lane ray state
     bool alive = false;
@@ -242,7 +264,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             if (alive && !atLeaf) {
 #if RT_PERSIST_WIDE4
                 // one 128-byte node = four child boxes (two BVH2 levels per dependent fetch)
-                ref = wide4_step<(MODE != 1) && RT_POP_CULL, MODE != 1>(nodes, ref, cur, tCur, stack, stackT, sp, status);
+                ref = wide4_step<false, MODE != 1>(nodes, ref, cur, tCur, stk, sp, status);
 #else
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + ref);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
@@ -252,7 +274,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
                 const uint32_t l = __float_as_uint(n0.w), r = __float_as_uint(n1.w);
                 if (lh && rh) {
                     const bool rightFirst = rt < lt;
-                    if (sp < RT_STACK_SIZE) stack[sp++] = rightFirst ? l : r;
+                    if (stk.room(sp, 1)) stk.push(sp, rightFirst ? l : r, 0u);
                     else atomicOr(status, 1u);
                     ref = rightFirst ? r : l;
                 } else if (lh || rh) {
@@ -277,12 +299,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
                     blasBase = -1;
                 }
                 --sp;
-#if RT_PERSIST_WIDE4
-                // a node whose entry distance (rounded down when it was pushed) is not in front of the committed hit
-                // cannot hold a closer one
-                if (RT_POP_CULL && MODE != 1 && (stackT[sp] & 0x7ffffffcu) >= __float_as_uint(tCur)) continue;
-#endif
-                ref = stack[sp];
+                ref = stk.at(sp);
                 break;
             }
         }

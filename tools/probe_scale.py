@@ -99,6 +99,8 @@ def main():
             rays = s.rays * args.reps
             out[name] = {"mrays_per_s": rays / t / 1e3 if t else None, "n_int": s.internal_visits / max(s.rays, 1),
                          "n_leaf": s.leaf_visits / max(s.rays, 1), "max_stack": int(s.max_stack), "ms_total": t}
+        import hashlib
+        out["image_sha1"] = hashlib.sha1(r.image(0).tobytes()).hexdigest()[:12]  # variants must not change the frame
         print(json.dumps(out), flush=True)
         ctx.status()
 
