@@ -65,6 +65,9 @@ def parse_args():
     ap.add_argument("--strong-strip-groups", type=int, default=None,
                     help="strip groups of the strong-scaling shard plan (default: sample sharding first, strips when samples run out)")
     ap.add_argument("--strong-reps", type=int, default=2)
+    ap.add_argument("--strong-depth", type=int, default=2, choices=[1, 2],
+                    help="MAX_RADIANCE_RAY_DEPTH of the strong-scaling frame (BASELINE config 3 is '2-bounce'; the reference's shaders are 1)")
+    ap.add_argument("--radiance-depth", type=int, default=1, choices=[1, 2], help="MAX_RADIANCE_RAY_DEPTH of the headline workload (1 = reference)")
     ap.add_argument("--no-target-scene", action="store_true", help="skip the 1.31 M-triangle incoherent-ray target measurement")
     return ap.parse_args()
 
@@ -79,7 +82,7 @@ def load_workload(args):
 def workload_config(args, wl):
     return {
         "workload": wl.description, "width": wl.width, "height": wl.height, "spp_per_step": wl.spp,
-        "triangles": wl.num_triangles, "instances": len(wl.transforms),
+        "triangles": wl.num_triangles, "instances": len(wl.transforms), "max_radiance_ray_depth": getattr(args, "radiance_depth", 1),
         "l2": "per-frame ray queues (~0.45 KB/pixel, ~0.9 GB per 1080p frame) exceed the 126 MB L2 and are rewritten "
               "every frame; the traversal structure of C2/C3 stays L1/L2-resident by design",
     }
@@ -239,6 +242,7 @@ def run_ours(args):
     setup = wl.setup
     env = scenes.sky_cube(64)
     jit = scenes.jitter_sequence(setup.seed, 1024, W, H)
+    ctx.set_render_options(args.radiance_depth, False)
     n_out = 2 if wl.realtime else 1
     outs = [torch.zeros(H * W * 4, dtype=torch.float32, device="cuda") for _ in range(n_out)]
     out_t = outs[0]
@@ -559,6 +563,7 @@ def measure_strong(args, ctx, rt, torch, dist, stream, world, rank, comm):
             img_h.copy_(frame_d if world > 1 else acc, non_blocking=True)
         ev[4].record(stream)
 
+    ctx.set_render_options(args.strong_depth, False)
     frame_once()  # warm-up (also grows the wavefront workspace)
     torch.cuda.synchronize()
     ctx.status()
@@ -576,6 +581,7 @@ def measure_strong(args, ctx, rt, torch, dist, stream, world, rank, comm):
         times.append(float(t.item()))
         parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
     rc = ctx.ray_counts(reset=True)
+    ctx.set_render_options(args.radiance_depth, False)
     r = torch.tensor([float(rc.primary + rc.secondary + rc.shadow)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
@@ -589,6 +595,7 @@ def measure_strong(args, ctx, rt, torch, dist, stream, world, rank, comm):
     return {"metric": "time to frame, ms (fixed frame, strong scaling; lower is better)", "time_to_frame_ms": ms, "all_ms": times,
             "n_gpus": world, "workload": f"{wl.description.split(' progressive')[0]}: ONE frame of {SPP} spp in total, split over {world} rank(s)",
             "width": W, "height": H, "spp_total": SPP, "triangles": wl.num_triangles,
+            "max_radiance_ray_depth": args.strong_depth,
             "shard_plan": {"strip_groups": plan.strip_groups, "sample_groups": plan.sample_groups, "strip_rows": plan.strip_rows,
                            "samples_on_rank0": len(plan.samples)},
             "root_breakdown_ms": dict(zip(["h2d_and_build", "dispatches", "nccl_reduce", "d2h_root"], parts[best])),

@@ -254,6 +254,13 @@ int rt_set_output(rt_context *ctx, uint32_t slot, float *rgba, uint64_t pitch) {
     ctx->pitch[slot] = pitch;
     return RT_OK;
 }
+int rt_set_render_options(rt_context *ctx, const rt_render_options *o) {
+    RT_REQUIRE(ctx && o, "null argument");
+    RT_REQUIRE(o->max_radiance_ray_depth == 1 || o->max_radiance_ray_depth == 2, "max_radiance_ray_depth must be 1 or 2");
+    RT_REQUIRE(o->half_render_targets <= 1, "half_render_targets must be 0 or 1");
+    ctx->render_options = *o;
+    return RT_OK;
+}
 int rt_set_tlas(rt_context *ctx, const void *tlas) {
     RT_REQUIRE(ctx != nullptr, "ctx");
     ctx->tlas = tlas;

@@ -60,6 +60,7 @@ struct rt_context {
     float *output[2] = {nullptr, nullptr};
     uint64_t pitch[2] = {0, 0};
     const void *tlas = nullptr;
+    rt_render_options render_options{1u, 0u};
 
     rt_workspace ws;
     cudaStream_t side_stream = nullptr;  // shadow depth-0 wave of a dispatch, overlapped with the secondary-ray chain

@@ -15,6 +15,8 @@
 //   * pass H tiles are 256 x 8 pixels (halo overhead 2k/256), pass V tiles 32 x 64 (2k/64); rows are staged with
 //     coalesced 16-byte loads and pass H writes its results back through shared memory so stores are coalesced too.
 // Out-of-image texels read as 0 for both the input and the joint image (D3D out-of-bounds load).
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -35,6 +37,7 @@ struct DenoiseArgs {
     const float4 *joint, *input;
     float4 *out;
     int w, h, k;
+    int half;  // stores round through fp16 (the reference's intermediate and output targets are R16G16B16A16_FLOAT)
     rt_denoiser_params prm;
     float wts[2 * MAX_EXTENT + 1];
 };
@@ -161,7 +164,9 @@ __global__ void __launch_bounds__(kThreadsDn, 3) k_denoise(const __grid_constant
                 const int x = bx + c;
                 if (x < A.w) {
                     const float *q = pl + warp * H_PITCH + hpad(c);
-                    A.out[size_t(y0) * A.w + x] = make_float4(q[0], q[PLANE], q[2 * PLANE], 1.0f);
+                    float4 v = make_float4(q[0], q[PLANE], q[2 * PLANE], 1.0f);
+                    if (A.half) v.x = __half2float(__float2half_rn(v.x)), v.y = __half2float(__float2half_rn(v.y)), v.z = __half2float(__float2half_rn(v.z));
+                    A.out[size_t(y0) * A.w + x] = v;
                 }
             }
         }
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(kThreadsDn, 3) k_denoise(const __grid_constant
             const float e = 1.0f / A.prm.gamma;
             cr = fminf(fmaxf(powf(cr, e), 0.0f), 1.0f), cg = fminf(fmaxf(powf(cg, e), 0.0f), 1.0f), cb = fminf(fmaxf(powf(cb, e), 0.0f), 1.0f);
         }
+        if (A.half) cr = __half2float(__float2half_rn(cr)), cg = __half2float(__float2half_rn(cg)), cb = __half2float(__float2half_rn(cb));
         A.out[size_t(y) * A.w + x0] = make_float4(cr, cg, cb, 1.0f);
     }
 }
@@ -206,6 +212,7 @@ extern "C" int rt_denoise(rt_context *ctx, const float *direct, const float *ind
     // maxKernelSize beyond MAX_EXTENT reads outside the reference's LDS tile (undefined); clamp.
     A.k = prm->maxKernelSize < 0 ? 0 : (prm->maxKernelSize > MAX_EXTENT ? MAX_EXTENT : prm->maxKernelSize);
     A.prm = *prm;
+    A.half = int(ctx->render_options.half_render_targets);
     // per-group weight table: BilateralFilter.hlsli:80-90
     for (int i = -MAX_EXTENT; i <= MAX_EXTENT; ++i) {
         int ai = i < 0 ? -i : i;

@@ -25,6 +25,8 @@
 //
 // Random numbers are a pure function of (pixel, frameCount) and are re-derived at each depth exactly as the
 // shaders re-initialise their seed, so no RNG state travels through the queues.
+#include <cuda_fp16.h>
+
 #include <cstdio>
 
 #include "shade.cuh"
@@ -44,6 +46,8 @@ struct Launch {
     float jitterScale;
     uint32_t realtime;
     uint32_t shadowsPerHit;  // 2, or 4 in the ambient-occlusion debug view
+    uint32_t maxDepth;       // MAX_RADIANCE_RAY_DEPTH: 1 (reference) or 2 (rt_set_render_options)
+    uint32_t halfTargets;    // stores round through fp16 (R16G16B16A16_FLOAT emulation)
 };
 
 struct WS {
@@ -63,6 +67,12 @@ struct WS {
     float4 *T0, *T1, *T2;
     rt_ray *shadowQ1;   // [4P]
     uint8_t *vis1;
+    // depth-2 wave (maxDepth == 2 only): the Phong-lobe ray of every secondary hit, same planar indexing as secQ
+    rt_ray *terQ;       // [2P]
+    float4 *terHitA;    // [2P]
+    uint32_t *terRec;   // [2P]
+    float4 *terRad;     // [2P] radiance returned by the depth-2 hit (or the environment)
+    float2 *T3;         // [2P] {brdf, pdf} of the depth-1 lobe sample
 };
 
 enum : uint32_t {
@@ -202,6 +212,9 @@ __device__ __forceinline__ void write_pixel(const Launch &L, float *out, uint64_
         cur = make_float4((fn * prev.x + cur.x) / fn1, (fn * prev.y + cur.y) / fn1, (fn * prev.z + cur.z) / fn1,
                           (fn * prev.w + cur.w) / fn1);
     }
+    if (L.halfTargets)  // what an R16G16B16A16_FLOAT target holds after the store (and returns as `prev` next frame)
+        cur = make_float4(__half2float(__float2half_rn(cur.x)), __half2float(__float2half_rn(cur.y)), __half2float(__float2half_rn(cur.z)),
+                          __half2float(__float2half_rn(cur.w)));
     *px = cur;
 }
 
@@ -441,7 +454,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constan
         const uint32_t kindPlane = lr >= cnt ? 1u : 0u, hitSlot = lr - kindPlane * cnt;
         const uint32_t r = lr < n ? kindPlane * ws.plane + hitSlot : 0xffffffffu;
         bool wantShadow = false;
-        f3 pos = mk3(0, 0, 0);
+        f3 pos = mk3(0, 0, 0), terDir = mk3(0, 0, 1);
+        float terTmax = -1.0f;
         LightEval le;
         uint32_t kind = 0, rec = 0;
         f3 specTerm = mk3(0, 0, 0);
@@ -476,17 +490,24 @@ __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constan
                         float exponent = expf((1.0f - R.mat.roughness) * 12.0f);
                         float pdf, brdf;
                         f3 mirror = reflect3(d, N);
-                        (void)phong_lobe(seed, mirror, exponent, pdf, brdf);
+                        const f3 lobe = phong_lobe(seed, mirror, exponent, pdf, brdf);
                         spec = spec + mk3(0, 0, 0) * brdf / pdf;
                         fres = fresnel_schlick(d, N, mk3(R.mat.specular[0], R.mat.specular[1], R.mat.specular[2]));
+                        if (L.maxDepth >= 2) {  // shootSecondaryRay at depth 1 traces instead of returning 0
+                            terDir = lobe, terTmax = RT_RAY_MAX_T;
+                            ws.T3[r] = make_float2(brdf, pdf);
+                        }
                     }
-                    specTerm = R.mat.reflectivity * spec * fres;
+                    // depth 1: the whole (zero or NaN) term; depth 2: the Fresnel factor, k_resolve multiplies the traced radiance in
+                    specTerm = L.maxDepth >= 2 ? fres : R.mat.reflectivity * spec * fres;
                     wantShadow = true;
                 }
             } else {
                 ws.T0[r] = make_float4(0, 0, 0, __uint_as_float(0u));
             }
         }
+        if (L.maxDepth >= 2 && lr < n) store_ray(&ws.terQ[r], pos, RT_RAY_EPSILON, terDir, terTmax);  // inactive (tmax < 0) unless a lobe ray was drawn
+        warp_count_add(&rayCounts[1], terTmax >= 0.0f ? 1u : 0u);
         const uint32_t sh = warp_alloc(wantShadow, &ws.counters[1]);
         if (wantShadow) {
             store_ray(&ws.shadowQ1[sh], pos, RT_RAY_EPSILON, le.dirL, useDir ? RT_RAY_MAX_T : -1.0f);
@@ -500,13 +521,80 @@ __global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K5b (maxDepth == 2)
+// shade() / shadeAOV() of a depth-2 hit: direct light without shadow rays (MAX_SHADOW_RAY_DEPTH 2: visibility 1), no indirect
+// diffuse (currentDepth < 1 only), the lobe sample drawn and its 0 * brdf / pdf term kept literally, exactly as depth 1 does
+// when the radiance depth is 1.
+__global__ void __launch_bounds__(kBlock) k_shade_tertiary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+                                                           uint32_t n_recs, const float *env, uint32_t envSize, uint32_t *status) {
+    const uint32_t cnt = ws.counters[0], n = cnt * 2;
+    for (uint32_t lr = blockIdx.x * blockDim.x + threadIdx.x; lr < n; lr += gridDim.x * blockDim.x) {
+        const uint32_t kindPlane = lr >= cnt ? 1u : 0u, hitSlot = lr - kindPlane * cnt;
+        const uint32_t r = kindPlane * ws.plane + hitSlot;
+        const float4 *rp = reinterpret_cast<const float4 *>(ws.terQ + r);
+        const float4 a = rp[0], b = rp[1];
+        if (b.w < 0.0f) continue;  // no lobe ray from this secondary hit
+        const float4 hA = ws.terHitA[r];
+        const f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+        f3 rad;
+        if (__float_as_uint(hA.w) == RT_NO_HIT) {
+            rad = sample_env(env, envSize, d) * L.f.options.environmentStrength;
+        } else {
+            uint32_t rec = ws.terRec[r];
+            if (rec >= n_recs) rec = 0, atomicOr(status, 8u);
+            const rt_hit_record_dev &R = recs[rec];
+            const f3 N = normalize3(interpolate_normal(R, __float_as_uint(hA.w), hA.y, hA.z));
+            const f3 pos = o + hA.x * d;
+            const uint32_t pix = ws.slotInfo[hitSlot].x;
+            const uint32_t x = L.x0 + pix % L.rw, y = image_row(L, pix / L.rw);
+            uint32_t seed = init_rand(x + y * L.width, L.f.cameraParams.frameCount);
+            const LightEval le = eval_lights(L.f, pos, N);
+            f3 direct = mk3(0, 0, 0);
+            const f3 dirC = le.dirPre * 1.0f, pointC = le.pointPre * 1.0f * le.falloff;  // visibility 1
+            if (!L.realtime && L.f.options.debug == 2) {
+                if (next_rand(seed) < 0.5f) direct = direct + dirC * 2.0f;
+                else direct = direct + pointC * 2.0f;
+            } else {
+                direct = direct + dirC;
+                direct = direct + pointC;
+            }
+            f3 fres = mk3(0, 0, 0), spec = mk3(0, 0, 0);
+            if ((R.mat.type == 1 || R.mat.type == 2) && R.mat.reflectivity > 0.001f) {
+                float exponent = expf((1.0f - R.mat.roughness) * 12.0f);
+                float pdf, brdf;
+                (void)phong_lobe(seed, reflect3(d, N), exponent, pdf, brdf);
+                spec = spec + mk3(0, 0, 0) * brdf / pdf;
+                fres = fresnel_schlick(d, N, mk3(R.mat.specular[0], R.mat.specular[1], R.mat.specular[2]));
+            }
+            const f3 albedo = mk3(R.mat.albedo[0], R.mat.albedo[1], R.mat.albedo[2]);
+            const f3 specTerm = R.mat.reflectivity * spec * fres;
+            if (L.realtime) rad = albedo * direct / RT_M_PI + specTerm;
+            else rad = (mk3(R.mat.emissive[0], R.mat.emissive[1], R.mat.emissive[2]) * R.mat.emissive[3] + albedo * ((direct + mk3(0, 0, 0)) / RT_M_PI)) + specTerm;
+        }
+        ws.terRad[r] = make_float4(rad.x, rad.y, rad.z, 1.0f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K7
 __device__ __forceinline__ f3 secondary_radiance(const Launch &L, const WS &ws, const rt_hit_record_dev *recs, uint32_t r) {
     const float4 t0 = ws.T0[r];
     const uint32_t kind = __float_as_uint(t0.w);
     if ((kind & 15u) == 0) return mk3(0, 0, 0);
     if ((kind & 15u) == 1) return mk3(t0.x, t0.y, t0.z);
-    const float4 t1 = ws.T1[r], t2 = ws.T2[r];
+    const float4 t1 = ws.T1[r];
+    float4 t2 = ws.T2[r];
+    if (L.maxDepth >= 2) {  // t2.xyz is the Fresnel factor: put the traced reflection in (shade(): spec += refl * brdf / pdf)
+        const rt_material_params &mm = recs[__float_as_uint(t2.w)].mat;
+        f3 term = mk3(0, 0, 0);
+        if ((mm.type == 1 || mm.type == 2) && mm.reflectivity > 0.001f) {
+            const float4 tr = ws.terRad[r];
+            const float2 bp = ws.T3[r];
+            f3 spec = mk3(0, 0, 0);
+            spec = spec + mk3(tr.x, tr.y, tr.z) * bp.x / bp.y;
+            term = mm.reflectivity * spec * mk3(t2.x, t2.y, t2.z);
+        }
+        t2.x = term.x, t2.y = term.y, t2.z = term.z;
+    }
     const uint32_t sh = ws.secShadow[r];
     const float v0 = float(ws.vis1[sh]), v1 = float(ws.vis1[2 * size_t(ws.plane) + sh]);
     const rt_material_params &m = recs[__float_as_uint(t2.w)].mat;
@@ -668,6 +756,10 @@ int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws, uint32_t part = 0, uin
                    oS1 = take(16 * P), oS2 = take(16 * P), oS3 = take(4 * P), oSQ0 = take(32 * 4 * P), oV0 = take(4 * P),
                    oSec = take(32 * 2 * P), oSecH = take(16 * 2 * P), oSecR = take(4 * 2 * P), oSecS = take(4 * 2 * P),
                    oT0 = take(16 * 2 * P), oT1 = take(16 * 2 * P), oT2 = take(16 * 2 * P), oSQ1 = take(32 * 4 * P), oV1 = take(4 * P);
+    // the depth-2 wave's arrays follow everything else, so the offsets above do not depend on the option
+    const bool depth2 = ctx->render_options.max_radiance_ray_depth >= 2;
+    const uint64_t oTerQ = take(depth2 ? 32 * 2 * P : 0), oTerH = take(depth2 ? 16 * 2 * P : 0), oTerR = take(depth2 ? 4 * 2 * P : 0),
+                   oTerRad = take(depth2 ? 16 * 2 * P : 0), oT3 = take(depth2 ? 8 * 2 * P : 0);
     const uint64_t one = align_up(o, 256);
     if (ctx->ws.bytes < one * parts) {
         if (ctx->ws.base) {
@@ -687,6 +779,8 @@ int ensure_workspace(rt_context *ctx, uint64_t P, WS &ws, uint32_t part = 0, uin
     ws.secHitA = (float4 *)(b + oSecH), ws.secRec = (uint32_t *)(b + oSecR), ws.secShadow = (uint32_t *)(b + oSecS);
     ws.T0 = (float4 *)(b + oT0), ws.T1 = (float4 *)(b + oT1), ws.T2 = (float4 *)(b + oT2), ws.shadowQ1 = (rt_ray *)(b + oSQ1);
     ws.vis1 = b + oV1;
+    ws.terQ = (rt_ray *)(b + oTerQ), ws.terHitA = (float4 *)(b + oTerH), ws.terRec = (uint32_t *)(b + oTerR);
+    ws.terRad = (float4 *)(b + oTerRad), ws.T3 = (float2 *)(b + oT3);
     return RT_OK;
 }
 
@@ -747,6 +841,8 @@ static int dispatch_impl(rt_context *ctx, rt_program *prog, uint32_t width, uint
     L.jitterScale = realtime ? 10.0f : 30.0f;  // S/ProgressiveRaytracing.hlsl:26, S/RealtimeRaytracing.hlsl:34
     L.realtime = realtime ? 1u : 0u;
     L.shadowsPerHit = (!realtime && L.f.options.showAmbientOcclusionOnly) ? 4u : 2u;
+    L.maxDepth = ctx->render_options.max_radiance_ray_depth;
+    L.halfTargets = ctx->render_options.half_render_targets;
     int rc = upload_records(prog);
     if (rc) return rc;
     const bool timing = ctx->timing;
@@ -850,6 +946,14 @@ static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, con
     if (stats) k_trace_queue<true, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, nullptr, nullptr, ws.vis1, ctx->status, sShadow);
     else k_trace_persistent<1><<<pgrid<1>(ctx), 128, 0, st>>>(ctx->tlas, ws.shadowQ1, ws.counters + 1, 2, 2 * ws.plane, TraceSink{nullptr, nullptr, ws.vis1, nullptr}, ctx->status, ws.counters + 6, 0, 0xFF);
     if (timing) RT_CUDA(cudaEventRecord(ctx->ev[6], st));
+    if (L.maxDepth >= 2) {
+        // depth-2 wave: the Phong-lobe rays of the secondary hits (incoherent closest-hit rays, counted as secondary rays)
+        if (stats) k_trace_queue<false, true><<<qgrid, kBlock, 0, st>>>(ctx->tlas, ws.terQ, ws.counters, 2, ws.plane, ws.terHitA, ws.terRec, nullptr, ctx->status, sSec);
+        else k_trace_persistent<0><<<pgrid<0>(ctx), 128, 0, st>>>(ctx->tlas, ws.terQ, ws.counters, 2, ws.plane, TraceSink{ws.terHitA, ws.terRec, nullptr, nullptr}, ctx->status, ws.counters + 7, 0, 0xFF);
+        if (timing) RT_CUDA(cudaEventRecord(ctx->ev[7], st));
+        k_shade_tertiary<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, prog->n_recs, prog->env_texels, prog->env_size, ctx->status);
+        ctx->launches += 2;
+    }
     if (overlap) RT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     k_resolve<<<qgrid, kBlock, 0, st>>>(L, ws, prog->dev_recs, ctx->output[0], ctx->pitch[0], ctx->output[1], ctx->pitch[1]);
     ctx->launches += 7;
@@ -865,6 +969,11 @@ static int dispatch_band(rt_context *ctx, rt_program *prog, const Launch &L, con
         ctx->t_shadow += ms;
         RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
         ctx->t_shadow += ms;
+        if (L.maxDepth >= 2) {
+            RT_CUDA(cudaEventSynchronize(ctx->ev[7]));
+            RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+            ctx->t_secondary += ms;
+        }
     }
     return RT_OK;
 }

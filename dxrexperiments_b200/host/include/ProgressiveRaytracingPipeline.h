@@ -28,6 +28,9 @@ public:
     // sample s as a single GPU would (update() takes its jitter from a sequential generator, :191-193).
     void setStripShard(UINT stripRows, UINT groups, UINT group) { mStripRows = stripRows, mStripGroups = groups, mStripGroup = group; }
     void skipFrame() { (void)mRngDist(mRng), (void)mRngDist(mRng); }
+    // MAX_RADIANCE_RAY_DEPTH (1 in the reference's shaders; 2 = one more Phong-lobe bounce) and emulation of the
+    // R16G16B16A16_FLOAT render targets createOutputResource() is asked for (rt_set_render_options); applied by render().
+    void setRenderOptions(UINT maxRadianceRayDepth, bool halfRenderTargets) { mRenderOptions = {maxRadianceRayDepth, halfRenderTargets ? 1u : 0u}; }
 
     // Environment: a procedural sky by default; loadEnvironmentDDS replaces it with an R16G16B16A16F / R32G32B32A32F
     // cube map file such as the reference's assets/textures/CathedralRadiance.dds.
@@ -57,6 +60,7 @@ protected:
     DXRFramework::RtTexture::SharedPtr mEnvCube;
     bool mActive = true;
     UINT mStripRows = 32, mStripGroups = 1, mStripGroup = 0;
+    rt_render_options mRenderOptions{1u, 0u};
     std::mt19937 mRng;
     std::uniform_real_distribution<float> mRngDist;
 };

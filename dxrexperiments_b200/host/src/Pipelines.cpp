@@ -156,6 +156,7 @@ void RaytracingPipelineBase::render(UINT /*frameIndex*/, UINT width, UINT height
     for (UINT i = 0; i < mNumOutputs; ++i)
         ThrowIfFailed(rt_set_output(ctx, i, static_cast<float *>(mOutputResource.at(i)->ptr()), uint64_t(width) * 16), "rt_set_output");
     ThrowIfFailed(rt_set_tlas(ctx, mRtScene->getTlasWrappedPtr()), "rt_set_tlas");
+    ThrowIfFailed(rt_set_render_options(ctx, &mRenderOptions), "rt_set_render_options");
 
     if (mStripGroups > 1) mRtContext->raytraceStrips(mRtBindings, mRtState, width, height, mStripRows, mStripGroups, mStripGroup);
     else mRtContext->raytrace(mRtBindings, mRtState, width, height, 3);

@@ -70,6 +70,7 @@ static int usage() {
     std::puts("dxr_headless [--model file.obj | --scene cornell|triangle] [--pipeline progressive|realtime] [--width W] [--height H]\n"
               "             [--spp N] [--seed S] [--no-jitter] [--eye x y z] [--at x y z] [--light-pos x y z] [--env-dds file | --env-raw file size]\n"
               "             [--out file.pfm] [--out2 file.pfm] [--denoise file.pfm] [--exr file.exr [--exr-half]] [--dump-frames file.bin] [--device N]\n"
+              "             [--radiance-depth 1|2] [--fp16-targets]\n"
               "             [--world N --rank R --comm-file path [--strip-groups G] [--strip-rows 32]]   (one process per GPU)");
     return 0;
 }
@@ -156,6 +157,7 @@ int main(int argc, char **argv) {
         }
         pipeline->loadResources(3);
         pipeline->createOutputResource(DXGI_FORMAT_R16G16B16A16_FLOAT, width, height);
+        pipeline->setRenderOptions(UINT(a.num("radiance-depth", 1)), a.has("fp16-targets"));
         if (stripGroups > 1) pipeline->setStripShard(UINT(a.num("strip-rows", 32)), stripGroups, stripGroup);
 
         auto t0 = std::chrono::steady_clock::now();

@@ -77,6 +77,7 @@ def _load():
         "rt_set_frame_constants": (i32, [vp, vp]),
         "rt_set_output": (i32, [vp, u32, vp, u64]),
         "rt_set_tlas": (i32, [vp, vp]),
+        "rt_set_render_options": (i32, [vp, vp]),
         "rt_dispatch_rays": (i32, [vp, vp, u32, u32, u32]),
         "rt_dispatch_rays_region": (i32, [vp, vp, u32, u32, u32, u32, u32, u32]),
         "rt_get_ray_counts": (i32, [vp, vp, i32]),
@@ -181,6 +182,11 @@ class Context:
 
     def status(self):
         check(lib.rt_get_status(self.handle))
+
+    def set_render_options(self, max_radiance_ray_depth: int = 1, half_render_targets: bool = False):
+        """MAX_RADIANCE_RAY_DEPTH (1 = the reference's shaders, 2 = one more Phong-lobe bounce) and R16G16B16A16_FLOAT emulation."""
+        o = (C.c_uint32 * 2)(max_radiance_ray_depth, 1 if half_render_targets else 0)
+        check(lib.rt_set_render_options(self.handle, o))
 
     def launches(self) -> int:
         return int(lib.rt_launch_count(self.handle))

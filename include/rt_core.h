@@ -177,6 +177,21 @@ int rt_set_frame_constants(rt_context *ctx, const rt_per_frame_constants *frame)
  * (src/DXRExperimentsApp.cpp:28); fp32 is a declared deviation. */
 int rt_set_output(rt_context *ctx, uint32_t slot, float *rgba, uint64_t pitch_bytes);
 int rt_set_tlas(rt_context *ctx, const void *tlas_result);
+/* Two things that are constants of the reference and options here (defaults = the reference's shaders / this library's
+ * declared fp32 deviation):
+ *   max_radiance_ray_depth — MAX_RADIANCE_RAY_DEPTH, 1 in assets/shaders/RaytracingCommon.hlsli:11.  2 lets the Phong-lobe
+ *     bounce continue one level (BASELINE config 3, "2-bounce"): a secondary hit on a reflective material shoots one more
+ *     incoherent closest-hit ray, whose hit is shaded with direct light only (no shadow rays at depth 2:
+ *     MAX_SHADOW_RAY_DEPTH 2; no indirect diffuse below depth 0: ProgressiveRaytracing.hlsl:107).  Parity with the
+ *     reference is pinned at 1; at 2 the CPU oracle follows the same shader source with the constant changed.
+ *   half_render_targets — 1: every value stored to an output (accumulation, AOVs, both denoiser passes) is rounded to fp16
+ *     and back, which is what the reference's R16G16B16A16_FLOAT targets hold (src/DXRExperimentsApp.cpp:28, :121); the
+ *     buffers stay RGBA fp32.  0 (default): full fp32, needed for multi-GPU sums and long accumulations. */
+typedef struct rt_render_options {
+    uint32_t max_radiance_ray_depth; /* 1 or 2 */
+    uint32_t half_render_targets;    /* 0 or 1 */
+} rt_render_options;
+int rt_set_render_options(rt_context *ctx, const rt_render_options *options);
 
 /* RtContext::raytrace -> DispatchRays (libs/DXRFramework/RtContext.cpp:192-222,
  * FL/UberShaderRayTracingProgram.cpp:213-272).  `depth` is accepted and ignored, as in the reference. */

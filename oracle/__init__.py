@@ -95,6 +95,7 @@ def lib():
         L.orc_primary_ray.argtypes = [vp, u32, u32, u32, u32, C.c_float, vp]
         L.orc_primary_rays.argtypes = [vp, u32, u32, C.c_float, vp]
         L.orc_sample_env.argtypes = [vp, vp, vp]
+        L.orc_set_render_options.argtypes = [u32, i32]
         _lib = L
     return _lib
 
@@ -364,6 +365,11 @@ def env_cube(texels):
     e.texels = tex.ctypes.data
     e.size = tex.shape[1]
     return e, tex
+
+
+def set_render_options(max_radiance_ray_depth: int = 1, half_render_targets: bool = False):
+    """MAX_RADIANCE_RAY_DEPTH (1 = the reference) and R16G16B16A16_FLOAT target emulation; process-wide."""
+    lib().orc_set_render_options(max_radiance_ray_depth, 1 if half_render_targets else 0)
 
 
 def render_progressive(tlas: Tlas, records: Records, env_texels, frame: T.PerFrameConstants, width, height,

@@ -96,6 +96,13 @@ void orc_trace(const orc_tlas *t, const rt_ray *rays, uint64_t n, uint32_t ray_f
 
 /* ---- pipelines ---- */
 
+/* Two things that are fixed in the reference and options here (process-wide; set before rendering):
+ *   max_radiance_ray_depth: MAX_RADIANCE_RAY_DEPTH (assets/shaders/RaytracingCommon.hlsli:11), 1 = the reference, 2 = the
+ *     Phong-lobe bounce continues one more level (BASELINE config 3 "2-bounce"; parity is pinned at 1 only);
+ *   half_render_targets: emulate the R16G16B16A16_FLOAT render targets (src/DXRExperimentsApp.cpp:28): every value stored to
+ *     an output (accumulation, AOVs, denoiser passes) is rounded to fp16 and back. */
+void orc_set_render_options(uint32_t max_radiance_ray_depth, int half_render_targets);
+
 /* One DispatchRays of ProgressiveRaytracing.hlsl over width x height; `accum` (RGBA fp32,
  * width*height*4) is gOutput: read-modify-written with the running mean of RayGen:36-38.
  * recs[i] is the hit record of instance i.  threads<=1: single-threaded. */

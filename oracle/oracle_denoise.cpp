@@ -101,8 +101,8 @@ extern "C" void orc_denoise(const float *direct, const float *indirect_specular,
                 } else {
                     filter_pixel(input, joint, x, y, 1, 0, k, wts, c);
                 }
-                float *o = tmp + (size_t(y) * W + x) * 4;
-                o[0] = c[0], o[1] = c[1], o[2] = c[2], o[3] = 1.0f;
+                float *o = tmp + (size_t(y) * W + x) * 4;  // the intermediate target has the swap chain's format too
+                o[0] = store_value(c[0]), o[1] = store_value(c[1]), o[2] = store_value(c[2]), o[3] = 1.0f;
             }
         });
     }
@@ -136,7 +136,7 @@ extern "C" void orc_denoise(const float *direct, const float *indirect_specular,
                 if (prm->gammaCorrect)
                     for (int i = 0; i < 3; ++i) c[i] = saturate(powf(c[i], 1.0f / prm->gamma));
                 float *o = out + (size_t(y) * W + x) * 4;
-                o[0] = c[0], o[1] = c[1], o[2] = c[2], o[3] = 1.0f;
+                o[0] = store_value(c[0]), o[1] = store_value(c[1]), o[2] = store_value(c[2]), o[3] = 1.0f;
             }
         });
     }

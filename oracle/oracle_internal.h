@@ -9,6 +9,52 @@
 
 namespace orc {
 
+// IEEE fp32 -> fp16 (round to nearest even) -> fp32: what a store to an R16G16B16A16_FLOAT target followed by a load returns.
+inline float half_round(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = x & 0x80000000u;
+    const uint32_t e = (x >> 23) & 0xFFu;
+    uint32_t man = x & 0x7FFFFFu;
+    if (e == 0xFFu) return f;  // Inf / NaN survive
+    const int32_t exp = int32_t(e) - 127 + 15;
+    uint16_t h;
+    if (exp >= 31) h = 0x7C00u;
+    else if (exp <= 0) {
+        if (exp < -10) h = 0;
+        else {
+            man |= 0x800000u;
+            const uint32_t shift = uint32_t(14 - exp);
+            uint32_t v = man >> shift;
+            const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+            if (rem > halfway || (rem == halfway && (v & 1u))) ++v;
+            h = uint16_t(v);
+        }
+    } else {
+        uint32_t v = (uint32_t(exp) << 10) | (man >> 13);
+        const uint32_t rem = man & 0x1FFFu;
+        if (rem > 0x1000u || (rem == 0x1000u && (v & 1u))) ++v;
+        h = uint16_t(v);
+    }
+    // back to fp32
+    const uint32_t he = (h >> 10) & 0x1Fu, hm = h & 0x3FFu;
+    uint32_t bits;
+    if (he == 0) {
+        if (hm == 0) bits = sign;
+        else {
+            float v = float(hm) * 5.9604644775390625e-08f;  // 2^-24
+            std::memcpy(&bits, &v, 4);
+            bits |= sign;
+        }
+    } else if (he == 31) bits = sign | 0x7F800000u;
+    else bits = sign | ((he - 15 + 127) << 23) | (hm << 13);
+    float r;
+    std::memcpy(&r, &bits, 4);
+    return r;
+}
+float store_value(float v);  // oracle_shade.cpp: rounds through fp16 when half render targets are emulated
+
+
 struct f3 {
     float x, y, z;
     float &operator[](int i) { return (&x)[i]; }

@@ -15,7 +15,16 @@ static const float M_PI_F = 3.1415927f;       // S/RaytracingUtils.hlsli:22
 static const float SAMPLER_PI = 3.14159265f;  // :69,92,103
 static const float RAY_MAX_T = 1.0e+38f;      // S/RaytracingCommon.hlsli:8
 static const float RAY_EPSILON = 0.0001f;     // :9
-static const uint32_t MAX_RADIANCE_RAY_DEPTH = 1, MAX_SHADOW_RAY_DEPTH = 2;
+static const uint32_t MAX_SHADOW_RAY_DEPTH = 2;
+// MAX_RADIANCE_RAY_DEPTH is 1 in the reference (S/RaytracingCommon.hlsli:11) — the only value parity is pinned at.
+// orc_set_render_options raises it to 2 for BASELINE's "2-bounce" configuration: the Phong-lobe bounce then continues one
+// level (shootSecondaryRay at depth 1 no longer returns 0); indirect diffuse stays at depth 0 (shade()'s own
+// `currentDepth < 1`, S/ProgressiveRaytracing.hlsl:107) and depth-2 hits take no shadow rays (MAX_SHADOW_RAY_DEPTH 2).
+static uint32_t MAX_RADIANCE_RAY_DEPTH = 1;
+// The reference's render targets are R16G16B16A16_FLOAT (src/DXRExperimentsApp.cpp:28): every store rounds to fp16 and every
+// read-back (the accumulation's `prev`) returns that rounded value.  Off by default (fp32 targets, the declared deviation).
+static bool HALF_TARGETS = false;
+float store_value(float v) { return HALF_TARGETS ? half_round(v) : v; }
 
 // S/RaytracingUtils.hlsli:26-38
 static uint32_t init_rand(uint32_t val0, uint32_t val1) {
@@ -356,6 +365,11 @@ void orc_primary_rays(const rt_per_frame_constants *frame, uint32_t width, uint3
         for (uint32_t x = 0; x < width; ++x) orc_primary_ray(frame, width, height, x, y, jitter_scale, out + size_t(y) * width + x);
 }
 
+void orc_set_render_options(uint32_t max_radiance_ray_depth, int half_render_targets) {
+    MAX_RADIANCE_RAY_DEPTH = max_radiance_ray_depth < 1 ? 1 : (max_radiance_ray_depth > 2 ? 2 : max_radiance_ray_depth);
+    HALF_TARGETS = half_render_targets != 0;
+}
+
 void orc_render_progressive(const orc_tlas *t, const rt_hit_record *recs, uint32_t n_recs, const rt_env_cube *env,
                             const rt_per_frame_constants *frame, uint32_t width, uint32_t height, float *accum, int threads,
                             rt_ray_counts *counts, rt_trace_stats *secondary_stats) {
@@ -374,7 +388,7 @@ void orc_render_progressive(const orc_tlas *t, const rt_hit_record *recs, uint32
             float *px = accum + (size_t(y) * width + x) * 4;
             float cur[4] = {fmaxf(p.color.x, 0.0f), fmaxf(p.color.y, 0.0f), fmaxf(p.color.z, 0.0f), 1.0f};
             uint32_t n = frame->cameraParams.accumCount;
-            for (int k = 0; k < 4; ++k) px[k] = (float(n) * px[k] + cur[k]) / float(n + 1);
+            for (int k = 0; k < 4; ++k) px[k] = store_value((float(n) * px[k] + cur[k]) / float(n + 1));
         }
     });
     for (auto &c : ctxs) {
@@ -404,9 +418,10 @@ void orc_render_realtime(const orc_tlas *t, const rt_hit_record *recs, uint32_t 
             c.primary++;
             trace_radiance(c, x, y, o, 0.0f, d, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, p);
             float *pd = direct + (size_t(y) * width + x) * 4, *ps = indirect_specular + (size_t(y) * width + x) * 4;
-            pd[0] = fmaxf(p.aov.direct.x, 0.0f), pd[1] = fmaxf(p.aov.direct.y, 0.0f), pd[2] = fmaxf(p.aov.direct.z, 0.0f), pd[3] = 1.0f;
-            ps[0] = fmaxf(p.aov.indirectSpecular.x, 0.0f), ps[1] = fmaxf(p.aov.indirectSpecular.y, 0.0f);
-            ps[2] = fmaxf(p.aov.indirectSpecular.z, 0.0f), ps[3] = 1.0f;
+            pd[0] = store_value(fmaxf(p.aov.direct.x, 0.0f)), pd[1] = store_value(fmaxf(p.aov.direct.y, 0.0f));
+            pd[2] = store_value(fmaxf(p.aov.direct.z, 0.0f)), pd[3] = 1.0f;
+            ps[0] = store_value(fmaxf(p.aov.indirectSpecular.x, 0.0f)), ps[1] = store_value(fmaxf(p.aov.indirectSpecular.y, 0.0f));
+            ps[2] = store_value(fmaxf(p.aov.indirectSpecular.z, 0.0f)), ps[3] = 1.0f;
         }
     });
     if (counts)
