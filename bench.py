@@ -660,7 +660,49 @@ def measure_target_scene(args, ctx, rt, torch):
             "note": "achieved = algorithmic bytes (48 + 64 n_int + 48 n_leaf per ray over the BVH2 visit counts of the same rays) / "
                     "CUDA-event launch time; traffic = dram bytes per launch of the same kernel from the committed ncu capture; "
                     "dram_frac = traffic / time / peak is the share of the HBM roof the kernel really uses"}
+    # the reference's own traversal lever: build flags -> 0 / 1 / 3 treelet passes (FL/TreeletReorder.cpp:66-80).  Same scene,
+    # same rays; build time (device, CUDA events) next to the traversal speed each tree yields.
+    tradeoff = {}
+    import ctypes as C2_
+    for name, flags in (("PREFER_FAST_BUILD (0 treelet passes)", T.BUILD_FLAG_PREFER_FAST_BUILD), ("NONE (1 pass: the application's build)", 0),
+                        ("PREFER_FAST_TRACE (3 passes)", T.BUILD_FLAG_PREFER_FAST_TRACE)):
+        m = wl.meshes[0]
+        vb, ib = ctx.upload(m.vertices), ctx.upload(m.indices)
+        desc = (T.GeometryDesc * 1)()
+        desc[0].vertex_buffer, desc[0].vertex_count, desc[0].vertex_stride_bytes = vb.ptr, m.vertices.shape[0], 24
+        desc[0].index_buffer, desc[0].index_count, desc[0].index_format = ib.ptr, m.indices.size, 32
+        desc[0].flags = T.GEOMETRY_FLAG_OPAQUE
+        info = T.PrebuildInfo()
+        rt.check(rt.lib.rt_blas_prebuild(ctx.handle, desc, 1, flags, C2_.byref(info)))
+        scr, res = ctx.alloc(info.scratch_bytes), ctx.alloc(info.result_bytes)
+        bt = []
+        for rep in range(4):
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            rt.check(rt.lib.rt_blas_build(ctx.handle, desc, 1, flags, scr.ptr, scr.nbytes, res.ptr, res.nbytes))
+            b1.record()
+            torch.cuda.synchronize()
+            if rep:
+                bt.append(b0.elapsed_time(b1))
+        del scr, res, vb, ib
+        rr = rt.Renderer(ctx, wl.meshes, wl.transforms, wl.materials, env, rt.PROGRESSIVE, W, H, outputs=[TorchBuffer(out)],
+                         instance_mesh=wl.instance_mesh, build_flags=flags)
+        for s in range(2):
+            rr.dispatch(scenes.make_frame(wl.setup, W, H, frame_count=s, accum_count=s, jitter=jit[s]))
+        ctx.enable_stage_timing(True)
+        ctx.stage_timing(reset=True)
+        ctx.ray_counts(reset=True)
+        for _ in range(2):
+            for s in range(SPP):
+                rr.dispatch(scenes.make_frame(wl.setup, W, H, frame_count=s, accum_count=s, jitter=jit[s]))
+        _tp, ts2, _tsh = ctx.stage_timing(reset=True)
+        ctx.enable_stage_timing(False)
+        rc2 = ctx.ray_counts(reset=True)
+        tradeoff[name] = {"build_ms": float(np.median(bt)), "build_mtri_per_s": wl.num_triangles / float(np.median(bt)) / 1e3,
+                          "incoherent_mrays_per_s": rc2.secondary / (ts2 * 1e-3) / 1e6}
+        del rr
     return {"workload": wl.description, "triangles": wl.num_triangles, "width": W, "height": H,
+            "build_flags_tradeoff": tradeoff,
             "incoherent_mrays_per_s": sec.rays / SPP / (ms_launch * 1e-3) / 1e6,
             "incoherent_rays_per_launch": sec.rays / SPP, "ms_per_launch": ms_launch,
             "n_int_per_ray": sec.internal_visits / max(sec.rays, 1), "n_leaf_per_ray": sec.leaf_visits / max(sec.rays, 1),

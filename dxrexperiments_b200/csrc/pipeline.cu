@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "shade.cuh"
 #include "trace.cuh"
@@ -855,7 +856,12 @@ static int dispatch_impl(rt_context *ctx, rt_program *prog, uint32_t width, uint
     // persistent kernels end with 8-20 % of their warps idle, k_primary leaves ~30 % of its warp slots unused — blocks of
     // the other band's kernels move in.  Bands touch disjoint pixels, so the image is bit-identical to the one-band run.
     // Instrumented and stage-timed dispatches, and small regions, run as one band.
-    const uint32_t bands = (!timing && !ctx->collect_stats && !ctx->capture && uint64_t(L.rw) * L.rh >= (1u << 18)) ? std::min<uint32_t>(RT_DISPATCH_BANDS, L.rh / 64) : 1u;
+    static const uint32_t band_limit = [] {  // RT_BANDS=1: one band per dispatch, for whole-frame kernel profiles (ncu); default RT_DISPATCH_BANDS
+        const char *e = getenv("RT_BANDS");
+        const int v = e ? atoi(e) : 0;
+        return uint32_t(v >= 1 && v <= RT_MAX_BANDS ? v : RT_DISPATCH_BANDS);
+    }();
+    const uint32_t bands = (!timing && !ctx->collect_stats && !ctx->capture && uint64_t(L.rw) * L.rh >= (1u << 18)) ? std::min<uint32_t>(band_limit, L.rh / 64) : 1u;
     if (bands > 1) {
         if (!ctx->side_stream) {
             RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));

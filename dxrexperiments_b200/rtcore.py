@@ -599,13 +599,13 @@ class Renderer:
     """Convenience host for tests/bench: one scene (instances of meshes), one program, fp32 outputs on the device."""
 
     def __init__(self, ctx: Context, meshes, transforms, materials, env_texels, kind=PROGRESSIVE, width=256, height=256,
-                 outputs=None, instance_mesh=None):
+                 outputs=None, instance_mesh=None, build_flags: int = 0):
         """outputs: optional list of caller-owned device buffers (anything with .ptr, e.g. a wrapped torch tensor)
         of width*height RGBA fp32, one per output slot; allocated here when omitted.
         instance_mesh: optional list, one mesh index per transform (instancing: many instances of few BLASes);
         by default instance i is mesh i."""
         self.ctx, self.width, self.height, self.kind = ctx, width, height, kind
-        self.blases = [ctx.build_blas_from_mesh(m) for m in meshes]
+        self.blases = [ctx.build_blas_from_mesh(m, build_flags=build_flags) for m in meshes]  # 0 = the application's flags (RtModel.cpp:86-118)
         if instance_mesh is None:
             instance_mesh = list(range(len(meshes)))
         assert len(instance_mesh) == len(transforms)
