@@ -98,6 +98,9 @@ int rt_host_free_pinned(void *host);
  * traversal section (rt_core's own wide nodes; opaque to callers).  A TLAS refers to its BLASes
  * by the device address of their result buffers (rt_instance_desc.blas), the analogue of the
  * Fallback Layer's WRAPPED_GPU_POINTER.  Buffers must stay alive while anything refers to them. */
+/* Limits: one acceleration structure holds at most 2^24 - 1 primitives (instances): node and primitive indices are 24 bit
+ * in the reference's node format (FL/RayTracingHelper.hlsli:112-118); more is RT_ERR_INVALID_ARG — split the mesh into
+ * several BLASes under one TLAS.  Scratch and result buffers must be 64-byte aligned. */
 int rt_blas_prebuild(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags,
                      rt_prebuild_info *info);
 int rt_blas_build(rt_context *ctx, const rt_geometry_desc *geoms, uint32_t n_geoms, uint32_t build_flags,
