@@ -70,7 +70,7 @@ static int usage() {
     std::puts("dxr_headless [--model file.obj | --scene cornell|triangle] [--pipeline progressive|realtime] [--width W] [--height H]\n"
               "             [--spp N] [--seed S] [--no-jitter] [--eye x y z] [--at x y z] [--light-pos x y z] [--env-dds file | --env-raw file size]\n"
               "             [--out file.pfm] [--out2 file.pfm] [--denoise file.pfm] [--exr file.exr [--exr-half]] [--dump-frames file.bin] [--device N]\n"
-              "             [--radiance-depth 1|2] [--fp16-targets]\n"
+              "             [--radiance-depth 1|2] [--fp16-targets] [--denoise-mock direct.pfm specular.pfm --denoise out.pfm [--kernel-size K]]\n"
               "             [--world N --rank R --comm-file path [--strip-groups G] [--strip-rows 32]]   (one process per GPU)");
     return 0;
 }
@@ -92,6 +92,28 @@ int main(int argc, char **argv) {
     try {
         if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("--world / --rank");
         auto context = RtContext::create(int(a.num("device", rank)));
+        if (a.has("denoise-mock")) {
+            // DenoiseCompositor with mock inputs (src/DenoiseCompositor.cpp:52-60 loads DirectLighting.png / IndirectSpecular.png and
+            // dispatch() falls back to them when it is handed null SRVs, :113-116): --denoise-mock direct.pfm specular.pfm --denoise out.pfm
+            std::vector<float> d, sp;
+            uint32_t dw = 0, dh = 0, sw = 0, sh = 0;
+            if (a.kv.at("denoise-mock").size() < 2 || !ImageIO::readPFM(a.kv.at("denoise-mock")[0], d, dw, dh) ||
+                !ImageIO::readPFM(a.kv.at("denoise-mock")[1], sp, sw, sh) || dw != sw || dh != sh)
+                throw std::runtime_error("--denoise-mock needs two PFM images of equal size");
+            auto denoiser = DenoiseCompositor::create(context);
+            denoiser->loadResources(3, true);
+            denoiser->setMockResources(context->createBuffer(d.data(), d.size() * sizeof(float)), context->createBuffer(sp.data(), sp.size() * sizeof(float)));
+            denoiser->createOutputResource(DXGI_FORMAT_R16G16B16A16_FLOAT, dw, dh);
+            if (a.has("kernel-size")) denoiser->mConstantBuffer.maxKernelSize = int(a.num("kernel-size", 12));
+            denoiser->dispatch({0, 0}, 0, dw, dh);
+            context->waitForGpu();
+            std::vector<float> out(size_t(dw) * dh * 4);
+            denoiser->getOutputResource()->download(out.data(), out.size() * sizeof(float));
+            if (!ImageIO::writePFM(a.str("denoise", "denoised.pfm"), out.data(), dw, dh)) throw std::runtime_error("cannot write the denoised image");
+            std::printf("{\"denoise_mock\": true, \"width\": %u, \"height\": %u, \"kernel_launches\": %llu, \"core\": \"%s\"}\n", dw, dh,
+                        (unsigned long long)context->launchCount(), rt_version());
+            return 0;
+        }
         // shard plan (dxrexperiments_b200/sharding.py): rank = sampleGroup * stripGroups + stripGroup
         UINT stripGroups = UINT(a.num("strip-groups", 0));
         if (stripGroups == 0) {  // samples first, strips when the samples run out

@@ -273,3 +273,30 @@ def test_headless_multi_gpu_frame_equals_single_gpu_frame(host_built, tmp_path, 
     assert rel_rmse(b, a) <= 1e-6
     info = json.loads(outs[0][0].strip().splitlines()[-1])
     assert info["world"] == world and info["strip_groups"] == strip_groups
+
+
+def write_pfm(path, rgb):
+    h, w = rgb.shape[:2]
+    with open(path, "wb") as f:
+        f.write(b"PF\n%d %d\n-1.0\n" % (w, h))
+        f.write(np.ascontiguousarray(rgb[::-1, :, :3], "<f4").tobytes())
+
+
+@pytest.mark.gpu
+def test_denoise_compositor_mock_resources_with_the_reference_inputs(host_built, tmp_path, orc):
+    """DenoiseCompositor::setMockResources + dispatch with null SRVs (src/DenoiseCompositor.cpp:52-60, 113-116), fed with the
+    committed crop of the reference's own mock inputs (DirectLighting.PNG / IndirectSpecular.PNG)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "denoise_mock_crop.npz"))
+    direct = g["direct_u8"].astype(np.float32) / np.float32(255.0)
+    spec = g["spec_u8"].astype(np.float32) / np.float32(255.0)
+    dp, sp, out = tmp_path / "direct.pfm", tmp_path / "spec.pfm", tmp_path / "out.pfm"
+    write_pfm(dp, direct), write_pfm(sp, spec)
+    r = subprocess.run([EXE, "--denoise-mock", str(dp), str(sp), "--denoise", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout.strip().splitlines()[-1])["denoise_mock"] is True
+    d4 = np.ones(direct.shape[:2] + (4,), np.float32); d4[..., :3] = direct[..., :3]
+    s4 = np.ones_like(d4); s4[..., :3] = spec[..., :3]
+    want, _ = orc.denoise(d4, s4, T.DenoiserParams(1.0, 2.2, 1, 0, 12, 0))
+    got = read_pfm(out)
+    ok = np.isfinite(want[..., :3]).all(axis=-1)
+    np.testing.assert_allclose(got[ok], want[..., :3][ok], rtol=1e-5, atol=1e-6)

@@ -2,7 +2,7 @@
 # tools/run_mgpu.sh <tag> <N> — multi-GPU evidence on an N-GPU box: N-rank parity tests, bench at N (weak headline + strong block).
 TAG=${1:-m}; N=${2:-2}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_multi.py tests/test_host_cpp.py -m gpu -q 2>&1 | tail -8 > gpurun_out/${TAG}_pytest_multi.log
+python -m pytest tests/test_gpu_multi.py tests/test_host_cpp.py tests/test_gpu_validation.py -m gpu -q 2>&1 | tail -8 > gpurun_out/${TAG}_pytest_multi.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_n${N}.json 2> gpurun_out/${TAG}_bench_n${N}.err
 $TR bench.py --gpus $N --steps 1 --warmup 3 --no-e2e --strong-strip-groups 2 > gpurun_out/${TAG}_bench_n${N}_strips2.json 2>> gpurun_out/${TAG}_bench_n${N}.err

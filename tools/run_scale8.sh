@@ -2,7 +2,7 @@
 # tools/run_scale8.sh <tag> — 8-GPU box: N-rank parity tests (2, 4, 8 ranks), then the bench at N = 1, 2, 4, 8 (weak headline + strong block)
 TAG=${1:-s}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_multi.py tests/test_host_cpp.py -m gpu -q 2>&1 | tail -6 > gpurun_out/${TAG}_pytest_multi.log
+python -m pytest tests/test_gpu_multi.py tests/test_host_cpp.py tests/test_gpu_validation.py -m gpu -q 2>&1 | tail -6 > gpurun_out/${TAG}_pytest_multi.log
 for N in 1 2 4 8; do
   if [ $N = 1 ]; then python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-target-scene --build-tris 0 --no-denoise > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_n1.err
   else python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 295$N bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_n$N.err; fi
