@@ -148,7 +148,8 @@ __device__ __forceinline__ void flush_stats(const TraceCtr &c, uint32_t rays, un
                            // 5.84 vs 5.40 Grays/s on C2, 3.29 vs 2.79 on 1.3 M triangles (before the treelet pass the BVH2 loop won on C2)
 #endif
 #ifndef RT_PRIMARY_MIN_BLOCKS
-#define RT_PRIMARY_MIN_BLOCKS 6
+#define RT_PRIMARY_MIN_BLOCKS 7  // 72 registers: the kernel is latency-bound (26 % of the warp slots active at 6 blocks); A/B round 2: 5 / 6 / 7 / 8
+                                 // blocks per SM = 5363 / 5767 / 6103 / 5802 Mrays/s on C2, 3053 / 3160 / 3329 / 3035 on 1.31 M triangles
 #endif
 template <bool STATS>
 __global__ void __launch_bounds__(kBlock, RT_PRIMARY_MIN_BLOCKS) k_primary(const __grid_constant__ Launch L, const void *tlas, WS ws, uint32_t *status,
