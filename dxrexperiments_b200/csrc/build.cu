@@ -78,6 +78,7 @@ __device__ __forceinline__ void block_reduce_aabb(float mn[3], float mx[3], uint
 __global__ void k_init_aabb(uint32_t *enc) {
     if (threadIdx.x < 3) enc[threadIdx.x] = enc_f32(FLT_MAX);
     else if (threadIdx.x < 6) enc[threadIdx.x] = enc_f32(-FLT_MAX);
+    else if (threadIdx.x < 8) enc[threadIdx.x] = 0;  // spare words of the 32-byte slot (k_lbvh_fit's exit-list length)
 }
 __global__ void k_decode_aabb(const uint32_t *enc, float *out) {
     // + 0.0f canonicalises -0 to +0 (fminf(-0,+0) is unspecified on the CPU side).
@@ -248,41 +249,74 @@ __global__ void __launch_bounds__(kSortThreads) k_scan_rows(uint32_t *hist, uint
     if (threadIdx.x == 0) row_total[blockIdx.x] = total;
 }
 
+// 16-byte asynchronous global -> shared copy; bytes < 16 zero-fills the rest (the last piece of the array)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, uint32_t bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+#ifndef RT_SORT_PREFETCH
+#define RT_SORT_PREFETCH 1  // 0: the tile's keys and values are loaded where they are needed (A/B measurements)
+#endif
 template <bool IOTA>
-__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t n,
-                                                                int shift, uint32_t tiles_per_block, const uint32_t *offsets,
-                                                                const uint32_t *row_total, uint32_t *keys_out, uint32_t *vals_out) {
+__global__ void __launch_bounds__(kSortThreads, 4) k_radix_scatter(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t n,
+                                                                   int shift, uint32_t tiles_per_block, const uint32_t *offsets,
+                                                                   const uint32_t *row_total, uint32_t *keys_out, uint32_t *vals_out) {
     __shared__ uint32_t warp_count[kSortWarps][kRadix];
     __shared__ uint32_t base[kRadix], tile_start[kRadix], tile_count[kRadix];
     __shared__ uint32_t s_warp[kSortWarps];
     __shared__ uint32_t s_key[kSortTile], s_val[kSortTile];
+    // Input staging, filled by cp.async one tile ahead: the keys of tile t+1 while tile t is ranked, the values of tile
+    // t+1 while tile t leaves and tile t+1 is ranked (values are not touched before the tile is laid out by digit).
+    // With 4 resident blocks per SM the exposed latency of a tile's loads was a quarter of the kernel's stall samples.
+    __shared__ __align__(16) uint32_t s_in_key[RT_SORT_PREFETCH ? kSortTile : 4];
+    __shared__ __align__(16) uint32_t s_in_val[(RT_SORT_PREFETCH && !IOTA) ? kSortTile : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // n < 2^24 elements (rt_blas_build / rt_tlas_build) and tiles are whole: 32-bit element indices never wrap
+    const uint32_t block_begin = blockIdx.x * tiles_per_block * kSortTile;
+    // one commit group per call, possibly empty, so that "all but the newest group" always means the same thing
+    auto fetch = [&](const uint32_t *src, uint32_t *dst, uint32_t tile, bool enabled) {
+        const uint32_t tile_begin = block_begin + tile * kSortTile;
+        if (RT_SORT_PREFETCH && enabled && tile < tiles_per_block && tile_begin < n) {
+            const uint32_t valid = min(uint32_t(kSortTile), n - tile_begin);
+#pragma unroll
+            for (int k = 0; k < kSortItems / 4; ++k) {  // kSortTile x 4 bytes = kSortThreads x (kSortItems / 4) x 16 bytes
+                const uint32_t e = (k * kSortThreads + threadIdx.x) * 4;
+                if (e < valid) cp_async16(dst + e, src + tile_begin + e, min(16u, (valid - e) * 4u));
+            }
+        }
+        cp_async_commit();
+    };
+    fetch(keys_in, s_in_key, 0, true);
+    fetch(vals_in, s_in_val, 0, !IOTA);
     {
         uint32_t unused;
         const uint32_t row_base = block_exclusive_scan_256(row_total[threadIdx.x], s_warp, unused);
         base[threadIdx.x] = row_base + offsets[threadIdx.x * gridDim.x + blockIdx.x];
     }
-    const uint64_t block_begin = uint64_t(blockIdx.x) * tiles_per_block * kSortTile;
     for (uint32_t tile = 0; tile < tiles_per_block; ++tile) {
-        const uint64_t tile_begin = block_begin + uint64_t(tile) * kSortTile;
+        const uint32_t tile_begin = block_begin + tile * kSortTile;
         if (tile_begin >= n) break;
+        const uint32_t tile_valid = min(uint32_t(kSortTile), n - tile_begin);
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) warp_count[w][threadIdx.x] = 0;
+        cp_async_wait<1>();  // this thread's pieces of keys(tile); the barrier makes everybody's visible
         __syncthreads();
-        uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
-        // all of the tile's loads are in flight before the first rank is computed (the ranking below synchronises the
-        // warp per item, which kept the compiler from hoisting them: ncu showed one exposed global load per item)
+        uint32_t key[kSortItems], prev[kSortItems], info[kSortItems];
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) {
-            const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
-            const bool valid = i < n;
-            key[r] = valid ? __ldcs(keys_in + i) : 0xffffffffu;
-            val[r] = valid ? (IOTA ? uint32_t(i) : __ldcs(vals_in + i)) : 0u;
+            const uint32_t e = warp * 32 * kSortItems + r * 32 + lane;
+            if (RT_SORT_PREFETCH) key[r] = e < tile_valid ? s_in_key[e] : 0xffffffffu;
+            else key[r] = e < tile_valid ? __ldcs(keys_in + tile_begin + e) : 0xffffffffu;
         }
+        if (RT_SORT_PREFETCH) __syncthreads();  // every thread holds its keys: the staging buffer is free again
+        fetch(keys_in, s_in_key, tile + 1, true);
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) {
-            const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
-            const bool valid = i < n;
+            const uint32_t e = warp * 32 * kSortItems + r * 32 + lane;
+            const bool valid = e < tile_valid;
             const uint32_t d = (key[r] >> shift) & (kRadix - 1);
             // lanes holding the same digit, from one ballot per digit bit: MATCH.ANY resolves one distinct value at a
             // time (~30 per warp here) and eight warps queue for it per scheduler — it was the kernel's bottleneck
@@ -293,19 +327,20 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
                 const unsigned m = __ballot_sync(0xffffffffu, bit);
                 peers &= bit ? m : ~m;
             }
-            rank[r] = 0;
-            if (valid) {
-                const int leader = __ffs(peers) - 1;
-                uint32_t prev = 0;
-                if (lane == leader) {
-                    prev = warp_count[warp][d];
-                    warp_count[warp][d] = prev + __popc(peers);
-                }
-                prev = __shfl_sync(peers, prev, leader);
-                rank[r] = prev + __popc(peers & ((1u << lane) - 1));
-            }
+            // The group's first lane bumps the warp's counter with ONE shared-memory atomic.  Its result is not used
+            // before the loop ends, so the eight items' ballots and atomics pipeline (a load -> store -> shuffle chain
+            // per item was a fifth of the stall samples).  Only this warp touches warp_count[warp]; __syncwarp orders
+            // the items' updates of one counter.
+            const uint32_t leader = uint32_t(__ffs(peers) - 1) & 31u;
+            prev[r] = 0;
+            if (valid && uint32_t(lane) == leader) prev[r] = atomicAdd(&warp_count[warp][d], uint32_t(__popc(peers)));
+            info[r] = uint32_t(__popc(peers & ((1u << lane) - 1))) | (leader << 8);
             __syncwarp();
         }
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r)  // rank inside the warp's part of the tile: group base + position in the group
+            info[r] = __shfl_sync(0xffffffffu, prev[r], int(info[r] >> 8)) + (info[r] & 0xffu);
+        cp_async_wait<1>();  // this thread's pieces of vals(tile); keys(tile + 1) may still be in flight
         __syncthreads();
         {  // per-digit exclusive prefix over the warps of this tile
             const int d = threadIdx.x;
@@ -328,16 +363,16 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
         // straight from the ranking registers issued 4-byte writes to ~32 different sectors per warp instruction.
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) {
-            const uint64_t i = tile_begin + uint64_t(warp) * 32 * kSortItems + r * 32 + lane;
-            if (i < n) {
+            const uint32_t e = warp * 32 * kSortItems + r * 32 + lane;
+            if (e < tile_valid) {
                 const uint32_t dd = (key[r] >> shift) & (kRadix - 1);
-                const uint32_t local = tile_start[dd] + warp_count[warp][dd] + rank[r];
+                const uint32_t local = tile_start[dd] + warp_count[warp][dd] + info[r];
                 s_key[local] = key[r];
-                s_val[local] = val[r];
+                s_val[local] = IOTA ? tile_begin + e : (RT_SORT_PREFETCH ? s_in_val[e] : __ldcs(vals_in + tile_begin + e));
             }
         }
         __syncthreads();
-        const uint32_t tile_valid = uint32_t(min(uint64_t(kSortTile), uint64_t(n) - tile_begin));
+        fetch(vals_in, s_in_val, tile + 1, !IOTA);  // every thread has taken its values of this tile
 #pragma unroll
         for (int r = 0; r < kSortItems; ++r) {
             const uint32_t idx = r * kSortThreads + threadIdx.x;
@@ -353,6 +388,7 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint32_t *
         base[threadIdx.x] += tile_count[threadIdx.x];
         __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------ Karras hierarchy
@@ -376,6 +412,9 @@ struct KarrasDev {
 constexpr int kFitBlock = RT_FIT_BLOCK;
 #ifndef RT_FIT_LOCAL
 #define RT_FIT_LOCAL 1  // 0: the global-atomic k_fit for every level (A/B measurements)
+#endif
+#ifndef RT_LBVH_FUSED
+#define RT_LBVH_FUSED 1  // 0: k_hierarchy + k_fit_local + k_fit_exits also for PREFER_FAST_BUILD (A/B measurements)
 #endif
 __global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, uint32_t n, rt_hierarchy_node *nodes, uint8_t *local) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -420,6 +459,20 @@ __global__ void __launch_bounds__(kThreads) k_hierarchy(const uint32_t *codes, u
 }
 
 // ------------------------------------------------------------------------------------------ rearrange
+#ifndef RT_GATHER_L2_HINT
+#define RT_GATHER_L2_HINT 0  // 64: ld.global.L2::64B for the random 48-byte record gather (A/B: DRAM read per record)
+#endif
+#if RT_GATHER_L2_HINT
+__device__ __forceinline__ uint4 ld_gather16(const uint4 *p) {
+    uint4 v;
+#if RT_GATHER_L2_HINT == 64
+    asm volatile("ld.global.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
+    asm volatile("ld.global.cs.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
+    return v;
+}
+#endif
 // FL/RearrangeTriangles.hlsl:18-36: out[dst] = in[perm[dst]]; also emits the packed 48-byte triangle.
 __global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_packed_tri *recs, const uint32_t *perm, uint32_t n,
                                                              rt_primitive *out_prims, rt_primitive_meta *out_meta, rt_packed_tri *packed) {
@@ -433,7 +486,11 @@ __global__ void __launch_bounds__(kThreads) k_rearrange_tris(const rt_packed_tri
         const uint32_t src = perm[b0 + threadIdx.x];
         const uint4 *q = reinterpret_cast<const uint4 *>(recs + src);
         // each record is read exactly once
+#if RT_GATHER_L2_HINT
+        s_rec[3 * threadIdx.x] = ld_gather16(q), s_rec[3 * threadIdx.x + 1] = ld_gather16(q + 1), s_rec[3 * threadIdx.x + 2] = ld_gather16(q + 2);
+#else
         s_rec[3 * threadIdx.x] = __ldcs(q), s_rec[3 * threadIdx.x + 1] = __ldcs(q + 1), s_rec[3 * threadIdx.x + 2] = __ldcs(q + 2);
+#endif
     }
     __syncthreads();
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_rec);  // 12 words per element
@@ -801,6 +858,16 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
             if (threadIdx.x == 0) s_qn[cur] = 0;
             __syncwarp();
         }
+    } else {
+        // ... while the other warps write the leaf nodes {center, slot | flags}, {halfDim, 1}, which no round touches
+        // (a third of this kernel's stall samples were warps waiting at the barrier below for warp 0's tail)
+        float4 *dst = reinterpret_cast<float4 *>(nodes + nInternal + b0);
+        for (uint32_t g = threadIdx.x - 32; g < 2 * cntLeaf; g += kFitBlock - 32) {
+            const uint32_t e = g >> 1;
+            const float *bx = s_box[e];
+            if (g & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(1u));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float((b0 + e) | RT_NODE_LEAF_FLAG | (s_proc[e] ? RT_NODE_PROCEDURAL_FLAG : 0u)));
+        }
     }
     __syncthreads();
     // Write-out.  Everything this block fitted is described by shared memory (boxes, subtree sizes, hierarchy records),
@@ -808,15 +875,6 @@ __global__ void __launch_bounds__(kFitBlock) k_fit_local(uint32_t n, const rt_hi
     // none.  (One thread storing its own node's 32 + 64 bytes touched 32 sectors per warp instruction.)
     const uint32_t en = s_en;
     if (threadIdx.x == 0 && en) s_base = atomicAdd(&counters[nInternal], en);  // counters[n-1] is no node's counter
-    {   // leaves: {center, slot | flags}, {halfDim, 1}
-        float4 *dst = reinterpret_cast<float4 *>(nodes + nInternal + b0);
-        for (uint32_t g = threadIdx.x; g < 2 * cntLeaf; g += kFitBlock) {
-            const uint32_t e = g >> 1;
-            const float *bx = s_box[e];
-            if (g & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(1u));
-            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float((b0 + e) | RT_NODE_LEAF_FLAG | (s_proc[e] ? RT_NODE_PROCEDURAL_FLAG : 0u)));
-        }
-    }
     // Child order of a fitted node: smaller subtree on the left; ties keep the Karras order.  Applied once, in place, to
     // the shared copy of the hierarchy records, so that the write-out loops below (which visit a node once per 16-byte
     // store) just read {left, right}.
@@ -950,6 +1008,312 @@ __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hie
         if (parent == 0) return;
         count += other;
         node = parent;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ hierarchy + fit in one pass
+// PREFER_FAST_BUILD (no treelet pass, no update caches): FL/BuildBVHSplits.hlsli:35-143 and FL/ComputeAABBs.hlsli:69-175
+// as ONE bottom-up sweep.  The reference's hierarchy is the binary radix tree of the sorted keys under its delta
+// (common prefix of the Morton codes, ties by `clz(i ^ j) + 31`); that tree is unique, and it can be grown from the leaves
+// (Apetrei 2014): a finished node covering the sorted slots [lo, hi] is the LEFT child of the node that splits at hi when
+// delta(hi, hi+1) > delta(lo-1, lo) — it shares the longer prefix with its right neighbour — and otherwise the RIGHT child
+// of the node that splits at lo-1 (delta = -1 outside [0, n), so the range [0, n-1] is the root; the two deltas are never
+// equal for distinct keys).  Karras' numbering follows from the same decision: a left child is internal node `hi`, a right
+// child internal node `lo`, the root node 0 (BuildBVHSplits.hlsli:128-141: children of a split at s are s and s+1).
+// So there is no search (k_hierarchy runs ~20 divergent binary-search steps per node), no hierarchy array and no memset
+// of it.  Subtree size = hi - lo + 1.  The block structure is k_fit_local's: a block owns kFitBlock sorted slots, meets
+// its children in shared memory at the SPLIT position (both neighbours of a split inside the block), fits round by
+// round, writes reference nodes, wide nodes and 4-wide nodes once and coalesced.  Nodes whose parent's split is on a
+// block boundary, or whose sibling reaches out of the block, leave through an exit list and finish in k_lbvh_exits.
+__device__ __forceinline__ int lbvh_delta(const uint32_t *codes, uint32_t n, uint32_t i) {  // delta(i, i+1); i = 0xffffffff is "-1"
+    if (i >= n - 1) return -1;
+    const uint32_t a = __ldg(codes + i), b = __ldg(codes + i + 1);
+    return a != b ? __clz(int(a ^ b)) : __clz(int(i ^ (i + 1))) + 31;
+}
+
+constexpr uint32_t kNoKid = 0xffffffffu;
+__global__ void __launch_bounds__(kFitBlock) k_lbvh_fit(uint32_t n, const uint32_t *codes, rt_aabb_node *nodes,
+                                                        const rt_packed_tri *packed, rt_wide_node *wide, rt_wide4_node *wide4,
+                                                        rt_ext_header *ext, uint32_t *exit_count, uint32_t *exit_nodes, uint32_t *exit_lo,
+                                                        uint32_t *exit_hi) {
+    constexpr int B = kFitBlock;
+    // shared index of a node: leaf -> slot - b0 in [0, B); internal -> B + id - b0 in [B, 2B)
+    extern __shared__ __align__(16) uint8_t s_dyn[];  // kFitLocalDynSmem bytes: the boxes and the 4-wide child lists
+    float(*s_box)[6] = reinterpret_cast<float(*)[6]>(s_dyn);
+    uint32_t(*s_w4)[4] = reinterpret_cast<uint32_t(*)[4]>(s_dyn + sizeof(float) * 6 * 2 * B);
+    __shared__ uint32_t s_kid[2][B];     // by split - b0: the node that arrived from the left / from the right
+    __shared__ uint16_t s_bound[2][B];   // by split - b0: lo - b0 of the left arrival / hi - b0 of the right arrival
+    __shared__ uint32_t s_arrive[B];     // by split - b0: arrivals
+    __shared__ uint32_t s_left[B], s_right[B];  // by id - b0: children of a node fitted here, smaller subtree first
+    __shared__ uint32_t s_range[B];      // by id - b0: (lo - b0) | (hi - b0) << 16
+    __shared__ uint8_t s_fitted[B], s_proc[B];
+    __shared__ int8_t s_delta[B + 1];    // s_delta[k] = delta(b0 - 1 + k, b0 + k)
+    __shared__ uint16_t s_queue[2][B];   // ready splits (minus b0) of this / the next round
+    __shared__ uint32_t s_exit[B];       // finished nodes that continue through global memory
+    __shared__ uint32_t s_qn[2], s_en, s_base;
+    const uint32_t b0 = blockIdx.x * B;
+    const uint32_t nInternal = n - 1;
+    const uint32_t slot = b0 + threadIdx.x;
+    const uint32_t cntLeaf = min(uint32_t(B), n - b0);
+    const uint32_t cntInt = b0 < nInternal ? min(uint32_t(B), nInternal - b0) : 0u;
+    s_arrive[threadIdx.x] = 0;
+    s_kid[0][threadIdx.x] = kNoKid, s_kid[1][threadIdx.x] = kNoKid;
+    s_fitted[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_qn[threadIdx.x] = 0;
+    if (threadIdx.x == 2) s_en = 0;
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    if (slot < n) {
+        const float4 *q = reinterpret_cast<const float4 *>(packed + slot);
+        q0 = q[0], q1 = q[1], q2 = q[2];
+        s_delta[threadIdx.x + 1] = int8_t(lbvh_delta(codes, n, slot));
+        if (threadIdx.x == 0) s_delta[0] = int8_t(lbvh_delta(codes, n, slot - 1));  // slot 0: index "-1"
+    }
+    auto shared_index = [&](uint32_t node) { return node >= nInternal ? node - nInternal - b0 : B + node - b0; };
+    auto load_box = [&](uint32_t si) {
+        Box b;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) b.c[k] = s_box[si][k], b.h[k] = s_box[si][3 + k];
+        return b;
+    };
+    // a finished node [lo, hi] (global slots, inside this block) reports to the split it hangs on
+    auto report = [&](uint32_t node, uint32_t lo, uint32_t hi, int next) {
+        const bool goRight = s_delta[hi - b0 + 1] > s_delta[lo - b0];
+        const uint32_t g = (goRight ? hi : lo - 1) - b0;  // lo - 1 - b0 wraps for a split left of the block
+        if (g < uint32_t(B - 1)) {                        // slots g and g + 1 both belong to this block
+            const int side = goRight ? 0 : 1;
+            s_kid[side][g] = node;
+            s_bound[side][g] = uint16_t((goRight ? lo : hi) - b0);
+            if (atomicAdd(&s_arrive[g], 1u) == 1u) s_queue[next][atomicAdd(&s_qn[next], 1u)] = uint16_t(g);
+        } else {
+            s_exit[atomicAdd(&s_en, 1u)] = node;
+        }
+    };
+    if (slot < n) {
+        const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+        float mn[3], mx[3];
+        const bool procedural = (__float_as_uint(q2.w) & RT_PACKED_PROCEDURAL) != 0;
+        if (procedural) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) mn[k] = v[k], mx[k] = v[3 + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = fminf(fminf(v[k], v[3 + k]), v[6 + k]);
+                mx[k] = fmaxf(fmaxf(v[k], v[3 + k]), v[6 + k]);
+                mn[k] = fminf(mn[k], mx[k] - 0.001f);  // AABB_Min_Padding
+            }
+        }
+        const Box box = aabb_to_box(mn, mx);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s_box[threadIdx.x][k] = box.c[k], s_box[threadIdx.x][3 + k] = box.h[k];
+        s_proc[threadIdx.x] = procedural ? 1 : 0;
+        if (n == 1) {
+            ext->root_center[0] = box.c[0], ext->root_center[1] = box.c[1], ext->root_center[2] = box.c[2];
+            ext->root_half[0] = box.h[0], ext->root_half[1] = box.h[1], ext->root_half[2] = box.h[2];
+        }
+    }
+    __syncthreads();  // s_delta, the cleared slots
+    if (slot < n && n > 1) report(nInternal + slot, slot, slot, 0);
+    __syncthreads();
+    // One ready split: both children are in shared memory (GetBoxFromChildBoxes, FL/RayTracingHelper.hlsli:297-307).
+    auto fit_ready = [&](uint32_t g, int next) {
+        const uint32_t lo = b0 + s_bound[0][g], hi = b0 + s_bound[1][g], split = b0 + g;
+        uint32_t a = s_kid[0][g], b = s_kid[1][g];
+        if (hi - split < split - lo + 1) {  // smaller subtree on the left; ties keep the Karras order
+            const uint32_t t = a; a = b; b = t;
+        }
+        const Box bl = load_box(shared_index(a)), br = load_box(shared_index(b));
+        float mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(bl.c[k] - bl.h[k], br.c[k] - br.h[k]);
+            mx[k] = fmaxf(bl.c[k] + bl.h[k], br.c[k] + br.h[k]);
+        }
+        const Box box = aabb_to_box(mn, mx);
+        const bool root = lo == 0 && hi == n - 1;
+        const uint32_t id = root ? 0u : (s_delta[hi - b0 + 1] > s_delta[lo - b0] ? hi : lo);
+        const uint32_t e = id - b0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s_box[B + e][k] = box.c[k], s_box[B + e][3 + k] = box.h[k];
+        s_left[e] = a, s_right[e] = b;
+        s_range[e] = (lo - b0) | ((hi - b0) << 16);
+        s_fitted[e] = 1;
+        if (!root) report(id, lo, hi, next);
+    };
+    // Rounds.  The number of ready splits never grows, so once a round fits in a warp the rest is run by warp 0 alone.
+    int cur = 0;
+    for (; s_qn[cur] > 32; cur ^= 1) {  // block-uniform: s_qn[cur] is stable between the two barriers
+        if (threadIdx.x < s_qn[cur]) fit_ready(s_queue[cur][threadIdx.x], cur ^ 1);
+        __syncthreads();
+        if (threadIdx.x == 0) s_qn[cur] = 0;
+        __syncthreads();
+    }
+    __syncthreads();  // every warp has read the exit condition before warp 0 starts rewriting the queue counters
+    if (threadIdx.x < 32) {
+        for (;; cur ^= 1) {
+            const uint32_t q = s_qn[cur];
+            if (q == 0) break;
+            if (threadIdx.x < q) fit_ready(s_queue[cur][threadIdx.x], cur ^ 1);
+            __syncwarp();
+            if (threadIdx.x == 0) s_qn[cur] = 0;
+            __syncwarp();
+        }
+    } else {
+        // ... while the other warps write the leaf nodes {center, slot | flags}, {halfDim, 1}, which no round touches
+        // (in k_fit_local a third of the stall samples are warps waiting at the barrier below for this tail)
+        float4 *dst = reinterpret_cast<float4 *>(nodes + nInternal + b0);
+        for (uint32_t g = threadIdx.x - 32; g < 2 * cntLeaf; g += B - 32) {
+            const uint32_t e = g >> 1;
+            const float *bx = s_box[e];
+            if (g & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(1u));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float((b0 + e) | RT_NODE_LEAF_FLAG | (s_proc[e] ? RT_NODE_PROCEDURAL_FLAG : 0u)));
+        }
+    }
+    __syncthreads();
+    // a node still waiting at a split is one whose sibling reaches out of the block
+    if (s_arrive[threadIdx.x] == 1u) {
+        const uint32_t l = s_kid[0][threadIdx.x];
+        s_exit[atomicAdd(&s_en, 1u)] = l != kNoKid ? l : s_kid[1][threadIdx.x];
+    }
+    __syncthreads();
+    // Write-out: everything this block fitted leaves as contiguous runs of 16-byte stores.
+    const uint32_t en = s_en;
+    auto to_ref = [&](uint32_t node) { return node >= nInternal ? (RT_NODE_LEAF_FLAG | (node - nInternal)) : node; };
+    {   // internal reference nodes: {center, left}, {halfDim, right}
+        float4 *dst = reinterpret_cast<float4 *>(nodes + b0);
+        for (uint32_t g = threadIdx.x; g < 2 * cntInt; g += B) {
+            const uint32_t e = g >> 1;
+            if (!s_fitted[e]) continue;
+            const float *bx = s_box[B + e];
+            if (g & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(s_right[e]));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float(s_left[e] & 0x00ffffffu));
+        }
+    }
+    {   // wide nodes: both child boxes and child references
+        float4 *dst = reinterpret_cast<float4 *>(wide + b0);
+        for (uint32_t g = threadIdx.x; g < 4 * cntInt; g += B) {
+            const uint32_t e = g >> 2, part = g & 3;
+            if (!s_fitted[e]) continue;
+            const uint32_t l = s_left[e], r = s_right[e];
+            const float *bx = s_box[shared_index(part < 2 ? l : r)];
+            const uint32_t w = part == 0 ? to_ref(l) : (part == 1 ? to_ref(r) : 0u);
+            if (part & 1) dst[g] = make_float4(bx[3], bx[4], bx[5], __uint_as_float(w));
+            else dst[g] = make_float4(bx[0], bx[1], bx[2], __uint_as_float(w));
+        }
+    }
+    // 4-wide traversal nodes (k_collapse4's rule: open, twice, the internal child with the largest surface area): the
+    // child lists first ...
+    if (threadIdx.x < cntInt && s_fitted[threadIdx.x]) {
+        uint32_t ref[4] = {RT_WIDE4_EMPTY, RT_WIDE4_EMPTY, RT_WIDE4_EMPTY, RT_WIDE4_EMPTY}, si[4] = {0, 0, 0, 0};
+        int cnt = 2;
+        {
+            const uint32_t l = s_left[threadIdx.x], r = s_right[threadIdx.x];
+            ref[0] = to_ref(l), ref[1] = to_ref(r), si[0] = shared_index(l), si[1] = shared_index(r);
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            int best = -1;
+            float bestArea = -1.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < cnt && !(ref[k] & RT_NODE_LEAF_FLAG)) {
+                    const float *h = s_box[si[k]] + 3;
+                    const float a = h[0] * h[1] + h[1] * h[2] + h[2] * h[0];
+                    if (a > bestArea) bestArea = a, best = k;
+                }
+            }
+            if (best < 0) break;
+            uint32_t opened = ref[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (k == best) opened = ref[k];
+            const uint32_t l = s_left[opened - b0], r = s_right[opened - b0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k == best) ref[k] = to_ref(l), si[k] = shared_index(l);
+                if (k == cnt) ref[k] = to_ref(r), si[k] = shared_index(r);
+            }
+            cnt++;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_w4[threadIdx.x][k] = ref[k];
+    }
+    __syncthreads();
+    {   // ... then the 128-byte nodes as one contiguous run
+        float4 *dst = reinterpret_cast<float4 *>(wide4 + b0);
+        for (uint32_t g = threadIdx.x; g < 8 * cntInt; g += B) {
+            const uint32_t e = g >> 3, part = g & 7;
+            if (!s_fitted[e]) continue;
+            const uint32_t ref = s_w4[e][part >> 1];
+            if (ref == RT_WIDE4_EMPTY) {
+                dst[g] = (part & 1) ? make_float4(-1.0f, -1.0f, -1.0f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RT_WIDE4_EMPTY));
+            } else {
+                const float *bx = s_box[(ref & RT_NODE_LEAF_FLAG) ? (ref & 0x00ffffffu) - b0 : B + ref - b0];
+                dst[g] = (part & 1) ? make_float4(bx[3], bx[4], bx[5], 0.0f) : make_float4(bx[0], bx[1], bx[2], __uint_as_float(ref));
+            }
+        }
+    }
+    if (b0 == 0 && nInternal > 0 && threadIdx.x == 0 && s_fitted[0]) {  // node 0 is the root: the whole tree was local
+        const float *bx = s_box[B];
+        ext->root_center[0] = bx[0], ext->root_center[1] = bx[1], ext->root_center[2] = bx[2];
+        ext->root_half[0] = bx[3], ext->root_half[1] = bx[4], ext->root_half[2] = bx[5];
+    }
+    // the nodes that leave the block continue in k_lbvh_exits: {node, lo, hi}
+    if (threadIdx.x == 0 && en) s_base = atomicAdd(exit_count, en);
+    __syncthreads();
+    if (threadIdx.x < en) {
+        const uint32_t node = s_exit[threadIdx.x];
+        uint32_t lo, hi;
+        if (node >= nInternal) {
+            lo = hi = node - nInternal;
+        } else {
+            const uint32_t rg = s_range[node - b0];
+            lo = b0 + (rg & 0xffffu), hi = b0 + (rg >> 16);
+        }
+        exit_nodes[s_base + threadIdx.x] = node;
+        exit_lo[s_base + threadIdx.x] = lo;
+        exit_hi[s_base + threadIdx.x] = hi;
+    }
+}
+
+// Second half of k_lbvh_fit: one thread per exit-list entry climbs through global memory.  A node [lo, hi] meets its
+// sibling at g_slot[split]: one 64-bit exchange carries {node + 1, far end of the range}; the second arrival fits the
+// parent (its Karras index and its own parent's split follow from the two deltas at the ends of the merged range).
+// Kept out of k_lbvh_fit on purpose: with the climb inside, a block stays resident until its longest chain of
+// dependent atomics ends (tens of microseconds against ~10 for the block's own work) and the kernel took 1.63 ms
+// instead of 0.7 + 0.2 (10 M triangles).
+__global__ void __launch_bounds__(kThreads) k_lbvh_exits(uint32_t n, const uint32_t *codes, unsigned long long *g_slot, rt_aabb_node *nodes,
+                                                         rt_wide_node *wide, rt_wide4_node *wide4, rt_ext_header *ext,
+                                                         const uint32_t *exit_count, const uint32_t *exit_nodes, const uint32_t *exit_lo,
+                                                         const uint32_t *exit_hi) {
+    const uint32_t nInternal = n - 1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= __ldcg(exit_count)) return;
+    uint32_t node = exit_nodes[i], lo = exit_lo[i], hi = exit_hi[i];
+    Box box = load_node_box(nodes, node);
+    bool goRight = lbvh_delta(codes, n, hi) > lbvh_delta(codes, n, lo - 1);
+    while (true) {
+        const uint32_t split = goRight ? hi : lo - 1;
+        const unsigned long long mine = (static_cast<unsigned long long>(goRight ? lo : hi) << 32) | (node + 1u);
+        __threadfence();
+        const unsigned long long other = atomicExch(g_slot + split, mine);
+        if (other == 0ull) return;  // first to arrive: the sibling will fit the parent
+        __threadfence();
+        const uint32_t sib = uint32_t(other) - 1u, far = uint32_t(other >> 32);
+        const Box sb = load_node_box(nodes, sib);
+        const uint32_t nlo = goRight ? lo : far, nhi = goRight ? far : hi;
+        const bool root = nlo == 0 && nhi == n - 1;
+        bool up = false;
+        uint32_t id = 0;
+        if (!root) {
+            up = lbvh_delta(codes, n, nhi) > lbvh_delta(codes, n, nlo - 1);
+            id = up ? nhi : nlo;
+        }
+        // Karras order: the child on the lower slots is "left"; fit_merge_store applies the size rule
+        fit_merge_store<true>(id, goRight ? node : sib, goRight ? sib : node, split - nlo + 1, nhi - split, goRight ? box : sb,
+                              goRight ? sb : box, nInternal, nodes, wide, ext, box, wide4);
+        if (root) return;
+        node = id, lo = nlo, hi = nhi, goRight = up;
     }
 }
 
@@ -1392,6 +1756,8 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
     uint32_t *parents = reinterpret_cast<uint32_t *>(result + R.parents);
     // one byte per internal node in the sort's dead ping-pong buffer (the sorted pairs end up in keysC / valsC)
     uint8_t *fit_local = (!top && RT_FIT_LOCAL) ? scratch + L.keysB : nullptr;
+    // full bottom-level build without treelet passes or update caches: hierarchy emission and fit are one kernel (k_lbvh_fit)
+    const bool fused = !top && !update && RT_FIT_LOCAL && RT_LBVH_FUSED && treelet_passes(flags) == 0 && !allows_update(flags);
     if (update) {
         k_invert_cache<<<grid, kThreads, 0, st>>>(sort_cache, n, perm);
         ctx->launches++;
@@ -1407,8 +1773,12 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
         int rc = sort_pairs(ctx, scratch, L, n);
         if (rc) return rc;
         const uint32_t *sorted_codes = reinterpret_cast<uint32_t *>(scratch + L.keysC);
-        RT_CUDA(cudaMemsetAsync(hier, 0, 12ull * (2ull * n - 1), st));
-        if (n > 1) {
+        if (fused) {
+            if (n > 1) RT_CUDA(cudaMemsetAsync(hier, 0, 8ull * (n - 1), st));  // g_slot: one 64-bit meeting word per split
+        } else {
+            RT_CUDA(cudaMemsetAsync(hier, 0, 12ull * (2ull * n - 1), st));
+        }
+        if (n > 1 && !fused) {
             k_hierarchy<<<rt_div_up(n - 1, kThreads), kThreads, 0, st>>>(sorted_codes, n, hier, fit_local);
             ctx->launches++;
         }
@@ -1448,9 +1818,25 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
             ctx->launches++;
         }
     }
-    RT_CUDA(cudaMemsetAsync(counters, 0, 4ull * n, st));
+    if (!fused) RT_CUDA(cudaMemsetAsync(counters, 0, 4ull * n, st));
     bool fitted_locally = false;
-    if (top) {
+    if (fused) {
+        RT_CUDA(cudaFuncSetAttribute(k_lbvh_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFitLocalDynSmem)));  // per device
+        // exit list {node, lo, hi} in buffers this path leaves unused (the sort's ping-pong pair, the arrival counters);
+        // its length in the spare word behind the encoded scene AABB (zeroed by k_init_aabb)
+        uint32_t *exit_count = reinterpret_cast<uint32_t *>(scratch + L.aabb_enc) + 7;
+        uint32_t *exit_nodes = reinterpret_cast<uint32_t *>(scratch + L.valsB), *exit_lo = reinterpret_cast<uint32_t *>(scratch + L.keysB);
+        const uint32_t *codes_sorted = reinterpret_cast<uint32_t *>(scratch + L.keysC);
+        unsigned long long *g_slot = reinterpret_cast<unsigned long long *>(hier);
+        rt_wide4_node *wide4 = reinterpret_cast<rt_wide4_node *>(result + R.wide4);
+        k_lbvh_fit<<<rt_div_up(n, kFitBlock), kFitBlock, kFitLocalDynSmem, st>>>(n, codes_sorted, nodes, packed, wide, wide4, ext,
+                                                                                 exit_count, exit_nodes, exit_lo, counters);
+        if (n > kFitBlock) {  // a build of one block leaves no exits
+            k_lbvh_exits<<<grid, kThreads, 0, st>>>(n, codes_sorted, g_slot, nodes, wide, wide4, ext, exit_count, exit_nodes, exit_lo, counters);
+            ctx->launches++;
+        }
+        fitted_locally = true;
+    } else if (top) {
         if (update)
             k_fit<true, true><<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, nullptr, boxes, perm, wide, ext, parents);
         else

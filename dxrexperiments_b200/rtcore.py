@@ -483,6 +483,17 @@ class Accel:
         nbytes = int(lib.rt_blob_bytes(self.n, 1 if self.top else 0))
         return self.result.download(np.uint8, nbytes)
 
+    def traversal_section(self) -> dict:
+        """The arrays the trace kernels read — BVH2 wide nodes (64 B), packed leaves (48 B triangles / 96 B instances),
+        4-wide nodes (128 B) — located through the 128-byte rt_ext_header behind the blob (csrc/common.cuh)."""
+        ext = (int(lib.rt_blob_bytes(self.n, 1 if self.top else 0)) + 63) // 64 * 64
+        hdr = self.result.download(np.uint64, 16, offset=ext)
+        off_wide, off_leaf, off_wide4 = int(hdr[2]), int(hdr[3]), int(hdr[8])
+        n_int = max(self.n - 1, 0)
+        return {"wide": self.result.download(np.uint32, 16 * n_int, offset=off_wide).reshape(-1, 16),
+                "leaf": self.result.download(np.uint32, (24 if self.top else 12) * self.n, offset=off_leaf),
+                "wide4": self.result.download(np.uint32, 32 * n_int, offset=off_wide4).reshape(-1, 32)}
+
     def scratch_layout(self) -> ScratchLayout:
         L = ScratchLayout()
         check(lib.rt_build_scratch_layout(self.n, 1 if self.top else 0, C.byref(L)))

@@ -49,7 +49,20 @@ def test_blas_stages_and_blob_bit_exact(name, variant, ctx, orc):
     np.testing.assert_array_equal(acc.stage("morton_codes"), ref.morton())          # criterion 1
     np.testing.assert_array_equal(acc.stage("sorted_codes"), ref.sorted_morton())
     np.testing.assert_array_equal(acc.stage("sorted_indices"), ref.perm())           # criterion 1
-    if ref.n > 1:
+    if ref.n > 1 and variant == "fast_build":
+        # PREFER_FAST_BUILD emits the hierarchy and fits the boxes in ONE bottom-up kernel (k_lbvh_fit): there is no
+        # hierarchy array; the child links of the blob carry the whole topology (parent links follow from them)
+        h_ref, nodes = ref.hierarchy(), T.parse_blas_blob(acc.blob())["nodes"]
+        n_int = ref.n - 1
+        left = np.where(nodes["flags"][:n_int] & 0x80000000, 0, nodes["flags"][:n_int] & 0x00FFFFFF)
+        parent = np.full(2 * ref.n - 1, 0xFFFFFFFF, np.uint32)
+        parent[nodes["right"][:n_int]] = np.arange(n_int, dtype=np.uint32)
+        parent[left] = np.arange(n_int, dtype=np.uint32)
+        np.testing.assert_array_equal(parent[1:], h_ref["parent"][1:] & 0x7FFFFFFF)
+        kids_gpu = np.sort(np.stack([left, nodes["right"][:n_int]]), axis=0)
+        kids_ref = np.sort(np.stack([h_ref["left"][:n_int], h_ref["right"][:n_int]]), axis=0)
+        np.testing.assert_array_equal(kids_gpu, kids_ref)
+    elif ref.n > 1:
         h_gpu, h_ref = acc.stage("hierarchy"), ref.hierarchy()
         np.testing.assert_array_equal(h_gpu["left"][: ref.n - 1], h_ref["left"][: ref.n - 1])
         np.testing.assert_array_equal(h_gpu["right"][: ref.n - 1], h_ref["right"][: ref.n - 1])
@@ -143,6 +156,24 @@ def test_blob_bit_exact_around_fit_block_boundaries(n, ctx, orc):
         ref = orc.Blas.from_mesh(mesh, build_flags=flags)
         acc = ctx.build_blas_from_mesh(mesh, build_flags=flags)
         np.testing.assert_array_equal(acc.blob(), ref.blob())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 513, 4097, 65537, 300001])
+def test_fused_fast_build_equals_staged_build(n, ctx):
+    """PREFER_FAST_BUILD runs k_lbvh_fit (hierarchy emission + fit in one bottom-up kernel); the same flags with
+    ALLOW_UPDATE run the staged chain (k_hierarchy, k_fit_local, k_fit_exits).  Same tree, same bytes: the reference
+    blob AND the traversal section (BVH2 wide nodes, packed triangles, 4-wide nodes)."""
+    mesh = scenes.triangle_soup(n, seed=4000 + n, extent=30.0, edge=1.0)
+    if n == 4097:
+        mesh.vertices["position"][: 3 * 2000] = np.tile(mesh.vertices["position"][:3], (2000, 1))  # 2000 equal keys across block boundaries
+    fused = ctx.build_blas_from_mesh(mesh, build_flags=T.BUILD_FLAG_PREFER_FAST_BUILD)
+    staged = ctx.build_blas_from_mesh(mesh, build_flags=T.BUILD_FLAG_PREFER_FAST_BUILD | T.BUILD_FLAG_ALLOW_UPDATE)
+    ctx.sync()
+    np.testing.assert_array_equal(fused.blob(), staged.blob())
+    f, s = fused.traversal_section(), staged.traversal_section()
+    for k in ("wide", "leaf", "wide4"):
+        np.testing.assert_array_equal(f[k], s[k], err_msg=k)
+    ctx.status()
 
 
 @pytest.mark.parametrize("kind", ["identical", "two_clusters", "line"])

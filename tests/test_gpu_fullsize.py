@@ -201,6 +201,32 @@ def test_c4_build_1m_bit_exact_and_10m_properties(ctx, rt, orc):
     assert (root_lo <= pos.min(0) + 1e-3).all() and (root_hi >= pos.max(0) - 1e-3).all()
 
 
+def test_fast_build_10m_fused_equals_staged(ctx):
+    """bench.py's build workload (10 M triangles, PREFER_FAST_BUILD = k_lbvh_fit, hierarchy + fit in one kernel) against
+    the staged chain (the same flags with ALLOW_UPDATE): identical blob and traversal section, and the tree is a tree."""
+    n = 10_000_000
+    soup = scenes.triangle_soup(n)
+    fused = ctx.build_blas_from_mesh(soup, build_flags=T.BUILD_FLAG_PREFER_FAST_BUILD)
+    ctx.sync()
+    ctx.status()
+    fb = fused.blob()
+    ft = fused.traversal_section()
+    del fused
+    staged = ctx.build_blas_from_mesh(soup, build_flags=T.BUILD_FLAG_PREFER_FAST_BUILD | T.BUILD_FLAG_ALLOW_UPDATE)
+    ctx.sync()
+    assert np.array_equal(fb, staged.blob())
+    st = staged.traversal_section()
+    for k in ("wide", "leaf", "wide4"):
+        assert np.array_equal(ft[k], st[k]), k
+    nodes = fb[16:16 + 32 * (2 * n - 1)].view(T.NODE_DTYPE)
+    # every node but the root is referenced exactly once (full-width references of the wide nodes: internal -> id, leaf -> bit 31 | slot)
+    lref, rref = ft["wide"][:, 3], ft["wide"][:, 7]
+    ids = np.concatenate([np.where(r >> 31, (r & 0x7FFFFFFF).astype(np.int64) + (n - 1), r.astype(np.int64)) for r in (lref, rref)])
+    cnt = np.bincount(ids, minlength=2 * n - 1)
+    assert cnt[0] == 0 and (cnt[1:] == 1).all()
+    assert (nodes["flags"][n - 1:] & 0x00FFFFFF == np.arange(n, dtype=np.uint32) & 0x00FFFFFF).all()
+
+
 def test_c5_realtime_1080p_and_denoise(ctx, rt, orc):
     wl = scenes.workload("C5")
     W, H = wl.width, wl.height
