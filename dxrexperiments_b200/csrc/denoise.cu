@@ -47,12 +47,47 @@ __device__ __forceinline__ float4 fetch(const float4 *img, int x, int y, int w, 
     return __ldg(img + size_t(y) * w + x);
 }
 
-__device__ __forceinline__ float range_weight(float sx, float sy, float sz, float cx, float cy, float cz) {
+[[maybe_unused]] __device__ __forceinline__ float range_weight(float sx, float sy, float sz, float cx, float cy, float cz) {
     float dist = ((fabsf(sx - cx) + fabsf(sy - cy)) + fabsf(sz - cz)) * 10.0f;
     return 1.0f - fminf(fmaxf(dist, 0.0f), 1.0f);
 }
 
 __device__ __forceinline__ int hpad(int c) { return c + (c >> 3); }
+
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest operations per issue slot, each lane's result
+// bit-identical to the scalar instruction).  The kernel is issue-bound (ncu: 66 % of the issue slots, DRAM 16 %), so the
+// filter's (texel, output) work is done for two neighbouring outputs per instruction wherever the operation has a packed
+// form; |x| and saturate only exist as scalar operand modifiers and stay scalar.
+#ifndef RT_DENOISE_PACKED
+#define RT_DENOISE_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 // PASS 0 = horizontal (DenoiseCompositorH.hlsl), PASS 1 = vertical + composite (DenoiseCompositorV.hlsl).
 template <int PASS>
@@ -64,8 +99,8 @@ __global__ void __launch_bounds__(kThreadsDn, 3) k_denoise(const __grid_constant
     float *pl = smem + 64;       // planes: in.r in.g in.b joint.r joint.g joint.b
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = A.k;
-    if (threadIdx.x < 64) {  // sW[jj] = weight of tap i = jj - k; zero outside the kernel (those taps are skipped anyway)
-        const int i = int(threadIdx.x) - k;
+    if (threadIdx.x < 64) {  // sW[RT_DENOISE_PACKED + jj] = weight of tap i = jj - k; zero outside the kernel
+        const int i = int(threadIdx.x) - RT_DENOISE_PACKED - k;
         sW[threadIdx.x] = (i >= -k && i <= k) ? A.wts[i + MAX_EXTENT] : 0.0f;
     }
     // ---- stage the tile and the +-k halo along the filter axis
@@ -120,6 +155,56 @@ __global__ void __launch_bounds__(kThreadsDn, 3) k_denoise(const __grid_constant
         // the order i = -k .. k.  The tap weight w[jj - r] lives in ring slot (jj - r) & 7: a slot is written once, when
         // its texel is fetched (r = 0), and read by output r exactly r steps later, so with the jj loop unrolled by 8
         // all slot indices are compile-time constants — one weight fetch per texel instead of one per tap.
+#if RT_DENOISE_PACKED
+        // Outputs r and r + 1 share every instruction that has a packed form.  A tap past an output's last one needs no
+        // test: its weight sW[jj - r] is 0 there, and x + 0 * s is x (s is finite), so such a half-pair is value-neutral.
+        f32x2 cx2[R / 2], cy2[R / 2], cz2[R / 2], ar2[R / 2], ag2[R / 2], ab2[R / 2], aw2[R / 2];
+#pragma unroll
+        for (int h = 0; h < R / 2; ++h) {
+            cx2[h] = pk2(cjx[2 * h], cjx[2 * h + 1]), cy2[h] = pk2(cjy[2 * h], cjy[2 * h + 1]), cz2[h] = pk2(cjz[2 * h], cjz[2 * h + 1]);
+            ar2[h] = ag2[h] = ab2[h] = aw2[h] = pk2(0.0f, 0.0f);
+        }
+        // ring2[p] = {w[jj], w[jj - 1]}: the weights outputs r and r + 1 apply to texel jj + r, fetched as a pair when texel jj
+        // is (the table is stored shifted by one, sW[0] = 0, so that w[-1] reads as 0)
+        f32x2 ring2[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) ring2[p] = pk2(0.0f, 0.0f);  // "before the first tap" reads as weight 0
+        const f32x2 one2 = pk2(1.0f, 1.0f);
+        auto block = [&](const int b, auto firstTag, auto checkTag) {
+            constexpr bool FIRST = decltype(firstTag)::value, CHECK = decltype(checkTag)::value;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int jj = 8 * b + p;
+                const float *q = at(jj - k);
+                const float sx = q[0], sy = q[PLANE], sz = q[2 * PLANE], jx = q[3 * PLANE], jy = q[4 * PLANE], jz = q[5 * PLANE];
+                ring2[p] = pk2(sW[jj + 1], sW[jj]);
+                const f32x2 sx2 = pk2(sx, sx), sy2 = pk2(sy, sy), sz2 = pk2(sz, sz), jx2 = pk2(jx, jx), jy2 = pk2(jy, jy), jz2 = pk2(jz, jz);
+#pragma unroll
+                for (int h = 0; h < R / 2; ++h) {
+                    const int r = 2 * h;
+                    if (FIRST && p < r) continue;              // jj - r < 0: before the first tap of both outputs
+                    if (CHECK && jj - r - 1 > 2 * k) continue;  // past the last tap of both
+                    float dxl, dxh, dyl, dyh, dzl, dzh;
+                    upk2(sub2(jx2, cx2[h]), dxl, dxh), upk2(sub2(jy2, cy2[h]), dyl, dyh), upk2(sub2(jz2, cz2[h]), dzl, dzh);
+                    const float ml = __saturatef(((fabsf(dxl) + fabsf(dyl)) + fabsf(dzl)) * 10.0f);
+                    const float mh = __saturatef(((fabsf(dxh) + fabsf(dyh)) + fabsf(dzh)) * 10.0f);
+                    const f32x2 bw = mul2(ring2[(p - r) & 7], sub2(one2, pk2(ml, mh)));
+                    ar2[h] = fma2(sx2, bw, ar2[h]), ag2[h] = fma2(sy2, bw, ag2[h]), ab2[h] = fma2(sz2, bw, ab2[h]);
+                    aw2[h] = add2(aw2[h], bw);
+                }
+            }
+        };
+        const int nblocks = (2 * k + R + 7) / 8, nfull = (2 * k + 1) / 8;  // blocks b < nfull have jj <= 2k for every p
+        block(0, std::true_type{}, std::integral_constant<bool, true>{});
+        int b = 1;
+        for (; b < nfull; ++b) block(b, std::false_type{}, std::false_type{});
+        for (; b < nblocks; ++b) block(b, std::false_type{}, std::true_type{});
+#pragma unroll
+        for (int h = 0; h < R / 2; ++h) {
+            upk2(ar2[h], ar[2 * h], ar[2 * h + 1]), upk2(ag2[h], ag[2 * h], ag[2 * h + 1]);
+            upk2(ab2[h], ab[2 * h], ab[2 * h + 1]), upk2(aw2[h], aw[2 * h], aw[2 * h + 1]);
+        }
+#else
         float ring[8];
         auto block = [&](const int b, auto firstTag, auto checkTag) {
             constexpr bool FIRST = decltype(firstTag)::value, CHECK = decltype(checkTag)::value;
@@ -144,6 +229,7 @@ __global__ void __launch_bounds__(kThreadsDn, 3) k_denoise(const __grid_constant
         int b = 1;
         for (; b < nfull; ++b) block(b, std::false_type{}, std::false_type{});
         for (; b < nblocks; ++b) block(b, std::false_type{}, std::true_type{});
+#endif
     }
     if (PASS == 0) {
         // results go back through shared memory (the input planes are dead) so that the global stores are coalesced
