@@ -160,6 +160,21 @@ __global__ void __launch_bounds__(kBlock, RT_PRIMARY_MIN_BLOCKS) k_primary(const
     const uint32_t lx = (tile % tilesX) * 8 + (lane & 7), ly = (tile / tilesX) * 4 + (lane >> 3);
     const bool inside = lx < L.rw && ly < L.rh;
     TraceCtr ctr{0, 0, 0, 0};
+#if RT_PRIMARY_PHASES && RT_PRIMARY_WIDE4
+    if (!STATS) {  // warp-synchronous traversal: every lane takes part in the votes, lanes outside the image carry no ray
+        f3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f);
+        if (inside) primary_ray(L.f, L.width, L.height, L.x0 + lx, image_row(L, ly), L.jitterScale, o, d);
+        TraceAccel A = resolve_tlas(tlas, status);
+        TraceHit h;
+        trace_ray4(A, o.x, o.y, o.z, 0.0f, d.x, d.y, d.z, RT_RAY_MAX_T, RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, 0xFF, 0, h, status, inside);
+        if (inside) {
+            const uint32_t p = ly * L.rw + lx;
+            ws.hitA[p] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            ws.hitRec[p] = h.record;
+        }
+        return;
+    }
+#endif
     if (inside) {
         const uint32_t x = L.x0 + lx, y = image_row(L, ly);
         f3 o, d;

@@ -14,7 +14,9 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef RT_STACK_SIZE
 #define RT_STACK_SIZE 64
+#endif
 
 // One 256-bit read-only load (LDG.E.256, new with sm_100): half the load instructions of two 16-byte loads for the
 // 128-byte nodes.  p must be 32-byte aligned.
@@ -176,6 +178,12 @@ __device__ __forceinline__ TraceAccel resolve_tlas(const void *tlas_result, uint
     return a;
 }
 
+#ifndef RT_PRIMARY_PHASES
+#define RT_PRIMARY_PHASES 0  // 1: trace_ray4 votes per iteration between a box step and a triangle step (see there)
+#endif
+#ifndef RT_PRIMARY_LEAF_THRESHOLD
+#define RT_PRIMARY_LEAF_THRESHOLD 8
+#endif
 #define RT_SENTINEL 0x7fffffffu  // never a valid internal index (indices are < 2^24)
 
 #ifndef RT_LDG256
@@ -271,19 +279,30 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
 // any-hit / opaque-flag handling: the caller's rays carry only cull flags (RayGen: CULL_BACK_FACING_TRIANGLES).
 __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
                                            float tmax, uint32_t rayFlags, uint32_t mask, uint32_t rayContribution, TraceHit &hit,
-                                           uint32_t *status) {
+                                           uint32_t *status, bool valid = true) {
     hit.prim = RT_NO_HIT;
     hit.t = tmax;
     hit.u = hit.v = 0.0f;
     hit.inst_index = hit.geom_index = hit.inst_id = hit.leaf_slot = hit.record = 0;
+#if RT_PRIMARY_PHASES
+    // Warp-synchronous variant: EVERY lane of the warp calls (valid = false for lanes without a ray) and the warp votes,
+    // per iteration, between a box step for the lanes at internal nodes and a triangle step for the lanes at leaves,
+    // instead of running both sides of the branch with complementary lane masks.
+    bool alive = valid && A.count != 0;
+#else
     if (A.count == 0) return false;
+#endif
     LocalStack stk;
     int sp = 0, blasBase = -1;
     float tCur = tmax;
     RayPre cur;
     ray_pre_box<true>(cur, ox, oy, oz, dx, dy, dz);
     float tUnused;
+#if RT_PRIMARY_PHASES
+    alive = alive && ray_box(tUnused, tCur, cur, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2]);
+#else
     if (!ray_box(tUnused, tCur, cur, A.root_c[0], A.root_c[1], A.root_c[2], A.root_h[0], A.root_h[1], A.root_h[2])) return false;
+#endif
     const bool plain = [&] {
         const float v[6] = {ox, oy, oz, dx, dy, dz};
         bool p = true;
@@ -300,8 +319,19 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
     uint32_t instIndex = 0, instOffset = 0, instId = 0;
     int cull = 0;
     uint32_t ref = A.root_ref;
+#if RT_PRIMARY_PHASES
+    while (true) {
+        const unsigned aliveMask = __ballot_sync(0xffffffffu, alive);
+        if (aliveMask == 0) break;
+        const bool atLeaf = alive && (ref & RT_NODE_LEAF_FLAG);
+        const unsigned leafMask = __ballot_sync(0xffffffffu, atLeaf);
+        const bool leafPhase = (aliveMask & ~leafMask) == 0 || __popc(leafMask) >= RT_PRIMARY_LEAF_THRESHOLD;
+        if (leafPhase ? !atLeaf : (!alive || atLeaf)) continue;  // lanes of the other kind wait for their phase
+        if (leafPhase) {
+#else
     while (true) {
         if (ref & RT_NODE_LEAF_FLAG) {
+#endif
             const uint32_t slot = ref & 0x00ffffffu;
             ref = RT_SENTINEL;
             if (!bottom) {
@@ -368,7 +398,11 @@ __device__ __forceinline__ bool trace_ray4(const TraceAccel &A, float ox, float 
                 ref = stk.ref[sp];
                 break;
             }
+#if RT_PRIMARY_PHASES
+            if (done) alive = false;
+#else
             if (done) break;
+#endif
         }
     }
     return hit.prim != RT_NO_HIT;

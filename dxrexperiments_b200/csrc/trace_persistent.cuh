@@ -25,7 +25,10 @@
 #define RT_LEAF_THRESHOLD 4
 #endif
 #ifndef RT_INT_UNROLL
-#define RT_INT_UNROLL 1  // internal-node steps per phase selection
+#define RT_INT_UNROLL 2  // internal-node steps per phase selection (A/B on C2 / C1M: 2 = +3.8 / +4.4 % on incoherent rays, +5.3 / +2.9 % on shadow rays; 3 and 4 lose again)
+#endif
+#ifndef RT_LEAF_UNROLL
+#define RT_LEAF_UNROLL 1  // leaf steps per phase selection
 #endif
 constexpr int kFetchThreshold = RT_FETCH_THRESHOLD;  // refill when >= this many lanes are idle
 constexpr int kLeafThreshold = RT_LEAF_THRESHOLD;    // run a leaf phase when >= this many lanes hold a leaf
@@ -142,6 +145,23 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
         alive = false;
     };
 
+    auto pop = [&]() {  // a lane whose subtree is exhausted takes the next node from its stack (or finishes)
+        if (alive && ref == RT_SENTINEL) {
+            if (sp == 0) {
+                finish();
+            } else {
+                if (bottom && sp == blasBase) {  // leaving the BLAS: back to the world-space ray (boxes only up there)
+                    bottom = false;
+                    if (!sameSpace) ray_pre_box<true>(cur, wox, woy, woz, wdx, wdy, wdz);
+                    nodes = topNodes;
+                    blasBase = -1;
+                }
+                --sp;
+                ref = stk.at(sp);
+            }
+        }
+    };
+
     for (;;) {
         // ------------------------------------------------------------------ fetch
         const unsigned aliveMask = __ballot_sync(FULL, alive);
@@ -197,7 +217,11 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
         const unsigned intMask = aliveMask & ~leafMask;
         if (intMask == 0 || __popc(leafMask) >= kLeafThreshold) {
             // ---------------------------------------------------------------- leaf phase
-            if (atLeaf) {
+            // RT_LEAF_UNROLL > 1: a lane that pops straight into another leaf (the sibling triangle) tests it right away
+#pragma unroll
+            for (int lu = 0; lu < RT_LEAF_UNROLL; ++lu) {
+            if (lu > 0) pop();
+            if (alive && ref != RT_SENTINEL && (ref & RT_NODE_LEAF_FLAG) && (lu == 0 || bottom)) {
                 const uint32_t slot = ref & 0x00ffffffu;
                 ref = RT_SENTINEL;
                 if (!bottom) {
@@ -262,6 +286,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
                     }
                 }
             }
+            }
         } else {
             // ---------------------------------------------------------------- internal phase
             // RT_INT_UNROLL > 1: a lane whose step (or the pop after it) ends at another internal node takes the next
@@ -269,22 +294,7 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             // counts, branches) is ~25 warp instructions per iteration against ~120 for a step.
 #pragma unroll
             for (int u = 0; u < RT_INT_UNROLL; ++u) {
-                if (u > 0) {  // pop between the unrolled steps (the same code as below)
-                    if (alive && ref == RT_SENTINEL) {
-                        if (sp == 0) {
-                            finish();
-                        } else {
-                            if (bottom && sp == blasBase) {
-                                bottom = false;
-                                if (!sameSpace) ray_pre_box<true>(cur, wox, woy, woz, wdx, wdy, wdz);
-                                nodes = topNodes;
-                                blasBase = -1;
-                            }
-                            --sp;
-                            ref = stk.at(sp);
-                        }
-                    }
-                }
+                if (u > 0) pop();
                 if (alive && ref != RT_SENTINEL && !(ref & RT_NODE_LEAF_FLAG)) {
 #if RT_PERSIST_WIDE4
                     // one 128-byte node = four child boxes (two BVH2 levels per dependent fetch)
@@ -311,22 +321,6 @@ k_trace_persistent(const void *tlas, const rt_ray *rays, const uint32_t *count, 
             }
         }
         // ------------------------------------------------------------------ pop
-        if (alive && ref == RT_SENTINEL) {
-            for (;;) {
-                if (sp == 0) {
-                    finish();
-                    break;
-                }
-                if (bottom && sp == blasBase) {  // leaving the BLAS: back to the world-space ray (boxes only up there)
-                    bottom = false;
-                    if (!sameSpace) ray_pre_box<true>(cur, wox, woy, woz, wdx, wdy, wdz);
-                    nodes = topNodes;
-                    blasBase = -1;
-                }
-                --sp;
-                ref = stk.at(sp);
-                break;
-            }
-        }
+        pop();
     }
 }
