@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(256) k_find_treelets(uint32_t n, const rt_hier
 // `local` (may be null): the per-node "subtree lies in one fit block" flags of k_hierarchy.  Re-forming a treelet
 // whose root is not local can move leaves from outside the block under one of its inner nodes, so those nodes lose the
 // flag; a treelet under a local root only permutes nodes and leaves of that block, and the flags stay true.
-__global__ void __launch_bounds__(32 * kWarps) k_treelet_reorder(uint32_t n, rt_hierarchy_node *hier, uint32_t *num_tris,
+#ifndef RT_TREELET_MINBLOCKS
+#define RT_TREELET_MINBLOCKS 12  // resident blocks per SM the register budget is set for: 40 registers, 48 warps per SM (A/B at 10 M triangles, one pass: 1 -> 10.68 ms, 10 -> 10.44, 12 -> 9.97, 16 -> 11.31)
+#endif
+__global__ void __launch_bounds__(32 * kWarps, RT_TREELET_MINBLOCKS) k_treelet_reorder(uint32_t n, rt_hierarchy_node *hier, uint32_t *num_tris,
                                                                  float *aabbs, const uint32_t *base, uint8_t *local) {
     __shared__ float s_cost[kWarps][kSubsets];
     __shared__ float s_box[kWarps][kFull][6];
