@@ -54,6 +54,13 @@ struct RayPre {  // GetRayData: TraverseFunction.hlsli:438-460
 // Component k of (x, y, z) as two select instructions.  Written as the nested conditional `k == 0 ? x : (k == 1 ? y : z)`
 // nvcc 12.9 emits a BRANCH per pick (BSSY / ISETP / BRA / MOV / BSYNC): ncu attributed 31 % of the closest-hit kernel's warp
 // instructions to the nine picks of the watertight triangle test, executed at 7-8 lanes.
+#ifndef RT_PUSH_BRANCHFREE
+#define RT_PUSH_BRANCHFREE 0  // 1: wide4_step stores every candidate and lets the stack pointer keep it or not, no branches.  Measured: the
+                              // unconditional local-memory stores cost far more than the branches (C2 primary 6744 -> 5570, incoherent 4816 -> 4436)
+#endif
+#ifndef RT_TRIANGLE_BRANCHFREE
+#define RT_TRIANGLE_BRANCHFREE 1  // 0: the reference's chain of early exits (A/B on C2: incoherent 4739 -> 4816, shadow 5242 -> 5280 Mrays/s)
+#endif
 #ifndef RT_PICK_SELP
 #define RT_PICK_SELP 1  // 0: the nested conditional (A/B)
 #endif
@@ -146,6 +153,22 @@ __device__ __forceinline__ bool ray_triangle(float &hitT, float &bu, float &bv, 
     float V = sub_(mul_(Ax, Cy), mul_(Ay, Cx));
     float W = sub_(mul_(Bx, Ay), mul_(By, Ax));
     float det = add_(add_(U, V), W);
+#if RT_TRIANGLE_BRANCHFREE
+    // The reference's early exits (:236-262) as ONE exit: a lane that leaves early only waits for the other lanes of its
+    // warp, and every exit costs a convergence barrier.  min / max of (U, V, W) give "some edge function is negative /
+    // positive" with the comparisons' own NaN behaviour (fminf / fmaxf return the non-NaN operand).
+    const bool anyNeg = fminf(fminf(U, V), W) < 0.0f, anyPos = fmaxf(fmaxf(U, V), W) > 0.0f;
+    bool bad = cull == 2 ? anyPos : (cull == 1 ? anyNeg : (anyNeg && anyPos));
+    bad = bad || det == 0.0f;
+    Az = mul_(r.sz, Az), Bz = mul_(r.sz, Bz), Cz = mul_(r.sz, Cz);
+    const float T = add_(add_(mul_(U, Az), mul_(V, Bz)), mul_(W, Cz));
+    const float hd = mul_(hitT, det), had = mul_(hitT, fabsf(det));
+    float sT = fabsf(T);
+    if ((T > 0.0f) != (det > 0.0f)) sT = -sT;
+    const bool bad2 = T > 0.0f || T < hd, bad1 = T < 0.0f || T > hd, bad0 = sT < 0.0f || sT > had;
+    bad = bad || (cull == 2 ? bad2 : (cull == 1 ? bad1 : bad0));
+    if (bad) return false;
+#else
     if (cull == 2) {
         if (U > 0.0f || V > 0.0f || W > 0.0f) return false;
     } else if (cull == 1) {
@@ -165,6 +188,7 @@ __device__ __forceinline__ bool ray_triangle(float &hitT, float &bu, float &bv, 
         if ((T > 0.0f) != (det > 0.0f)) s = -s;
         if (s < 0.0f || s > mul_(hitT, fabsf(det))) return false;
     }
+#endif
     float rcpDet = div_(1.0f, det);
     bu = mul_(V, rcpDet);
     bv = mul_(W, rcpDet);
@@ -215,9 +239,15 @@ __device__ __forceinline__ void key_cas(uint32_t &a, uint32_t &b) {
     const uint32_t lo = min(a, b), hi = max(a, b);
     a = lo, b = hi;
 }
+// a ? x : y as ONE select instruction (nvcc turns some of these conditionals into branches, see pick())
+__device__ __forceinline__ uint32_t select_u32(uint32_t cond, uint32_t x, uint32_t y) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.u32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(x), "r"(y), "r"(cond));
+    return r;
+}
 __device__ __forceinline__ uint32_t ref_of(uint32_t key, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-    const uint32_t lo = (key & 1u) ? r1 : r0, hi = (key & 1u) ? r3 : r2;
-    return (key & 2u) ? hi : lo;
+    const uint32_t lo = select_u32(key & 1u, r1, r0), hi = select_u32(key & 1u, r3, r2);
+    return select_u32(key & 2u, hi, lo);
 }
 
 // One internal step over a 4-wide node: test the four child boxes (RayBoxTest arithmetic unchanged), order the
@@ -234,6 +264,8 @@ struct LocalStack {
     uint32_t ref[RT_STACK_SIZE], key[RT_STACK_SIZE];
     __device__ __forceinline__ bool room(int sp, int n) const { return sp + n <= RT_STACK_SIZE; }
     __device__ __forceinline__ void push(int &sp, uint32_t r, uint32_t k) { ref[sp] = r, key[sp] = k, ++sp; }
+    // store always, keep the slot only if `keep`: no branch (the caller has checked room())
+    __device__ __forceinline__ void push_if(int &sp, uint32_t r, uint32_t k, bool keep) { ref[sp] = r, key[sp] = k, sp += keep ? 1 : 0; }
 };
 
 template <bool WITH_T, bool SORTED = true, class S>
@@ -259,6 +291,20 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
         uint32_t first = RT_SENTINEL;
         const bool v[4] = {b0, b1, b2 && r2 != RT_WIDE4_EMPTY, b3 && r3 != RT_WIDE4_EMPTY};
         const uint32_t r[4] = {r0, r1, r2, r3};
+#if RT_PUSH_BRANCHFREE
+        // Hits leave in slot order: the lowest hit slot is visited next, the others are pushed highest first.  Written
+        // without branches: every candidate is STORED at the top of the stack and the stack pointer keeps it or not
+        // (the nested conditionals were 8 % of the shadow kernel's warp instructions, most of them convergence barriers).
+        if (stk.room(sp, 3)) {
+            first = select_u32(v[3], r[3], first);
+#pragma unroll
+            for (int k = 2; k >= 0; --k) {
+                stk.push_if(sp, first, 0u, v[k] && first != RT_SENTINEL);
+                first = select_u32(v[k], r[k], first);
+            }
+            return first;
+        }
+#endif
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             if (v[k]) {
@@ -278,6 +324,14 @@ __device__ __forceinline__ uint32_t wide4_step(const rt_wide4_node *nodes, uint3
              k3 = hit_key(b3 && r3 != RT_WIDE4_EMPTY, t3, 3);
     key_cas(k0, k1), key_cas(k2, k3), key_cas(k0, k2), key_cas(k1, k3), key_cas(k1, k2);
     if (k0 == 0xffffffffu) return RT_SENTINEL;
+#if RT_PUSH_BRANCHFREE
+    if (stk.room(sp, 3)) {  // the other hits, farthest first: stored unconditionally, kept if they are hits
+        stk.push_if(sp, ref_of(k3, r0, r1, r2, r3), k3, k3 != 0xffffffffu);
+        stk.push_if(sp, ref_of(k2, r0, r1, r2, r3), k2, k2 != 0xffffffffu);
+        stk.push_if(sp, ref_of(k1, r0, r1, r2, r3), k1, k1 != 0xffffffffu);
+        return ref_of(k0, r0, r1, r2, r3);
+    }
+#endif
     if (k1 != 0xffffffffu) {  // push the other hits, farthest first
         if (!stk.room(sp, 3)) {
             atomicOr(status, 1u);

@@ -71,10 +71,14 @@ struct PersistStack {
         else lm[sp - RT_SMEM_STACK] = r;
         ++sp;
     }
+    __device__ __forceinline__ void push_if(int &sp, uint32_t r, uint32_t k, bool keep) {
+        if (keep) push(sp, r, k);
+    }
     __device__ __forceinline__ uint32_t at(int sp) const { return sp < RT_SMEM_STACK ? sm[sp * kPersistThreads] : lm[sp - RT_SMEM_STACK]; }
 #else
     uint32_t lm[RT_STACK_SIZE];
     __device__ __forceinline__ void push(int &sp, uint32_t r, uint32_t) { lm[sp++] = r; }
+    __device__ __forceinline__ void push_if(int &sp, uint32_t r, uint32_t, bool keep) { lm[sp] = r, sp += keep ? 1 : 0; }
     __device__ __forceinline__ uint32_t at(int sp) const { return lm[sp]; }
 #endif
     __device__ __forceinline__ bool room(int sp, int n) const { return sp + n <= RT_STACK_SIZE; }
