@@ -22,7 +22,8 @@
 #define RT_FETCH_THRESHOLD 24
 #endif
 #ifndef RT_LEAF_THRESHOLD
-#define RT_LEAF_THRESHOLD 4
+#define RT_LEAF_THRESHOLD 2  // re-tuned once the triangle test lost its branches (pick()): 4 -> 2 is +0 / +3 / +4 % on incoherent rays over
+                             // 82 k / 1.3 M / 5.2 M triangles and +0.5 / +3 / +5 % on shadow rays; 1 and 3 are worse
 #endif
 #ifndef RT_INT_UNROLL
 #define RT_INT_UNROLL 2  // internal-node steps per phase selection (A/B on C2 / C1M: 2 = +3.8 / +4.4 % on incoherent rays, +5.3 / +2.9 % on shadow rays; 3 and 4 lose again)
