@@ -58,7 +58,10 @@ typedef struct rt_scratch_layout {
     uint64_t morton_codes;   /* n x u32, load order                                  (FL/CalculateMortonCodes.hlsli) */
     uint64_t sorted_codes;   /* n x u32                                               (FL/BitonicSort.cpp)           */
     uint64_t sorted_indices; /* n x u32: sorted slot -> load-order primitive          (FL/BitonicSort.cpp)           */
-    uint64_t hierarchy;      /* (2n-1) x rt_hierarchy_node                            (FL/BuildBVHSplits.hlsli)      */
+    uint64_t hierarchy;      /* (2n-1) x rt_hierarchy_node                            (FL/BuildBVHSplits.hlsli)
+                                NOT produced by bottom-level builds with PREFER_FAST_BUILD and without ALLOW_UPDATE: those emit
+                                the hierarchy and fit the boxes in one bottom-up kernel; the child links of the blob's nodes
+                                carry the same topology                                                                  */
     uint64_t primitives;     /* BLAS: n x 48-byte load-order records {float v[9]; u32 primitiveIndex, geometryIndex,
                                 geometryFlags} = Primitive + PrimitiveMetaData of FL/BottomLevelLoadTriangles.hlsli      */
     uint64_t metadata;       /* same offset as `primitives` (the metadata lives in the same records)                  */
