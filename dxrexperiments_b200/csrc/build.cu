@@ -296,9 +296,10 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_radix_scatter(const uint32_
             unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
             for (int b = 0; b < kRadixBits; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const unsigned m = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? m : ~m;
+                // all ones where this lane's digit has bit b: peers &= bit ? m : ~m becomes ONE three-input logic op
+                const uint32_t sel = uint32_t(int32_t(d << (31 - b)) >> 31);
+                const unsigned m = __ballot_sync(0xffffffffu, sel != 0u);
+                peers &= ~(m ^ sel);
             }
             // The group's first lane bumps the warp's counter with ONE shared-memory atomic.  Its result is not used
             // before the loop ends, so the eight items' ballots and atomics pipeline (a load -> store -> shuffle chain
@@ -970,9 +971,9 @@ __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hie
                                                         rt_wide_node *wide, rt_wide4_node *wide4, rt_ext_header *ext,
                                                         const uint32_t *exit_nodes, const uint16_t *exit_sizes) {
     const uint32_t nInternal = n - 1;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= __ldcg(&counters[nInternal])) return;
+    const uint32_t entries = __ldcg(&counters[nInternal]);
     const uint32_t *hw = reinterpret_cast<const uint32_t *>(hier);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < entries; i += gridDim.x * blockDim.x) {  // grid: see k_lbvh_exits
     uint32_t node = exit_nodes[i];
     uint32_t count = exit_sizes[i];
     Box box = load_node_box(nodes, node);
@@ -981,15 +982,16 @@ __global__ void __launch_bounds__(kThreads) k_fit_exits(uint32_t n, const rt_hie
         const uint32_t l = __ldg(hw + 3 * size_t(parent) + 1), r = __ldg(hw + 3 * size_t(parent) + 2);
         __threadfence();
         const uint32_t other = atomicAdd(&counters[parent], count);
-        if (other == 0) return;  // first to arrive: the sibling will fit the parent
+        if (other == 0) break;  // first to arrive: the sibling will fit the parent
         __threadfence();
         const bool isLeft = (l == node);
         const Box sb = load_node_box(nodes, isLeft ? r : l);
         fit_merge_store<true>(parent, l, r, isLeft ? count : other, isLeft ? other : count, isLeft ? box : sb, isLeft ? sb : box, nInternal,
                               nodes, wide, ext, box, wide4);
-        if (parent == 0) return;
+        if (parent == 0) break;
         count += other;
         node = parent;
+    }
     }
 }
 
@@ -1269,8 +1271,10 @@ __global__ void __launch_bounds__(kThreads) k_lbvh_exits(uint32_t n, const uint3
                                                          const uint32_t *exit_count, const uint32_t *exit_nodes, const uint32_t *exit_lo,
                                                          const uint32_t *exit_hi) {
     const uint32_t nInternal = n - 1;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= __ldcg(exit_count)) return;
+    // The list holds a few entries per fit block (~8 of 256 slots); the grid is sized for one entry per 8 leaves and strides
+    // over longer lists.  (One thread per LEAF meant 39 000 blocks at 10 M triangles of which 1 200 had work.)
+    const uint32_t count = __ldcg(exit_count);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     uint32_t node = exit_nodes[i], lo = exit_lo[i], hi = exit_hi[i];
     Box box = load_node_box(nodes, node);
     bool goRight = lbvh_delta(codes, n, hi) > lbvh_delta(codes, n, lo - 1);
@@ -1279,7 +1283,7 @@ __global__ void __launch_bounds__(kThreads) k_lbvh_exits(uint32_t n, const uint3
         const unsigned long long mine = (static_cast<unsigned long long>(goRight ? lo : hi) << 32) | (node + 1u);
         __threadfence();
         const unsigned long long other = atomicExch(g_slot + split, mine);
-        if (other == 0ull) return;  // first to arrive: the sibling will fit the parent
+        if (other == 0ull) break;  // first to arrive: the sibling will fit the parent
         __threadfence();
         const uint32_t sib = uint32_t(other) - 1u, far = uint32_t(other >> 32);
         const Box sb = load_node_box(nodes, sib);
@@ -1294,8 +1298,9 @@ __global__ void __launch_bounds__(kThreads) k_lbvh_exits(uint32_t n, const uint3
         // Karras order: the child on the lower slots is "left"; fit_merge_store applies the size rule
         fit_merge_store<true>(id, goRight ? node : sib, goRight ? sib : node, split - nlo + 1, nhi - split, goRight ? box : sb,
                               goRight ? sb : box, nInternal, nodes, wide, ext, box, wide4);
-        if (root) return;
+        if (root) break;
         node = id, lo = nlo, hi = nhi, goRight = up;
+    }
     }
 }
 
@@ -1814,7 +1819,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
         k_lbvh_fit<<<rt_div_up(n, kFitBlock), kFitBlock, kFitLocalDynSmem, st>>>(n, codes_sorted, nodes, packed, wide, wide4, ext,
                                                                                  exit_count, exit_nodes, exit_lo, counters);
         if (n > kFitBlock) {  // a build of one block leaves no exits
-            k_lbvh_exits<<<grid, kThreads, 0, st>>>(n, codes_sorted, g_slot, nodes, wide, wide4, ext, exit_count, exit_nodes, exit_lo, counters);
+            k_lbvh_exits<<<std::max(1, rt_div_up(n / 8, kThreads)), kThreads, 0, st>>>(n, codes_sorted, g_slot, nodes, wide, wide4, ext, exit_count, exit_nodes, exit_lo, counters);
             ctx->launches++;
         }
         fitted_locally = true;
@@ -1839,7 +1844,7 @@ static int build_common(rt_context *ctx, uint32_t n, bool top, uint32_t flags, u
             fitted_locally = true;
             if (n > 1) {
                 // every block leaves at least one and on average ~log2(kFitBlock) entries; n bounds it
-                k_fit_exits<<<grid, kThreads, 0, st>>>(n, hier, counters, nodes, wide, reinterpret_cast<rt_wide4_node *>(result + R.wide4), ext,
+                k_fit_exits<<<std::max(1, rt_div_up(n / 4, kThreads)), kThreads, 0, st>>>(n, hier, counters, nodes, wide, reinterpret_cast<rt_wide4_node *>(result + R.wide4), ext,
                                                        exit_nodes, exit_sizes);
                 ctx->launches++;
             }
