@@ -645,5 +645,19 @@ class Renderer:
             x0, y0, x1, y1 = region
             check(lib.rt_dispatch_rays_region(self.ctx.handle, self.program.handle, self.width, self.height, x0, y0, x1, y1))
 
+    def realtime_band(self, frame: T.PerFrameConstants, band, params: T.DenoiserParams, tmp: "Buffer", final: "Buffer"):
+        """One rank's share of a realtime frame sharded by row bands (sharding.band_plan): render rows [r0, r1) of the two
+        AOVs, run DenoiseCompositor on exactly those rows, and leave only the core rows [y0, y1) in `final` (a full-size,
+        initially zero RGBA32F buffer) — the sum of the ranks' `final` buffers (rt_accum_reduce, weight 1) is the frame."""
+        self.dispatch(frame, region=(0, band.r0, self.width, band.r1))
+        row = 16 * self.width
+        off = band.r0 * row
+        check(lib.rt_denoise(self.ctx.handle, self.out[0].ptr + off, self.out[1].ptr + off, tmp.ptr + off, final.ptr + off,
+                             self.width, band.r1 - band.r0, C.byref(params)))
+        if band.y0 > band.r0:
+            check(lib.rt_memset(self.ctx.handle, final.ptr + off, 0, (band.y0 - band.r0) * row))
+        if band.r1 > band.y1:
+            check(lib.rt_memset(self.ctx.handle, final.ptr + band.y1 * row, 0, (band.r1 - band.y1) * row))
+
     def image(self, slot=0) -> np.ndarray:
         return self.out[slot].download(np.float32).reshape(self.height, self.width, 4)

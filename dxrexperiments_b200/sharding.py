@@ -86,3 +86,28 @@ def tiles_for_rank(rank: int, world: int, width: int, height: int, tile: int = 6
                 out.append((x0, y0, min(x0 + tile, width), min(y0 + tile, height)))
             k += 1
     return out
+
+
+@dataclass
+class BandPlan:
+    """Realtime frame (RealtimeRaytracingPipeline + DenoiseCompositor) sharded by contiguous row bands."""
+    rank: int
+    world: int
+    y0: int   # core rows [y0, y1): what this rank contributes to the composited frame
+    y1: int
+    r0: int   # rows [r0, r1) this rank renders and filters: the core plus the filter's reach on both sides
+    r1: int
+
+
+def band_plan(rank: int, world: int, height: int, halo: int) -> BandPlan:
+    """Rank `rank` of `world` owns rows [y0, y1) of a `height`-row frame and renders / denoises `halo` more rows on each
+    side (clipped at the image border): the separable bilateral filter reaches maxKernelSize rows up and down
+    (BilateralFilter.hlsli:92-115), so with halo >= maxKernelSize the core rows of a band's filter output are the rows
+    the full-frame filter produces, bit for bit.  The core bands partition the frame; a rank's buffer is zero outside
+    its core, so the weight-1 sum of rt_accum_reduce composites the frame."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    if height <= 0 or halo < 0:
+        raise ValueError("height must be positive and halo non-negative")
+    y0, y1 = height * rank // world, height * (rank + 1) // world
+    return BandPlan(rank, world, y0, y1, max(0, y0 - halo), min(height, y1 + halo))

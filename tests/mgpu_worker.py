@@ -29,6 +29,8 @@ def main():
     setup = scenes.FrameSetup(camera=scenes.BUNNY_CAMERA)
     env = scenes.sky_cube(16)
     jit = scenes.jitter_sequence(setup.seed, spp, W, H)
+    if os.environ.get("MGPU_MODE") == "realtime":
+        return realtime_bands(ctx, comm, rank, world, W, H, [mesh, ground], mats, env, setup, out_path)
     p = sharding.plan(rank, world, spp, strip_groups=strip_groups, strip_rows=16)
     r = rt.Renderer(ctx, [mesh, ground], [scenes.IDENTITY_3X4] * 2, mats, env, rt.PROGRESSIVE, W, H)
     for local, s in enumerate(p.samples):
@@ -52,6 +54,38 @@ def main():
                "nccl_version": comm.nccl_version(), "version": rt.lib.rt_version().decode()}
         with open(out_path, "w") as f:
             json.dump(res, f)
+    comm.close()
+    ctx.close()
+
+
+def realtime_bands(ctx, comm, rank, world, W, H, meshes, mats, env, setup, out_path):
+    """SURVEY 8e-ii: one realtime frame (1 spp AOVs + DenoiseCompositor) sharded by row bands with the filter's reach as halo;
+    the weight-1 rt_accum_reduce composites the bands on rank 0, which compares with the frame ONE GPU produces."""
+    from dxrexperiments_b200 import types as T
+    k = 12
+    prm = T.DenoiserParams(1.0, 2.2, 1, 0, k, 0)  # src/DenoiseCompositor.cpp:45-50
+    f = scenes.make_frame(setup, W, H, 0, 0, jitter=(0.2, -0.3))
+    band = sharding.band_plan(rank, world, H, halo=k)
+    r = rt.Renderer(ctx, meshes, [scenes.IDENTITY_3X4] * len(meshes), mats, env, rt.REALTIME, W, H)
+    tmp, final = ctx.alloc(16 * W * H).zero(), ctx.alloc(16 * W * H).zero()
+    r.realtime_band(f, band, prm, tmp, final)
+    count = W * H * 4
+    recv = ctx.alloc(4 * count).zero() if rank == 0 else None
+    comm.reduce(final.ptr, recv.ptr if recv else None, count, 1.0, root=0)
+    ctx.sync()
+    ctx.status()
+    if rank == 0:
+        got = recv.download(np.float32).reshape(H, W, 4)
+        single = rt.Renderer(ctx, meshes, [scenes.IDENTITY_3X4] * len(meshes), mats, env, rt.REALTIME, W, H)
+        single.dispatch(f)
+        ref, _ = ctx.denoise(single.image(0), single.image(1), prm)
+        a, b = got.astype(np.float64), ref.astype(np.float64)
+        res = {"world": world, "mode": "realtime row bands, halo 12", "rel_rmse": float(np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))),
+               "max_abs": float(np.abs(a - b).max()), "bit_identical": bool(np.array_equal(got, ref)), "mean": float(b[..., :3].mean()),
+               "alpha_min": float(got[..., 3].min()), "alpha_max": float(got[..., 3].max()), "strip_groups": 0, "spp": 1,
+               "nccl_version": comm.nccl_version(), "version": rt.lib.rt_version().decode()}
+        with open(out_path, "w") as fh:
+            json.dump(res, fh)
     comm.close()
     ctx.close()
 

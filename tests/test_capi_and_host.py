@@ -137,6 +137,14 @@ def test_sharding_plans():
             wsum[rows] += pl.weight
         assert (hits == 1).all(), (world, spp, groups)
         np.testing.assert_allclose(wsum, 1.0, rtol=1e-12)
+    # realtime row bands: the cores partition the frame, the rendered rows add the filter's reach, clipped at the border
+    for world, h, halo in ((1, 37, 12), (2, 1080, 12), (3, 203, 20), (8, 2160, 12), (5, 7, 3)):
+        bands = [sharding.band_plan(r, world, h, halo) for r in range(world)]
+        assert bands[0].y0 == 0 and bands[-1].y1 == h and all(a.y1 == b.y0 for a, b in zip(bands, bands[1:]))
+        for b in bands:
+            assert b.r0 == max(0, b.y0 - halo) and b.r1 == min(h, b.y1 + halo) and b.r0 <= b.y0 <= b.y1 <= b.r1
+    with pytest.raises(ValueError):
+        sharding.band_plan(2, 2, 100, 12)
     assert sharding.default_strip_groups(8, 64) == 1 and sharding.default_strip_groups(8, 2) == 4 and sharding.default_strip_groups(8, 1) == 8
     with pytest.raises(ValueError):
         sharding.plan(0, 4, 8, strip_groups=3)

@@ -64,6 +64,42 @@ def test_interleaved_dispatch_rejects_bad_arguments(ctx, rt):
             r.dispatch(f, strips=bad)
 
 
+def _run_ranks(tmp_path, world, strip_groups, spp, mode="progressive"):
+    n = _gpu_count()
+    if n < world:
+        pytest.skip(f"needs {world} GPUs, this box has {n}")
+    out, idf = tmp_path / "result.json", tmp_path / "nccl_id"
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MGPU_STRIP_GROUPS=str(strip_groups),
+                   MGPU_SPP=str(spp), MGPU_OUT=str(out), MGPU_ID_FILE=str(idf), MGPU_MODE=mode)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(o)
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    return json.load(open(out))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_realtime_row_bands_composited_by_the_reduce_equal_the_single_gpu_frame(tmp_path, world):
+    """realtime AOVs + DenoiseCompositor sharded by row bands (halo = the filter's reach), composited on rank 0
+    by the weight-1 rt_accum_reduce: x + 0 + ... + 0 is x, so the frame is the single-GPU frame bit for bit."""
+    res = _run_ranks(tmp_path, world, 0, 1, mode="realtime")
+    assert res["bit_identical"], res
+    assert abs(res["alpha_min"] - 1.0) < 1e-6 and abs(res["alpha_max"] - 1.0) < 1e-6, res
+    evidence = os.path.join(ROOT, "gpurun_out", f"mgpu_realtime_bands_w{world}.json")
+    os.makedirs(os.path.dirname(evidence), exist_ok=True)
+    json.dump(res, open(evidence, "w"))
+
+
 @pytest.mark.parametrize("world,strip_groups,spp", [(2, 1, 8), (2, 2, 4), (4, 2, 8), (8, 2, 16)])
 def test_nccl_reduced_frame_equals_single_gpu_frame(tmp_path, world, strip_groups, spp):
     n = _gpu_count()

@@ -117,6 +117,32 @@ def test_realtime_aovs_and_denoise_match_oracle(case_fn, w, h, ctx, rt, orc):
     np.testing.assert_allclose(gout, oout, rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("world,k", [(2, 12), (3, 12), (5, 20), (4, 3)])
+def test_realtime_frame_sharded_by_row_bands_equals_the_full_frame(world, k, ctx, rt):
+    """the realtime pipeline + DenoiseCompositor sharded by screen bands with the filter's reach as halo.  Every
+    "rank" renders rows [r0, r1) of the AOVs, filters exactly those rows and keeps its core rows; the sum of the ranks'
+    buffers (what rt_accum_reduce with weight 1 computes) is the full-frame result, bit for bit."""
+    from dxrexperiments_b200 import sharding
+    case = two_material_case()
+    w, h = 200, 123  # ragged against the tile sizes of both filter passes
+    f = scenes.make_frame(case.setup, w, h, 0, 0, jitter=(0.25, -0.15))
+    prm = T.DenoiserParams(1.0, 2.2, 1, 0, k, 0)
+    full = case.renderer(rt, ctx, rt.REALTIME, w, h)
+    full.dispatch(f)
+    ref, _ = ctx.denoise(full.image(0), full.image(1), prm)
+    total = np.zeros((h, w, 4), np.float32)
+    for rank in range(world):
+        band = sharding.band_plan(rank, world, h, halo=k)
+        r = case.renderer(rt, ctx, rt.REALTIME, w, h)
+        tmp, final = ctx.alloc(16 * w * h).zero(), ctx.alloc(16 * w * h).zero()
+        r.realtime_band(f, band, prm, tmp, final)
+        img = final.download(np.float32).reshape(h, w, 4)
+        assert not img[: band.y0].any() and not img[band.y1:].any()  # nothing outside the core rows
+        total += img
+    np.testing.assert_array_equal(total, ref)
+    ctx.status()
+
+
 @pytest.mark.parametrize("k,tonemap,gamma,dbg", [(12, 1, 0, 0), (1, 0, 0, 1), (20, 1, 1, 0), (25, 1, 0, 0), (7, 0, 1, 2), (5, 1, 0, 3)])
 @pytest.mark.parametrize("w,h", [(64, 64), (130, 71), (1922 // 8, 1126 // 8)])
 def test_denoise_parameters_and_ragged_sizes(k, tonemap, gamma, dbg, w, h, ctx, orc):
