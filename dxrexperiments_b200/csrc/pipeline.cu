@@ -255,7 +255,19 @@ __device__ __forceinline__ uint32_t octant_of(f3 d) {
     return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
 }
 
-__global__ void __launch_bounds__(kShadeThreads) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+// The shading kernels are latency-bound (ncu: long-scoreboard stalls, 41-47 % of the warp slots occupied at 52-64 registers): register
+// budgets for more resident blocks, small spills included, are worth 2.3 % of the C2 frame and 1.8 % of the 1.31 M-triangle frame
+// together (A/B: k_shade_primary 4 -> 5 blocks of 256, k_shade_secondary 8 -> 10 blocks of 128, k_resolve 9 -> 12 blocks of 128).
+#ifndef RT_SHADE0_MIN_BLOCKS
+#define RT_SHADE0_MIN_BLOCKS 5
+#endif
+#ifndef RT_SHADE1_MIN_BLOCKS
+#define RT_SHADE1_MIN_BLOCKS 10
+#endif
+#ifndef RT_RESOLVE_MIN_BLOCKS
+#define RT_RESOLVE_MIN_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(kShadeThreads, RT_SHADE0_MIN_BLOCKS) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
                                                                  uint32_t n_recs, const float *env, uint32_t envSize, float *out0,
                                                                  uint64_t pitch0, float *out1, uint64_t pitch1,
                                                                  unsigned long long *rayCounts, uint32_t *status) {
@@ -461,7 +473,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_queue(const void *tlas, const 
 // Depth-1 shade()/shadeAOV() of a secondary hit.  At depth 1 shootSecondaryRay returns 0 and shadow rays
 // are still traced (MAX_SHADOW_RAY_DEPTH 2); the Phong-lobe sample is still drawn (and its 0*brdf/pdf
 // term kept literally, so a zero pdf produces the same NaN as the shader).
-__global__ void __launch_bounds__(kBlock) k_shade_secondary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+__global__ void __launch_bounds__(kBlock, RT_SHADE1_MIN_BLOCKS) k_shade_secondary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
                                                             uint32_t n_recs, const float *env, uint32_t envSize,
                                                             unsigned long long *rayCounts, uint32_t *status) {
     const uint32_t cnt = ws.counters[0], n = cnt * 2;
@@ -631,7 +643,7 @@ __device__ __forceinline__ f3 secondary_radiance(const Launch &L, const WS &ws, 
     return (mk3(m.emissive[0], m.emissive[1], m.emissive[2]) * m.emissive[3] + albedo * diffuseComponent) + specTerm;
 }
 
-__global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs, float *out0,
+__global__ void __launch_bounds__(kBlock, RT_RESOLVE_MIN_BLOCKS) k_resolve(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs, float *out0,
                                                     uint64_t pitch0, float *out1, uint64_t pitch1) {
     const uint32_t n = ws.counters[0];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
