@@ -7,8 +7,10 @@
 //   * scene AABB is one fused pass (block reduce + ordered-int atomics) instead of ceil(log8 N) dispatches;
 //   * the O(log^2 N)-pass bitonic sort becomes a 4-pass stable LSD radix sort, which yields exactly the
 //     order BitonicSortCommon.hlsli:37-47 defines (ascending key, ties by ascending index);
-//   * the fit pass also emits this library's traversal section (64-byte nodes with both child boxes,
-//     48-byte triangles) so no separate packing pass re-reads the tree.
+//   * the fit pass also emits this library's traversal section (64-byte nodes with both child boxes, 128-byte
+//     4-wide nodes, 48-byte triangles) so no separate packing pass re-reads the tree;
+//   * a plain LBVH build (PREFER_FAST_BUILD: no treelet pass) emits the Karras hierarchy and fits the boxes in ONE
+//     bottom-up kernel (k_lbvh_fit / k_lbvh_exits): no binary searches, no hierarchy array.
 // This file is compiled with -fmad=false: every float op below is the IEEE operation written.
 #include <algorithm>
 #include <cfloat>
