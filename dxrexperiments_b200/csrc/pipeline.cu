@@ -256,18 +256,17 @@ __device__ __forceinline__ uint32_t octant_of(f3 d) {
 }
 
 // The shading kernels are latency-bound (ncu: long-scoreboard stalls, 41-47 % of the warp slots occupied at 52-64 registers): register
-// budgets for more resident blocks, small spills included, are worth 2.3 % of the C2 frame and 1.8 % of the 1.31 M-triangle frame
-// together (A/B: k_shade_primary 4 -> 5 blocks of 256, k_shade_secondary 8 -> 10 blocks of 128, k_resolve 9 -> 12 blocks of 128).
-#ifndef RT_SHADE0_MIN_BLOCKS
-#define RT_SHADE0_MIN_BLOCKS 5
-#endif
+// budgets for more resident blocks are worth ~1 % of a stage-timed frame (A/B: k_shade_secondary 8 -> 10 blocks of 128: 99.8 -> 94.4 us,
+// k_resolve 9 -> 12 blocks of 128: 61.5 -> 60.1 us; in the overlapped dispatch the gain hides behind the other band's traversal).
+// k_shade_primary stays at its natural 64 registers: 5 blocks of 256 (48 registers) spill 240 bytes per thread, +67 MB of DRAM
+// writes per frame, 138 -> 154 us under ncu.
 #ifndef RT_SHADE1_MIN_BLOCKS
 #define RT_SHADE1_MIN_BLOCKS 10
 #endif
 #ifndef RT_RESOLVE_MIN_BLOCKS
 #define RT_RESOLVE_MIN_BLOCKS 12
 #endif
-__global__ void __launch_bounds__(kShadeThreads, RT_SHADE0_MIN_BLOCKS) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
+__global__ void __launch_bounds__(kShadeThreads) k_shade_primary(const __grid_constant__ Launch L, WS ws, const rt_hit_record_dev *recs,
                                                                  uint32_t n_recs, const float *env, uint32_t envSize, float *out0,
                                                                  uint64_t pitch0, float *out1, uint64_t pitch1,
                                                                  unsigned long long *rayCounts, uint32_t *status) {
