@@ -197,6 +197,49 @@ def test_sample_sharded_accumulation_world2_gloo(tmp_path, strip_groups):
     assert "MAXREL" in r.stdout
 
 
+BAND_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import oracle
+from dxrexperiments_b200 import sharding, types as T
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+w, h, k = 61, 53, 12
+rng = np.random.Generator(np.random.PCG64(5))           # the same AOVs on every rank (a rank renders only its rows of them)
+direct = rng.random((h, w, 4), dtype=np.float32); direct[:, : w // 3, :3] *= 0.05
+spec = (rng.random((h, w, 4), dtype=np.float32) ** 3).astype(np.float32)
+prm = T.DenoiserParams(1.0, 2.2, 1, 0, k, 0)
+band = sharding.band_plan(rank, world, h, halo=k)
+out = oracle.denoise(direct[band.r0:band.r1], spec[band.r0:band.r1], prm)
+out = out[0] if isinstance(out, tuple) else out
+final = np.zeros((h, w, 4), np.float32)
+final[band.y0:band.y1] = out[band.y0 - band.r0: band.y1 - band.r0]  # the core rows only: halo rows are cleared
+t = torch.from_numpy(final)
+dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)                         # rt_accum_reduce with weight 1
+if rank == 0:
+    ref = oracle.denoise(direct, spec, prm)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    assert np.array_equal(t.numpy(), ref), float(np.abs(t.numpy() - ref).max())
+    print("BANDS_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_realtime_row_bands_world2_gloo(tmp_path):
+    """N > 1 host logic of the band-sharded realtime frame on CPU: two gloo ranks filter their band plus the filter's reach (the
+    oracle's DenoiseCompositor stands in for rt_denoise), keep their core rows and sum-reduce; rank 0 must hold the full-frame
+    filter output bit for bit."""
+    script = tmp_path / "band_worker.py"
+    script.write_text(BAND_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29733", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29733", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "BANDS_OK" in r.stdout
+
+
 def test_python_constants_match_the_c_header():
     """The ctypes mirror (dxrexperiments_b200/types.py) and include/rt_types.h must not drift apart: every enum value the
     Python side names is parsed out of the header and compared."""
