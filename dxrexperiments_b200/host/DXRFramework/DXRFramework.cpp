@@ -97,6 +97,12 @@ void RtContext::raytraceStrips(std::shared_ptr<RtBindings> bindings, std::shared
                   "rt_dispatch_rays_interleaved");
 }
 
+void RtContext::raytraceRegion(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height,
+                               uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    ThrowIfFalse(bindings && state && state->getProgram(), "raytraceRegion: bindings/state without a program");
+    ThrowIfFailed(rt_dispatch_rays_region(mCtx, state->getProgram()->getNative(), width, height, x0, y0, x1, y1), "rt_dispatch_rays_region");
+}
+
 void RtContext::traceRays(std::shared_ptr<RtProgram> program, std::shared_ptr<RtScene> scene, const rt_ray *rays, uint64_t n, uint32_t rayFlags,
                           uint32_t instanceMask, uint32_t rayContribution, uint32_t geometryMultiplier, rt_hit *hits) {
     ThrowIfFalse(program && scene && scene->getTlasWrappedPtr(), "traceRays: program / built scene");

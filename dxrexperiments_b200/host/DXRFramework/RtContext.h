@@ -55,6 +55,11 @@ public:
     void raytraceStrips(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height,
                         uint32_t stripRows, uint32_t groups, uint32_t group);
 
+    // A pixel rectangle [x0, x1) x [y0, y1) of the frame (rt_dispatch_rays_region): the row bands of a realtime frame
+    // sharded across GPUs render the rows their DenoiseCompositor pass needs.
+    void raytraceRegion(std::shared_ptr<RtBindings> bindings, std::shared_ptr<RtState> state, uint32_t width, uint32_t height,
+                        uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1);
+
     // TraceRay() with the program's hit groups honoured in full — any-hit and intersection shaders, procedural
     // primitives, every ray flag (FL/TraverseFunction.hlsli:520-799) — for `n` caller-supplied rays (host arrays).
     // Record of a candidate = rayContribution + geometryIndex * geometryMultiplier + InstanceContributionToHitGroupIndex

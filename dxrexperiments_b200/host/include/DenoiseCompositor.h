@@ -17,6 +17,8 @@ public:
         uint64_t indirectSpecularSrv;
     };
     void dispatch(InputComponents inputs, UINT frameIndex, UINT width, UINT height);
+    // one rank's row band of a frame sharded across GPUs: filters rows [row0, row1), keeps rows [core0, core1) (Pipelines.cpp)
+    void dispatchBand(InputComponents inputs, UINT width, UINT height, UINT row0, UINT row1, UINT core0, UINT core1);
 
     // loadMockResources: the reference loads assets/textures/{DirectLighting,IndirectSpecular}.PNG
     // (src/DenoiseCompositor.cpp:52-70); here the mock inputs are set with setMockResources().

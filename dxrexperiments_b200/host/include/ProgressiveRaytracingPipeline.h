@@ -28,6 +28,9 @@ public:
     // sample s as a single GPU would (update() takes its jitter from a sequential generator, :191-193).
     void setStripShard(UINT stripRows, UINT groups, UINT group) { mStripRows = stripRows, mStripGroups = groups, mStripGroup = group; }
     void skipFrame() { (void)mRngDist(mRng), (void)mRngDist(mRng); }
+    // setRowBand: render() covers image rows [row0, row1) only (RtContext::raytraceRegion) — the band of a realtime frame
+    // this rank renders and filters (its core rows plus the filter's reach, DenoiseCompositor::dispatchBand).
+    void setRowBand(UINT row0, UINT row1) { mBandRow0 = row0, mBandRow1 = row1; }
     // MAX_RADIANCE_RAY_DEPTH (1 in the reference's shaders; 2 = one more Phong-lobe bounce) and emulation of the
     // R16G16B16A16_FLOAT render targets createOutputResource() is asked for (rt_set_render_options); applied by render().
     void setRenderOptions(UINT maxRadianceRayDepth, bool halfRenderTargets) { mRenderOptions = {maxRadianceRayDepth, halfRenderTargets ? 1u : 0u}; }
@@ -60,6 +63,7 @@ protected:
     DXRFramework::RtTexture::SharedPtr mEnvCube;
     bool mActive = true;
     UINT mStripRows = 32, mStripGroups = 1, mStripGroup = 0;
+    UINT mBandRow0 = 0, mBandRow1 = 0;  // row1 > row0: render only these rows
     rt_render_options mRenderOptions{1u, 0u};
     std::mt19937 mRng;
     std::uniform_real_distribution<float> mRngDist;

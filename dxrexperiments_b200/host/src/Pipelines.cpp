@@ -1,6 +1,7 @@
 // Pipelines.cpp — host side of the two ray-tracing pipelines and the denoise compositor, re-hosted on the C ABI.
 // Follows src/ProgressiveRaytracingPipeline.cpp:27-247, src/RealtimeRaytracingPipeline.cpp:27-235 and
 // src/DenoiseCompositor.cpp:15-148 of the reference (constants, update() arithmetic, record layout, dispatch order).
+#include <algorithm>
 #include <cmath>
 
 #include "../include/DenoiseCompositor.h"
@@ -158,7 +159,8 @@ void RaytracingPipelineBase::render(UINT /*frameIndex*/, UINT width, UINT height
     ThrowIfFailed(rt_set_tlas(ctx, mRtScene->getTlasWrappedPtr()), "rt_set_tlas");
     ThrowIfFailed(rt_set_render_options(ctx, &mRenderOptions), "rt_set_render_options");
 
-    if (mStripGroups > 1) mRtContext->raytraceStrips(mRtBindings, mRtState, width, height, mStripRows, mStripGroups, mStripGroup);
+    if (mBandRow1 > mBandRow0) mRtContext->raytraceRegion(mRtBindings, mRtState, width, height, 0, mBandRow0, width, std::min(mBandRow1, height));
+    else if (mStripGroups > 1) mRtContext->raytraceStrips(mRtBindings, mRtState, width, height, mStripRows, mStripGroups, mStripGroup);
     else mRtContext->raytrace(mRtBindings, mRtState, width, height, 3);
     for (auto &o : mOutputResource) mRtContext->insertUAVBarrier(o);
 }
@@ -210,6 +212,27 @@ void DenoiseCompositor::setMockResources(RtBuffer::SharedPtr direct, RtBuffer::S
 
 void DenoiseCompositor::createOutputResource(DXGI_FORMAT, UINT width, UINT height) {
     for (auto &o : mOutputResource) o = mRtContext->createBuffer(uint64_t(width) * height * 16);
+}
+
+// Multi-GPU (the reference is single-GPU): filter image rows [row0, row1) only and keep the core rows
+// [core0, core1) of the result — the rest of the output stays / becomes zero, so that the weight-1 sum of the ranks' outputs
+// (RtContext::reduceAccumulation) is the frame.  With row0 <= core0 - maxKernelSize and row1 >= core1 + maxKernelSize
+// (clipped at the image border) the core rows are the rows dispatch() produces on the whole frame, bit for bit: the
+// filter reaches maxKernelSize rows up and down (BilateralFilter.hlsli:92-115).
+void DenoiseCompositor::dispatchBand(InputComponents inputs, UINT width, UINT height, UINT row0, UINT row1, UINT core0, UINT core1) {
+    ThrowIfFalse(inputs.directLightingSrv != 0 && inputs.indirectSpecularSrv != 0, "DenoiseCompositor::dispatchBand: no inputs");
+    ThrowIfFalse(mOutputResource[0] && mOutputResource[1], "DenoiseCompositor: createOutputResource was not called");
+    ThrowIfFalse(row0 <= core0 && core0 <= core1 && core1 <= row1 && row1 <= height && row0 < row1, "DenoiseCompositor::dispatchBand: rows");
+    rt_context *ctx = mRtContext->getNative();
+    const uint64_t row = uint64_t(width) * 4;  // floats per row
+    float *tmp = static_cast<float *>(mOutputResource[0]->ptr()), *out = static_cast<float *>(mOutputResource[1]->ptr());
+    ThrowIfFailed(rt_memset(ctx, out, 0, uint64_t(height) * row * 4), "rt_memset");
+    ThrowIfFailed(rt_denoise(ctx, reinterpret_cast<const float *>(inputs.directLightingSrv) + row0 * row,
+                             reinterpret_cast<const float *>(inputs.indirectSpecularSrv) + row0 * row, tmp + row0 * row, out + row0 * row, width,
+                             row1 - row0, &mConstantBuffer),
+                  "rt_denoise");
+    if (core0 > row0) ThrowIfFailed(rt_memset(ctx, out + row0 * row, 0, uint64_t(core0 - row0) * row * 4), "rt_memset");
+    if (row1 > core1) ThrowIfFailed(rt_memset(ctx, out + core1 * row, 0, uint64_t(row1 - core1) * row * 4), "rt_memset");
 }
 
 void DenoiseCompositor::dispatch(InputComponents inputs, UINT, UINT width, UINT height) {

@@ -71,7 +71,7 @@ static int usage() {
               "             [--spp N] [--seed S] [--no-jitter] [--eye x y z] [--at x y z] [--light-pos x y z] [--env-dds file | --env-raw file size]\n"
               "             [--out file.pfm] [--out2 file.pfm] [--denoise file.pfm] [--exr file.exr [--exr-half]] [--dump-frames file.bin] [--device N]\n"
               "             [--radiance-depth 1|2] [--fp16-targets] [--denoise-mock direct.pfm specular.pfm --denoise out.pfm [--kernel-size K]]\n"
-              "             [--world N --rank R --comm-file path [--strip-groups G] [--strip-rows 32]]   (one process per GPU)");
+              "             [--world N --rank R --comm-file path [--strip-groups G] [--strip-rows 32] [--band-shard]]   (one process per GPU)");
     return 0;
 }
 
@@ -180,7 +180,17 @@ int main(int argc, char **argv) {
         pipeline->loadResources(3);
         pipeline->createOutputResource(DXGI_FORMAT_R16G16B16A16_FLOAT, width, height);
         pipeline->setRenderOptions(UINT(a.num("radiance-depth", 1)), a.has("fp16-targets"));
-        if (stripGroups > 1) pipeline->setStripShard(UINT(a.num("strip-rows", 32)), stripGroups, stripGroup);
+        // --band-shard (realtime pipeline + --denoise, one frame): rank r renders AND filters its row band plus the filter's reach;
+        // the reduce composites the filtered bands instead of the AOVs (dxrexperiments_b200/sharding.py band_plan)
+        const bool bandShard = a.has("band-shard") && world > 1;
+        UINT core0 = 0, core1 = height, row0 = 0, row1 = height;
+        const UINT halo = 12;  // DenoiseCompositor's maxKernelSize (src/DenoiseCompositor.cpp:49)
+        if (bandShard) {
+            if (pipelineName != "realtime" || !a.has("denoise") || spp != 1) throw std::runtime_error("--band-shard needs --pipeline realtime --denoise --spp 1");
+            core0 = UINT(uint64_t(height) * rank / world), core1 = UINT(uint64_t(height) * (rank + 1) / world);
+            row0 = core0 > halo ? core0 - halo : 0, row1 = std::min(height, core1 + halo);
+            pipeline->setRowBand(row0, row1);
+        } else if (stripGroups > 1) pipeline->setStripShard(UINT(a.num("strip-rows", 32)), stripGroups, stripGroup);
 
         auto t0 = std::chrono::steady_clock::now();
         pipeline->buildAccelerationStructures();
@@ -192,7 +202,7 @@ int main(int argc, char **argv) {
         if (a.has("dump-frames")) frames.open(a.str("dump-frames", ""), std::ios::binary);
         UINT mySamples = 0;
         for (UINT f = 0; f < spp; ++f) {
-            if (f % sampleGroups != sampleGroup) {  // another sample group's frame: keep the jitter sequence in step
+            if (!bandShard && f % sampleGroups != sampleGroup) {  // another sample group's frame: keep the jitter sequence in step
                 pipeline->skipFrame();
                 continue;
             }
@@ -208,7 +218,17 @@ int main(int argc, char **argv) {
         // ---- the path's one collective: every output is summed onto rank 0, weighted by the rank's share of the samples
         std::vector<RtBuffer::SharedPtr> finalOut;
         for (int i = 0; i < pipeline->getNumOutputs(); ++i) finalOut.push_back(pipeline->getOutputResource(i));
-        if (world > 1) {
+        std::shared_ptr<DenoiseCompositor> bandDenoiser;
+        RtBuffer::SharedPtr bandFrame;
+        if (bandShard) {
+            bandDenoiser = DenoiseCompositor::create(context);
+            bandDenoiser->loadResources(3, false);
+            bandDenoiser->createOutputResource(DXGI_FORMAT_R16G16B16A16_FLOAT, width, height);
+            bandDenoiser->dispatchBand({finalOut[0]->gpuHandle(), finalOut[1]->gpuHandle()}, width, height, row0, row1, core0, core1);
+            const uint64_t floats = uint64_t(width) * height * 4;
+            bandFrame = rank == 0 ? context->createBuffer(floats * 4) : nullptr;
+            context->reduceAccumulation(bandDenoiser->getOutputResource(), bandFrame, floats, 1.0f, 0);
+        } else if (world > 1) {
             const uint64_t floats = uint64_t(width) * height * 4;
             for (size_t i = 0; i < finalOut.size(); ++i) {
                 RtBuffer::SharedPtr recv = rank == 0 ? context->createBuffer(floats * 4) : nullptr;
@@ -231,7 +251,9 @@ int main(int argc, char **argv) {
         if (a.has("out")) save(finalOut[0], a.str("out", ""));
         if (a.has("exr")) save(finalOut[0], a.str("exr", ""));
         if (a.has("out2") && finalOut.size() > 1) save(finalOut[1], a.str("out2", ""));
-        if (a.has("denoise") && rank == 0) {
+        if (bandShard) {
+            save(bandFrame, a.str("denoise", ""));
+        } else if (a.has("denoise") && rank == 0) {
             if (pipeline->getNumOutputs() < 2) throw std::runtime_error("--denoise needs --pipeline realtime");
             auto denoiser = DenoiseCompositor::create(context);
             denoiser->loadResources(3, false);

@@ -275,6 +275,30 @@ def test_headless_multi_gpu_frame_equals_single_gpu_frame(host_built, tmp_path, 
     assert info["world"] == world and info["strip_groups"] == strip_groups
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_headless_band_sharded_realtime_frame_equals_single_gpu_frame(host_built, tmp_path, world):
+    """--band-shard: every dxr_headless process renders AND filters its row band of a realtime frame (plus the filter's reach),
+    RtContext::reduceAccumulation composites the filtered bands with weight 1: the frame on rank 0 is the frame one GPU renders
+    and filters, bit for bit."""
+    try:
+        n = sum(1 for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.splitlines() if l.startswith("GPU "))
+    except Exception:
+        n = 0
+    if n < world:
+        pytest.skip(f"needs {world} GPUs, this box has {n}")
+    common = [EXE, "--scene", "cornell", "--pipeline", "realtime", "--width", "200", "--height", "123", "--spp", "1", "--seed", "5"]
+    single = tmp_path / "single.pfm"
+    r = subprocess.run(common + ["--denoise", str(single)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    multi, idf = tmp_path / "multi.pfm", tmp_path / "id"
+    procs = [subprocess.Popen(common + ["--denoise", str(multi), "--world", str(world), "--rank", str(k), "--comm-file", str(idf), "--band-shard"],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for k in range(world)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    np.testing.assert_array_equal(read_pfm(multi), read_pfm(single))
+
+
 def write_pfm(path, rgb):
     h, w = rgb.shape[:2]
     with open(path, "wb") as f:
